@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched SNAC simulator (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+A "step" is one pass of the hot path over the whole batch: every env of the vector env advances by
+one step (dmp_step: action in, observation/reward/done out).  Workload = BASELINE.json configs[2]:
+2D static dense plan, random-action rollouts, 1,048,576 envs in total, sharded over the ranks
+(one independent slice per GPU, no data-path collective; one NCCL all-reduce of the 4-double
+episode-statistics vector after the timed region).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (dim, dynamic, plan_choose, density, default total envs, B_alg bytes per env-step (f32 obs, step mode))
+    "1d_dynamic": (1, True, 0, "dense", 65536, 67),
+    "1d_static_step": (1, False, 2, None, 65536, 64),
+    "2d_static_dense": (2, False, 0, None, 1048576, 262),
+    "2d_dynamic_dense": (2, True, 0, "dense", 1048576, 268),
+    "3d_static_dense": (3, False, 0, None, 262144, 330),
+    "3d_dynamic_dense": (3, True, 0, "dense", 262144, 336),
+}
+METRIC = "env-steps/sec"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def load_plans_fixture(dim, density, split="train"):
+    import numpy as np
+    z = np.load(os.path.join(ROOT, "tests", "golden", "plans_packed.npz"))
+    if dim == 1:
+        return z["1d_%s" % split].astype(np.float64)
+    a = z["%dd_%s_%s" % (dim, density, split)]
+    bits = np.unpackbits(a, axis=1)[:, :400].reshape(len(a), 20, 20).astype(np.float64)
+    out = np.zeros((len(a), 26, 26))
+    out[:, 3:23, 3:23] = bits * (6.0 if dim == 3 else 1.0)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (NVML) -- runs during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port (python restatement of the reference algorithm), one process per core
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    wl, n_envs, n_steps, seed = args
+    import numpy as np
+    from oracle import dmp_oracle as O
+    dim, dynamic, plan_choose, density, _, _ = WORKLOADS[wl]
+    plans = load_plans_fixture(dim, density) if dynamic else None
+    envs = [O.make_env(dim, dynamic, plan_choose=plan_choose, plans=plans) for _ in range(n_envs)]
+    rng = np.random.RandomState(seed)
+    for e in envs:
+        e.reset(int(rng.randint(len(e.plans))))
+    A = O.SPEC[dim]["actions"]
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        acts = rng.randint(A, size=n_envs)
+        sizes = rng.randint(1, 4, size=n_envs)
+        for i, e in enumerate(envs):
+            _, _, d = e.step(int(acts[i]), int(sizes[i]))
+            if d:
+                e.reset(int(rng.randint(len(e.plans))))
+    return n_envs * n_steps, time.perf_counter() - t0
+
+
+def cpu_port_throughput(wl, n_envs_per_proc, n_steps, procs=None):
+    """Aggregate env-steps/s of the oracle port over `procs` processes (default: all usable cores)."""
+    import multiprocessing as mp
+    cores = procs or len(os.sched_getaffinity(0))
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(wl, n_envs_per_proc, n_steps, 1000 + i) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    return total / max(max(r[1] for r in res), 1e-9), cores, total, wall
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port, kind "port": the reference is Python
+    and cannot travel to the GPU box), all host cores, same metric/config; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    cores = len(os.sched_getaffinity(0))
+    # bounded sample: about 1.5 M env-steps per core in total (~20-30 s of python per core)
+    per_step = max(1, min(64, int(1.5e6 / max(args.steps + args.warmup, 1))))
+    cpu_port_throughput(wl, per_step, max(args.warmup, 1), cores)                   # warm-up (untimed)
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(wl, per_step, args.steps, 2000 + i) for i in range(cores)])
+    t = max(r[1] for r in res)
+    total = sum(r[0] for r in res)
+    value = total / t
+    sample = "%d procs x %d envs x %d steps of %s (python oracle port of the reference algorithm, reset on done)" % (
+        cores, per_step, args.steps, wl)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl, "envs_per_step": cores * per_step},
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from snac_b200.vecenv import BatchedDMPEnv
+
+    wl = args.workload
+    dim, dynamic, plan_choose, density, default_envs, b_alg = WORKLOADS[wl]
+    total_envs = args.envs or default_envs
+    n = total_envs // world                              # strong scaling: the batch is sharded
+    env = BatchedDMPEnv(dim, dynamic=dynamic, plan_choose=plan_choose,
+                        plans=load_plans_fixture(dim, density) if dynamic else None,
+                        num_envs=n, device=dev, auto_reset=True, env_base=rank * n,
+                        obs_dtype=torch.float32)
+    D, A = env.obs_dim, env.action_dim
+    K, W = args.steps, args.warmup
+
+    # rings: observations (rollout storage) sized past L2 so stores really go to HBM; actions pre-generated
+    obs_bytes = n * D * 4
+    R = min(256, max(2, -(-2 * L2_BYTES // obs_bytes)))
+    obs_ring = torch.empty((R, 1, n, D), dtype=torch.float32, device=dev)
+    rew_ring = torch.empty((R, 1, n), dtype=torch.float32, device=dev)
+    done_ring = torch.empty((R, 1, n), dtype=torch.uint8, device=dev)
+    RA = 16
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    act_ring = torch.randint(0, A, (RA, 1, n), dtype=torch.uint8, device=dev, generator=g)
+    env.reset()
+    torch.cuda.synchronize()
+
+    # one CUDA graph of G steps (G even: the device-resident Philox step counter alternates slots)
+    G = max(32, R + (R & 1))
+
+    def launch_step(i):
+        env.rollout(1, actions=act_ring[i % RA], out=(obs_ring[i % R], rew_ring[i % R], done_ring[i % R]),
+                    use_device_t=True, t_slot=i & 1)
+
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        for i in range(4):
+            launch_step(i)                                   # sets func attributes before capture
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for i in range(G):
+                launch_step(i)
+        n_replay_w = max(1, -(-W // G))
+        n_replay = max(1, -(-K // G))
+        K_eff = n_replay * G                                 # EXACT number of timed steps
+        for _ in range(n_replay_w):
+            graph.replay()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            e0.record(stream)
+            for _ in range(n_replay):
+                graph.replay()
+            e1.record(stream)
+            stream.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    stats = env.stats(allreduce=True).cpu().numpy()          # NCCL all-reduce of the 4-double stats vector
+    env.check_errors()
+    value = total_envs * K_eff / (ms * 1e-3)
+    per_gpu_steps_s = n * K_eff / (ms * 1e-3)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = per_gpu_steps_s * b_alg / 1e9
+
+    # ---- e2e: the reference-facing call with HOST buffers (actions in, obs/reward/done out) -------
+    from snac_b200.compat import HostStepper
+    hs = HostStepper(env)
+    Ke = max(4, min(K_eff, args.e2e_steps))
+    rng = np.random.RandomState(99 + rank)
+    host_actions = [rng.randint(0, A, size=n).astype(np.uint8) for _ in range(4)]
+    for i in range(3):
+        hs.step(host_actions[i % 4])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        o, r, d = hs.step(host_actions[i % 4])
+    torch.cuda.synchronize()
+    te = time.perf_counter() - t0
+    tt = torch.tensor([te], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    te = float(tt.item())
+    e2e = {"value": total_envs * Ke / te, "unit": "env-steps/s", "steps": Ke,
+           "h2d_bytes_per_step": int(hs.h2d_bytes) * world, "d2h_bytes_per_step": int(hs.d2h_bytes) * world,
+           "api": "HostStepper.step(actions: np.uint8[N]) -> (obs f32[N,%d], reward f32[N], done bool[N]) numpy, pinned" % D}
+
+    line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K_eff, "warmup": n_replay_w * G,
+            "ms_per_step": ms / K_eff, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 bit-grid / i32 counters, f32 observations", "data": "synthetic",
+            "config": {"workload": wl, "total_envs": total_envs, "envs_per_gpu": n, "mode": "step (1 launch per vector step, CUDA graph of %d)" % G,
+                       "actions": "uniform random over %d actions, pre-generated in HBM" % A,
+                       "step_size": "Philox4x32-10 in-kernel", "auto_reset": True,
+                       "l2": "obs ring of %d x %.1f MB (> 2 x L2) + state %.1f MB" % (R, obs_bytes / 1e6, n * 64 / 1e6),
+                       "parallelism": "env-sharded x%d, NCCL all-reduce of episode stats only" % world},
+            "clocks": clk.summary(),
+            "e2e": e2e, "gpu_launches": K_eff,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "k%dd_rollout<float> (K=1)" % dim,
+                         "bytes_per_env_step": b_alg, "envs_per_launch": n},
+            "episode_stats": {"sum_return": float(stats[0]), "sum_iou": float(stats[1]), "episodes": float(stats[2]),
+                              "steps": float(stats[3])}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, total, wall = cpu_port_throughput(wl, 16, 1500)
+        line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                "sample": "%d procs x 16 envs x 1500 steps of %s, python oracle port, reset on done (%.1f s wall)" % (cores, wl, wall)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2048)
+    ap.add_argument("--warmup", type=int, default=64)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="2d_static_dense", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="total envs over all GPUs (default: the BASELINE config's)")
+    ap.add_argument("--e2e-steps", type=int, default=48)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

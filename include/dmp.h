@@ -1,0 +1,204 @@
+/*
+ * dmp.h -- C ABI of libdmp.so, the B200 (sm_100a) batched simulator for SNAC's
+ * "deep mobile printing" (DMP) mobile-construction environments.
+ *
+ * The reference (ai4ce/SNAC) is pure Python and has NO FFI for this path; its boundary is the
+ * duck-type of the env classes.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference root).  A binding a reference maintainer would add
+ * is a ctypes stub -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer inside DmpState / DmpIO is a DEVICE pointer owned by the caller
+ *     (PyTorch tensors in this repo); the library never allocates, frees or synchronises;
+ *   - every launch goes on the caller's stream (`stream` is a cudaStream_t passed as void*);
+ *   - functions return DMP_OK or a DMP_E* code and never throw;
+ *   - envs are independent: entry points are thread-safe for distinct DmpState objects.
+ *
+ * State layout in HBM (structure-of-arrays, 128-bit accesses; n = n_envs)
+ *   1D  cells : uint4 [4][n]   32 x u16 per env: [0..29] column heights, [30] count_brick, [31] count_step
+ *       aux   : uint2 [n]      .x = pos | plan_idx << 16 ; .y = episode return so far (f32 bits)
+ *   2D  cells : uint4 [4][n]   16 x u32 per env: words 0..12 = 400 occupancy bits (bit r*20+c of the
+ *                              20x20 interior), word 13 = pos_row | pos_col << 8 | plan_idx << 16,
+ *                              word 14 = count_brick | count_step << 16, word 15 = episode return (f32)
+ *       aux   : unused (NULL)
+ *   3D  cells : u16 [n][400]   per-env contiguous 20x20 height map (row-major), 800 B, 16 B aligned
+ *       aux   : uint4 [n]      .x = pos_row | pos_col << 8 | plan_idx << 16 ; .y = count_brick | count_step << 16 ;
+ *                              .z = episode return (f32 bits) ; .w = reserved
+ *   positions are stored in the reference's padded coordinates (1D: 2..31, 2D/3D: 3..22).
+ * Plan tables (n_plans rows; static envs have exactly one row)
+ *   1D  plans : u8  [n_plans][32]    target heights (30 used)
+ *   2D  plans : u32 [n_plans][16]    400 plan bits in words 0..12 (same bit order as the grid)
+ *   3D  plans : u8  [n_plans][400]   target heights
+ *       plan_total : i32 [n_plans]   brick budget (the reference's total_brick, incl. 2D's floor of 30)
+ * Per-env episode statistics (updated on done when DMP_F_AUTORESET is set)
+ *   ep_cnt u32[n] episodes finished, ep_len u32[n] sum of their lengths,
+ *   ep_ret f64[n] sum of their returns, ep_iou f64[n] sum of their final IoUs
+ */
+#ifndef DMP_H_
+#define DMP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMP_ABI_VERSION 1
+
+/* return codes */
+#define DMP_OK       0
+#define DMP_EINVAL   1   /* bad argument (dim, obs kind, null pointer, K < 1, ...) */
+#define DMP_ECUDA    2   /* CUDA launch error; dmp_last_error() has the cudaError_t */
+
+/* observation element types */
+#define DMP_OBS_F32  0
+#define DMP_OBS_F64  1
+#define DMP_OBS_I16  2   /* raw counters only */
+
+/* DmpIO.flags */
+#define DMP_F_AUTORESET  1   /* on done: fold the episode into ep_* and reset the env in the same launch */
+#define DMP_F_NORMALISE  2   /* obs columns D-2, D-1 = count_brick/total_brick, count_step/total_step
+                                (the dynamic envs' format, e.g. Env/2D/DMP_Env_2D_dynamic_usedata_plan.py:64-65);
+                                computed as an IEEE fp64 division, then cast to the obs type. f32/f64 only */
+#define DMP_F_TSLOT1     4   /* read the step counter from t_dev[1] (see DmpState.t_dev) */
+
+/* DmpState.plan_mode: which plan an env gets when it auto-resets and DmpIO.next_plan is NULL */
+#define DMP_PLAN_PHILOX      0   /* random_choose_paln=True : counter-based draw                */
+#define DMP_PLAN_SEQUENTIAL  1   /* random_choose_paln=False: (plan_idx + 1) % n_plans            */
+#define DMP_PLAN_KEEP        2   /* keep the current plan (static envs)                           */
+
+/* DmpState.action_dist: distribution of in-kernel synthetic actions (DmpIO.actions == NULL) */
+#define DMP_ACT_UNIFORM  0
+#define DMP_ACT_REF3D    1   /* p = [.2,.2,.2,.2,.05,.05,.05,.05], Env/3D/DMP_simulator_3d_static_circle.py:361-362 */
+
+/* bits latched into *DmpState.err (device int32) */
+#define DMP_ERR_ACTION   1   /* action outside the env's action set (the reference raises UnboundLocalError,
+                                Env/1D/DMP_Env_1D_static.py:130-133) */
+#define DMP_ERR_STEPSIZE 2   /* injected step size outside {1,2,3} */
+#define DMP_ERR_PLANIDX  4   /* injected plan index outside [0, n_plans) */
+
+typedef struct DmpState {
+    int32_t  dim;          /* 1, 2 or 3 */
+    int32_t  dynamic;      /* 0: static plan classes, 1: dataset-plan classes (affects 3D termination rules) */
+    int32_t  n_plans;
+    int32_t  total_step;   /* 750 / 600 / 1300 (3D static) / 1000 (3D dynamic) */
+    int32_t  plan_mode;    /* DMP_PLAN_* */
+    int32_t  action_dist;  /* DMP_ACT_*  */
+    int64_t  n_envs;       /* envs resident on this device */
+    int64_t  env_base;     /* global index of local env 0 (Philox counter; multi-GPU sharding) */
+    uint64_t seed;         /* Philox key */
+    uint64_t t;            /* global step index of the NEXT step (host-maintained Philox counter) */
+    uint64_t* t_dev;       /* nullable. Device-resident step counter for CUDA-graph replay (2 slots): when set,
+                              a launch reads t from t_dev[slot] (slot = DMP_F_TSLOT1 ? 1 : 0) instead of `t`
+                              and writes t + K to t_dev[slot ^ 1]; consecutive launches alternate the slot */
+    void*    cells;
+    void*    aux;
+    const void*    plans;
+    const int32_t* plan_total;
+    uint32_t* ep_cnt;
+    uint32_t* ep_len;
+    double*   ep_ret;
+    double*   ep_iou;
+    int32_t*  err;         /* one int32: OR of DMP_ERR_* */
+} DmpState;
+
+typedef struct DmpIO {
+    const uint8_t* actions;     /* [K][n] ; NULL -> Philox synthetic actions                              */
+    const uint8_t* step_sizes;  /* [K][n] in {1,2,3}; NULL -> Philox (replaces np.random.randint(1,4))     */
+    const int32_t* next_plan;   /* [K][n] plan index to use if the env auto-resets at that step; NULL -> plan_mode */
+    void*    obs;               /* [K][n][D] of obs_kind ; NULL -> not materialised ("state-only" mode)     */
+    float*   reward;            /* [K][n] ; NULL -> not materialised                                        */
+    uint8_t* done;              /* [K][n] ; NULL -> not materialised                                        */
+    int32_t  obs_kind;          /* DMP_OBS_* */
+    int32_t  flags;             /* DMP_F_*   */
+} DmpIO;
+
+typedef struct DmpLayout {
+    int64_t cells_bytes, aux_bytes;        /* state arrays for n envs            */
+    int64_t plan_row_bytes;                /* bytes per plan-table row           */
+    int32_t obs_dim, n_actions;            /* D and A of the env family          */
+    int32_t grid_rows, grid_cols;          /* padded grid of dmp_export_state    */
+    int32_t total_step_static, total_step_dynamic;
+} DmpLayout;
+
+/* version / diagnostics */
+int dmp_abi_version(void);
+int dmp_last_error(void);                  /* last cudaError_t seen by this library (per process) */
+
+/* sizes for host-side allocation of the arrays described above */
+int dmp_layout(int dim, int64_t n_envs, DmpLayout* out);
+
+/* ---- plan sources (init path) ------------------------------------------------------------------
+ * dmp_plan_static: on-device generator of the static plans
+ *   replaces create_plan(): Env/1D/DMP_Env_1D_static.py:34-55 (0 sine, 1 Gaussian, 2 step),
+ *   Env/2D/DMP_Env_2D_static.py:31-52 and Env/3D/DMP_simulator_3d_static_circle.py:42-65
+ *   (0 dense / 1 sparse 20-gon of matplotlib.patches.CirclePolygon).
+ *   Writes one plan-table row + its brick budget.  Returns DMP_EINVAL for a bad plan_choose
+ *   (the reference raises ValueError at reset()).
+ * dmp_plans_pack: converts a dataset in the reference's own format -- float64 arrays as stored
+ *   in Env/ *D/data_*_envplan_500_*.pkl (1D [n][30], 2D/3D [n][26][26]) already copied to the
+ *   device -- into plan-table rows + budgets (Env/2D/DMP_Env_2D_dynamic_usedata_plan.py:36-46,
+ *   Env/3D/DMP_simulator_3d_dynamic_triangle_usedata.py:47-49). */
+int dmp_plan_static(int dim, int plan_choose, void* plans_row_out, int32_t* plan_total_out, void* stream);
+int dmp_plans_pack(int dim, const double* raw, int n_plans, void* plans_out, int32_t* plan_total_out, void* stream);
+
+/* ---- reset ---------------------------------------------------------------------------------------
+ * replaces reset(): Env/1D/DMP_Env_1D_static.py:66-83, Env/1D/DMP_Env_1D_dynamic_usedata_plan.py:40-70,
+ * Env/2D/DMP_Env_2D_static.py:54-76, Env/2D/DMP_Env_2D_dynamic_usedata_plan.py:34-66,
+ * Env/3D/DMP_simulator_3d_static_circle.py:67-86, Env/3D/DMP_simulator_3d_dynamic_triangle_usedata.py:45-75
+ * and VectorizedEnvWrapper.reset / reset_at (multiprocess.py:20-23).
+ *   mask     : u8[n] nullable (NULL = all envs); only envs with mask != 0 are touched
+ *   plan_idx : i32[n] nullable; NULL -> by plan_mode (Philox draw keyed by (env, t_draw) / +1 / keep)
+ *   obs      : [n][D] nullable; rows of reset envs are written (raw counters are 0 either way)
+ * Episode statistics ep_* are NOT touched (use dmp_stats_clear). */
+int dmp_reset(const DmpState* st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw,
+              void* obs, int obs_kind, void* stream);
+
+/* ---- step / rollout (the hot path) --------------------------------------------------------------
+ * dmp_step replaces step(action) of the six classes (Env/1D/DMP_Env_1D_static.py:85-136,
+ * Env/1D/DMP_Env_1D_dynamic_usedata_plan.py:71-120, Env/2D/DMP_Env_2D_static.py:95-154,
+ * Env/2D/DMP_Env_2D_dynamic_usedata_plan.py:85-147, Env/3D/DMP_simulator_3d_static_circle.py:153-230,
+ * Env/3D/DMP_simulator_3d_dynamic_triangle_usedata.py:142-231), their *_hindsight_replay
+ * step(action, step_size) forms, and VectorizedEnvWrapper.step (multiprocess.py:24-32).
+ * dmp_rollout advances every env K steps in ONE launch (state stays on chip between steps);
+ * it replaces the `for t in range(T)` loop of multiprocess.py:82-84.  dmp_step == dmp_rollout(K=1).
+ * The caller advances DmpState.t by K afterwards. */
+int dmp_step(const DmpState* st, const DmpIO* io, void* stream);
+int dmp_rollout(const DmpState* st, const DmpIO* io, int K, void* stream);
+
+/* ---- IoU / statistics ----------------------------------------------------------------------------
+ * dmp_iou replaces iou(): Env/1D/DMP_Env_1D_static.py:138-151, Env/3D/DMP_simulator_3d_static_circle.py:257-276
+ * and the 2D formula of Env/2D/DMP_Env_2D_static.py:169-175.  iou_out: f64[n].
+ * dmp_stats_reduce sums the per-env episode statistics into out[4] = {sum return, sum IoU, episodes, steps}
+ * (device doubles; deterministic two-pass tree; `scratch` >= dmp_stats_scratch_bytes(n) bytes). The 4-vector
+ * is what the multi-GPU driver all-reduces over NCCL. */
+int dmp_iou(const DmpState* st, double* iou_out, void* stream);
+int64_t dmp_stats_scratch_bytes(int64_t n_envs);
+int dmp_stats_reduce(const DmpState* st, double* out4, void* scratch, void* stream);
+int dmp_stats_clear(const DmpState* st, void* stream);
+
+/* ---- state export / import (attribute views, get_state/set_state, parity tests) -----------------
+ * grid    : i32 [n][rows][cols] in the reference's padded form (environment_memory, -1 frame)
+ * scalars : i32 [n][8] = pos_row (1D: pos), pos_col (1D: 0), count_brick, count_step, plan_idx, total_brick, 0, 0
+ * ret_acc : f32 [n] nullable */
+int dmp_export_state(const DmpState* st, int32_t* grid, int32_t* scalars, float* ret_acc, void* stream);
+int dmp_import_state(const DmpState* st, const int32_t* grid, const int32_t* scalars, const float* ret_acc, void* stream);
+
+/* ---- standalone stage kernels (a)-(e) of the step, for unit parity and per-stage timing ----------
+ * They run the same __device__ stage functions the fused kernels are built from, one stage per launch,
+ * communicating through `scratch` (i32 [n][4]: action-valid/brick-placed flag, target cell row, col, reserved).
+ *   (a) move      : position update + boundary clamp (+3D collision walk)       [clip_position, move_step]
+ *   (b) deposit   : brick deposition into the grid + count_brick                 [step(): drop / build branch]
+ *   (c) observe   : observation-window gather -> obs (smem-staged, 128-bit stores) [observation_, np.hstack]
+ *   (d) reward    : reward + done decision, IoU of finished episodes              [reward rules, iou()]
+ *   (e) done_reset: fold finished episodes into ep_* and reset them               [caller-side reset()] */
+int dmp_stage_move(const DmpState* st, const DmpIO* io, int32_t* scratch, void* stream);
+int dmp_stage_deposit(const DmpState* st, const DmpIO* io, int32_t* scratch, void* stream);
+int dmp_stage_observe(const DmpState* st, const DmpIO* io, int32_t* scratch, void* stream);
+int dmp_stage_reward(const DmpState* st, const DmpIO* io, int32_t* scratch, void* stream);
+int dmp_stage_done_reset(const DmpState* st, const DmpIO* io, int32_t* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMP_H_ */

@@ -1,0 +1,361 @@
+"""Reference-facing surface: the same class names, constructor arguments, methods, attributes and
+return types as the reference's env classes and ``multiprocess.py``, backed by the CUDA vector env.
+
+    deep_mobile_printing_1d1r(plan_choose)            Env/1D/DMP_Env_1D_static.py:6
+    deep_mobile_printing_1d1r_dynamic(data_path, random_choose_paln)   Env/1D/DMP_Env_1D_dynamic_usedata_plan.py:7
+    deep_mobile_printing_2d1r / _2d1r_dynamic         Env/2D/DMP_Env_2D_static.py:6, ..._dynamic_usedata_plan.py:6
+    deep_mobile_printing_3d1r / _3d1r_dynamic         Env/3D/DMP_simulator_3d_static_circle.py:7, ..._dynamic_triangle_usedata.py:6
+    VectorizedEnvWrapper(env, num_envs)               multiprocess.py:15-32
+
+Stochastic draws follow the reference exactly: ``step`` draws ``np.random.randint(1, 4)`` and a random
+``reset`` draws ``np.random.randint(0, len(dataset))`` from the process-global numpy RNG, in the same
+order as the reference, and injects them into the kernel -- so ``np.random.seed(s)`` reproduces the
+reference's trajectories bit for bit.  ``step(action, step_size)`` (the *_hindsight_replay form) is
+accepted as well.
+
+These scalar classes exist for drop-in compatibility; one env per launch is latency-bound on a GPU.
+Throughput comes from ``VectorizedEnvWrapper`` / ``BatchedDMPEnv`` with thousands of envs.
+"""
+from __future__ import annotations
+
+import argparse
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .vecenv import BatchedDMPEnv, load_plan_dataset
+
+
+class HostStepper:
+    """Host-buffer step for a BatchedDMPEnv: numpy actions in, numpy (obs, reward, done) out, through
+    pinned staging buffers (H2D of the actions, D2H of the results, one stream sync per step)."""
+
+    def __init__(self, env: BatchedDMPEnv):
+        self.env = env
+        n, D = env.num_envs, env.obs_dim
+        self._a_pin = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        self._s_pin = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        self._a_dev = torch.empty((1, n), dtype=torch.uint8, device=env.device)
+        self._s_dev = torch.empty((1, n), dtype=torch.uint8, device=env.device)
+        self._obs_dev = torch.empty((1, n, D), dtype=env.obs_dtype, device=env.device)
+        self._rew_dev = torch.empty((1, n), dtype=torch.float32, device=env.device)
+        self._done_dev = torch.empty((1, n), dtype=torch.uint8, device=env.device)
+        self._obs_pin = torch.empty((n, D), dtype=env.obs_dtype, pin_memory=True)
+        self._rew_pin = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        self._done_pin = torch.empty(n, dtype=torch.bool, pin_memory=True)
+        self.actions_buffer = self._a_pin.numpy()          # write actions here to skip one host copy
+        self.h2d_bytes = n
+        self.d2h_bytes = n * D * self._obs_pin.element_size() + 4 * n + n
+
+    def step(self, actions, step_sizes=None):
+        env = self.env
+        if actions is not self.actions_buffer:
+            self.actions_buffer[:] = actions
+        with torch.cuda.device(env.device):
+            self._a_dev[0].copy_(self._a_pin, non_blocking=True)
+            s = None
+            if step_sizes is not None:
+                self._s_pin.numpy()[:] = step_sizes
+                self._s_dev[0].copy_(self._s_pin, non_blocking=True)
+                s = self._s_dev
+            env.rollout(1, actions=self._a_dev, step_sizes=s, out=(self._obs_dev, self._rew_dev, self._done_dev))
+            self._obs_pin.copy_(self._obs_dev[0], non_blocking=True)
+            self._rew_pin.copy_(self._rew_dev[0], non_blocking=True)
+            self._done_pin.copy_(self._done_dev[0].view(torch.bool), non_blocking=True)
+            torch.cuda.current_stream(env.device).synchronize()
+        return self._obs_pin.numpy(), self._rew_pin.numpy(), self._done_pin.numpy()
+
+
+# --------------------------------------------------------------------------------------------------
+# scalar drop-in classes
+# --------------------------------------------------------------------------------------------------
+class _ScalarDMP:
+    """One reference-style env (N = 1 on the device)."""
+    _dim = 0
+    _dynamic = False
+
+    def _setup(self, plan_choose=0, data_path=None, random_choose_paln=True, device="cuda", plans=None):
+        self.plan_choose = plan_choose
+        self.random_choose_paln = random_choose_paln
+        self.index_for_non_random = 0
+        self.index_random = None
+        if self._dynamic:
+            if plans is None:
+                plans = load_plan_dataset(data_path, self._dim)
+            self.plan_dataset = [np.asarray(p, dtype=np.float64) for p in plans]
+            self.plan_dataset_len = len(self.plan_dataset)
+        self._device = device
+        self._plans_arg = None if not self._dynamic else np.asarray(self.plan_dataset)
+        self._env: Optional[BatchedDMPEnv] = None
+        self.step_size = 1
+        self.count_step = 0
+        self.total_brick = 0
+        self.plan = None
+        self.input_plan = None
+        self.one_hot = None
+        self.environment_memory = None
+        self.position_memory = None
+        self.observation = None
+        self.brick_memory = None
+        self._set_count_brick(None)
+        # constants (reference __init__ blocks)
+        probe = {1: (30, 20, 2, 3, 7, 750, 750), 2: (20, 20, 3, 5, 51, 600, 600), 3: (20, 20, 3, 8, 51, 1300, 1000)}[self._dim]
+        self.plan_width, self.plan_height, self.HALF_WINDOW_SIZE, self.action_dim, self.state_dim = probe[:5]
+        self.total_step = probe[6] if self._dynamic else probe[5]
+        self.environment_width = self.plan_width + 2 * self.HALF_WINDOW_SIZE
+        if self._dim == 1:
+            self.environment_height = 100
+            self.wall = np.ones((1, 2)) * (-1)
+        else:
+            self.environment_height = self.plan_height + 2 * self.HALF_WINDOW_SIZE
+        if self._dim == 3:
+            self.plan_length, self.z, self.blank_size, self.check, self.start = 10, 6, 2, [], None
+            self.environment_length = self.plan_length + 2 * self.HALF_WINDOW_SIZE
+
+    # 1D base classes spell the counter 'conut_brick' (Env/1D/DMP_Env_1D_static.py:14); expose both
+    def _set_count_brick(self, v):
+        self.count_brick = v
+        self.conut_brick = v
+
+    def _ensure(self):
+        if self._env is None:
+            self._env = BatchedDMPEnv(self._dim, dynamic=self._dynamic, plan_choose=self.plan_choose,
+                                      plans=self._plans_arg, num_envs=1, device=self._device,
+                                      obs_dtype=torch.float64, random_choose_paln=self.random_choose_paln)
+            self._dense_plans = self._env.plans_dense()
+
+    def _sync_attrs(self):
+        st = self._env.export_state()
+        sc = st["scalars"][0].cpu().numpy()
+        self.environment_memory = st["grid"][0].cpu().numpy().astype(np.float64)
+        self._set_count_brick(int(sc[2]))
+        self.count_step = int(sc[3])
+        pos = int(sc[0]) if self._dim == 1 else [int(sc[0]), int(sc[1])]
+        return pos
+
+    def reset(self):
+        self._ensure()
+        idx = 0
+        if self._dynamic:
+            if self.random_choose_paln:                      # e.g. Env/2D/DMP_Env_2D_dynamic_usedata_plan.py:35-38
+                self.index_random = int(np.random.randint(0, self.plan_dataset_len))
+                idx = self.index_random
+            else:                                            # :39-44
+                idx = self.index_for_non_random
+                self.index_for_non_random += 1
+                if self.index_for_non_random == self.plan_dataset_len:
+                    self.index_for_non_random = 0
+        obs = self._env.reset(plan_idx=[idx]).cpu().numpy().reshape(1, -1)
+        self.plan = self._dense_plans[idx]
+        tb = float(self._env.plan_totals()[idx].item())
+        self.total_brick = tb
+        if self._dim != 1:
+            h = self.HALF_WINDOW_SIZE
+            self.input_plan = self.plan[h:h + self.plan_height, h:h + self.plan_width]
+        if self._dim == 1 and not self._dynamic:
+            self.one_hot = None
+        pos = self._sync_attrs()
+        self.position_memory = [pos]
+        self.brick_memory = [[-1, -1]] if self._dim == 1 else None
+        if self._dim == 3:
+            self.check, self.step_size = [], 1
+        return self._format_obs(obs, pos, reset=True)
+
+    def step(self, action, step_size=None):
+        if self._env is None or self.position_memory is None:
+            raise AttributeError("call reset() before step()")
+        a = int(action)
+        self.step_size = int(np.random.randint(1, 4)) if step_size is None else int(step_size)
+        if self._dim != 3 and not (0 <= a < self.action_dim):
+            # the reference increments count_step, draws, then fails on the unbound 'position'
+            self._env.step([255], [self.step_size])
+            self._env._err.zero_()
+            self._sync_attrs()
+            raise UnboundLocalError("local variable 'position' referenced before assignment")
+        if self._dim == 3 and a < 0:
+            raise ValueError("negative actions are not supported by the device path")
+        obs, rew, done = self._env.step([min(a, 255)], [self.step_size])
+        obs = obs.cpu().numpy().reshape(1, -1).copy()
+        r, d = float(rew.item()), bool(done.item())
+        pos = self._sync_attrs()
+        self.position_memory.append(pos)
+        if self._dim == 1:
+            self.brick_memory.append([pos, self.environment_memory[0, pos]] if a == 2 else [-1, -1])
+        self._env._err.zero_()
+        return self._format_obs(obs, pos, reset=False), self._reward_type(a, r, d), d
+
+    def _reward_type(self, a, r, d):
+        """The reference returns the python int 0 on moves (and on 2D drops above the plan) and floats
+        elsewhere; 3D always returns floats."""
+        if self._dim == 3:
+            return r
+        drop = self.action_dim - 1
+        if a != drop:
+            return 0
+        if self._dim == 2 and r == 0.0 and not (self.count_brick >= self.total_brick):
+            return 0
+        return r
+
+    def _normalised(self, obs):
+        o = obs.copy()
+        o[0, -2] = self.count_brick / self.total_brick
+        o[0, -1] = self.count_step / self.total_step
+        return o
+
+    def _format_obs(self, obs, pos, reset):
+        if not self._dynamic:
+            return obs
+        if self._dim == 1:                                   # Env/1D/DMP_Env_1D_dynamic_usedata_plan.py:66-70, :114-118
+            out = [obs, self._normalised(obs), self.plan]
+            if reset:
+                out.append(pos)
+            return out
+        return [self._normalised(obs), self.input_plan, pos]  # Env/2D/..._usedata_plan.py:64-66
+
+    def iou(self):
+        return float(self._env.iou().item())
+
+    def render(self, *a, **k):
+        raise NotImplementedError("render() needs matplotlib and is outside the simulator hot path")
+
+
+class deep_mobile_printing_1d1r(_ScalarDMP):
+    _dim, _dynamic = 1, False
+
+    def __init__(self, plan_choose=0, device="cuda"):
+        self._setup(plan_choose=plan_choose, device=device)
+
+
+class deep_mobile_printing_1d1r_dynamic(_ScalarDMP):
+    _dim, _dynamic = 1, True
+
+    def __init__(self, data_path=None, random_choose_paln=True, device="cuda", plans=None):
+        self._setup(data_path=data_path, random_choose_paln=random_choose_paln, device=device, plans=plans)
+
+
+class deep_mobile_printing_2d1r(_ScalarDMP):
+    _dim, _dynamic = 2, False
+
+    def __init__(self, plan_choose=0, device="cuda"):
+        self._setup(plan_choose=plan_choose, device=device)
+
+
+class deep_mobile_printing_2d1r_dynamic(_ScalarDMP):
+    _dim, _dynamic = 2, True
+
+    def __init__(self, data_path=None, random_choose_paln=True, device="cuda", plans=None):
+        self._setup(data_path=data_path, random_choose_paln=random_choose_paln, device=device, plans=plans)
+
+
+class deep_mobile_printing_3d1r(_ScalarDMP):
+    _dim, _dynamic = 3, False
+
+    def __init__(self, plan_choose=1, device="cuda"):          # 3D default is 1 (…static_circle.py:8)
+        self._setup(plan_choose=plan_choose, device=device)
+
+
+class deep_mobile_printing_3d1r_dynamic(_ScalarDMP):
+    _dim, _dynamic = 3, True
+
+    def __init__(self, data_path=None, random_choose_paln=True, device="cuda", plans=None):
+        self._setup(data_path=data_path, random_choose_paln=random_choose_paln, device=device, plans=plans)
+
+
+# --------------------------------------------------------------------------------------------------
+# multiprocess.py replacement
+# --------------------------------------------------------------------------------------------------
+class VectorizedEnvWrapper:
+    """``VectorizedEnvWrapper(env, num_envs)`` of multiprocess.py:15-32 with num_envs INDEPENDENT,
+    device-resident copies of ``env`` (the reference repeats one shared object, quirk Q1 -- not reproduced).
+    reset() -> (N,1,D) float64; step(actions) -> ((N,1,D) float64, (N,) float64, (N,) bool), all numpy.
+    Per-env step sizes are drawn as np.random.randint(1, 4, size=N): the same global-RNG stream the
+    reference consumes when it loops over N env objects."""
+
+    def __init__(self, env_: _ScalarDMP, num_envs: int = 1, obs_dtype=torch.float64, auto_reset: bool = False):
+        self.env = env_
+        self.num_envs = num_envs
+        self.envs = [env_ for _ in range(num_envs)]
+        self._proto = env_
+        self.total_step = env_.total_step
+        self.vec = BatchedDMPEnv(env_._dim, dynamic=env_._dynamic, plan_choose=env_.plan_choose,
+                                 plans=env_._plans_arg, num_envs=num_envs, device=env_._device,
+                                 obs_dtype=obs_dtype, random_choose_paln=env_.random_choose_paln,
+                                 auto_reset=auto_reset, normalise=False)
+        self._host = HostStepper(self.vec)
+
+    def _draw_plans(self, n):
+        if not self._proto._dynamic:
+            return None
+        if self._proto.random_choose_paln:
+            return np.random.randint(0, self._proto.plan_dataset_len, size=n).astype(np.int32)
+        return None
+
+    def reset(self):
+        obs = self.vec.reset(plan_idx=self._draw_plans(self.num_envs))
+        return obs.cpu().numpy().reshape(self.num_envs, 1, -1)
+
+    def reset_at(self, env_index):
+        p = self._draw_plans(1)
+        m = np.zeros(self.num_envs, np.uint8)
+        m[env_index] = 1
+        pi = None
+        if p is not None:
+            pi = np.zeros(self.num_envs, np.int32)
+            pi[env_index] = p[0]
+        obs = self.vec.reset(mask=m, plan_idx=pi)
+        return obs[env_index].cpu().numpy().reshape(1, -1)
+
+    def step(self, actions):
+        sizes = np.random.randint(1, 4, size=self.num_envs).astype(np.uint8)
+        obs, rew, done = self._host.step(np.asarray(actions).astype(np.uint8), sizes)
+        return (obs.reshape(self.num_envs, 1, -1).astype(np.float64, copy=True),
+                rew.astype(np.float64), done.copy())
+
+
+def main(args=None):
+    """CLI of multiprocess.py:34-97: --env {1DStatic,...,3DDynamic} --plan_type INT --num_envs INT."""
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--env', type=str, default=None,
+                        help='Environment Name: {1DStatic, 1DDynamic,2DStatic, 2DDynamic, 3DStatic, 3DDynamic}')
+    parser.add_argument('--plan_type', type=int, default=None, help='type of shapes')
+    parser.add_argument('--num_envs', type=int, default=3, help='Number of environments')
+    parser.add_argument('--data_root', type=str, default='./Env', help='directory holding the reference .pkl plan datasets')
+    args = parser.parse_args(args)
+    if args.env is None:
+        print("please choose an environment in the list: {1DStatic, 1DDynamic,2DStatic, 2DDynamic, 3DStatic, 3DDynamic} ")
+        return None
+    need_plan = {"1DStatic": "{0: sin, 1:Gaussian, 2: Step}", "2DStatic": "{0: Dense, 1: Sparse}",
+                 "2DDynamic": "{0: Dense, 1: Sparse}", "3DStatic": "{0: Dense, 1: Sparse}", "3DDynamic": "{0: Dense, 1: Sparse}"}
+    if args.env in need_plan and args.plan_type is None:
+        print("please choose a shape from list: " + need_plan[args.env])
+        return None
+    dens = ["dense", "sparse"][args.plan_type or 0]
+    if args.env == "1DStatic":
+        env_input = deep_mobile_printing_1d1r(plan_choose=args.plan_type)
+    elif args.env == "1DDynamic":
+        env_input = deep_mobile_printing_1d1r_dynamic(data_path=args.data_root + "/1D/data_1d_dynamic_sin_envplan_500_train.pkl")
+    elif args.env == "2DStatic":
+        env_input = deep_mobile_printing_2d1r(plan_choose=args.plan_type)
+    elif args.env == "2DDynamic":
+        env_input = deep_mobile_printing_2d1r_dynamic(data_path=args.data_root + "/2D/data_2d_dynamic_" + dens + "_envplan_500_train.pkl")
+    elif args.env == "3DStatic":
+        env_input = deep_mobile_printing_3d1r(plan_choose=args.plan_type)
+    elif args.env == "3DDynamic":      # the reference loads the 2D dataset here (quirk Q5); we load the 3D one
+        env_input = deep_mobile_printing_3d1r_dynamic(data_path=args.data_root + "/3D/data_3d_dynamic_" + dens + "_envplan_500_train.pkl")
+    else:
+        raise SystemExit("unknown --env %s" % args.env)
+    env = VectorizedEnvWrapper(env_input, num_envs=args.num_envs)
+    T = env.total_step
+    observations = env.reset()
+    for t in range(T):
+        actions = np.random.randint(3, size=args.num_envs)     # multiprocess.py:83 (actions 0..2 only, quirk Q2)
+        observations, rewards, dones = env.step(actions)
+    print(observations.shape)
+    print(rewards.shape)
+    print(dones.shape)
+    return observations, rewards, dones
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,325 @@
+// dmp_1d.cu -- 1D mobile-construction envs (30-column height field, 5-cell window, 3 actions).
+//
+// Reference semantics: Env/1D/DMP_Env_1D_static.py:57-151 and
+// Env/1D/DMP_Env_1D_dynamic_usedata_plan.py:32-133 (same step logic; dataset plan).
+//
+// Mapping: one env per thread, state = 4 coalesced 128-bit loads (30 x u16 heights + the two
+// counters) + one 64-bit load (position, plan index, running return).  Heights are parked in shared
+// memory in the reference's padded form (a -1 halfword pair either side) so the 5-cell window is
+// three conflict-free word reads + funnel shifts; observations are staged per warp and streamed out
+// contiguously.
+#include "dmp_common.cuh"
+
+namespace {
+
+constexpr int B1 = 128;
+constexpr int S1_WORDS = 17;          // padded 34 halfwords: word 0 and 16 are the -1 walls
+
+struct Env1 {
+    int pos, plan_idx, cb, cs;
+    float ret;
+};
+
+// stage (a): clip_position, Env/1D/DMP_Env_1D_static.py:57-64
+__device__ __forceinline__ void stage_move1(Env1& e, int a, int s) {
+    const int p = (a == 0) ? e.pos - s : e.pos + s;
+    e.pos = min(max(p, D1_LO), D1_HI);
+}
+
+// stage (b): environment_memory[0, position] += 1 (:104); returns the new height
+__device__ __forceinline__ int stage_deposit1(uint32_t* g, const Env1& e) {
+    const int w = e.pos >> 1, sh = (e.pos & 1) * 16;
+    const uint32_t x = g[w * B1];
+    const uint32_t h = ((x >> sh) & 0xFFFFu) + 1u;
+    g[w * B1] = (x & ~(0xFFFFu << sh)) | ((h & 0xFFFFu) << sh);
+    return (int)h;
+}
+
+// stage (c): window [pos-2, pos+2] + counters (:131-133)
+template <typename ObsT>
+__device__ __forceinline__ void stage_observe1(const uint32_t* g, const Env1& e, ObsT* row, bool normalise,
+                                               int total_brick, int total_step) {
+    const int p0 = e.pos - D1_HW;
+    const int w = p0 >> 1, sh = (p0 & 1) * 16;
+    const uint32_t x0 = g[w * B1], x1 = g[(w + 1) * B1], x2 = g[(w + 2) * B1];
+    const uint32_t q0 = __funnelshift_r(x0, x1, sh), q1 = __funnelshift_r(x1, x2, sh), q2 = x2 >> sh;
+    row[0] = obs_from_int<ObsT>((int)(int16_t)(q0 & 0xFFFF));
+    row[1] = obs_from_int<ObsT>((int)(int16_t)(q0 >> 16));
+    row[2] = obs_from_int<ObsT>((int)(int16_t)(q1 & 0xFFFF));
+    row[3] = obs_from_int<ObsT>((int)(int16_t)(q1 >> 16));
+    row[4] = obs_from_int<ObsT>((int)(int16_t)(q2 & 0xFFFF));
+    obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, total_step, row[5], row[6]);
+}
+
+// IoU, Env/1D/DMP_Env_1D_static.py:138-151: cross = sum(min(g, p)); iou = cross / (sum p + sum g - cross)
+__device__ __forceinline__ double iou1_words(const uint32_t (&hw)[15], const uint8_t* __restrict__ plan) {
+    int a1 = 0, a2 = 0, cross = 0;
+#pragma unroll
+    for (int j = 0; j < 15; ++j) {
+        const int h0 = hw[j] & 0xFFFF, h1 = hw[j] >> 16;
+        const int p0 = plan[2 * j], p1 = plan[2 * j + 1];
+        a1 += p0 + p1;
+        a2 += h0 + h1;
+        cross += min(h0, p0) + min(h1, p1);
+    }
+    return __ddiv_rn((double)cross, (double)(a1 + a2 - cross));
+}
+
+template <typename ObsT>
+__global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO io, const int K) {
+    extern __shared__ uint4 smem_raw[];
+    uint32_t* G = reinterpret_cast<uint32_t*>(smem_raw);                 // [S1_WORDS][B1]
+    ObsT* tiles = reinterpret_cast<ObsT*>(G + S1_WORDS * B1);            // [B1/32][32*7]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n = st.n_envs;
+    const int64_t env = (int64_t)blockIdx.x * B1 + tid;
+    const int64_t env0 = env - lane;
+    const int nvalid = (int)min((int64_t)32, n - env0);
+    const bool live = env < n;
+    ObsT* tile = tiles + warp * (32 * D1_OBS);
+    uint32_t* g = G + tid;
+
+    uint4* cells = reinterpret_cast<uint4*>(st.cells);
+    uint2* aux = reinterpret_cast<uint2*>(st.aux);
+    const uint8_t* __restrict__ plans = reinterpret_cast<const uint8_t*>(st.plans);
+    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
+    uint2 ax = make_uint2(D1_LO, 0);
+    if (live) {
+        v0 = cells[env]; v1 = cells[n + env]; v2 = cells[2 * n + env]; v3 = cells[3 * n + env];
+        ax = aux[env];
+    }
+    g[0] = 0xFFFFFFFFu;
+    g[1 * B1] = v0.x;  g[2 * B1] = v0.y;  g[3 * B1] = v0.z;  g[4 * B1] = v0.w;
+    g[5 * B1] = v1.x;  g[6 * B1] = v1.y;  g[7 * B1] = v1.z;  g[8 * B1] = v1.w;
+    g[9 * B1] = v2.x;  g[10 * B1] = v2.y; g[11 * B1] = v2.z; g[12 * B1] = v2.w;
+    g[13 * B1] = v3.x; g[14 * B1] = v3.y; g[15 * B1] = v3.z;
+    g[16 * B1] = 0xFFFFFFFFu;
+    Env1 e;
+    e.pos = ax.x & 0xFFFF; e.plan_idx = ax.x >> 16; e.ret = __uint_as_float(ax.y);
+    e.cb = v3.w & 0xFFFF; e.cs = v3.w >> 16;
+    int total_brick = __ldg(st.plan_total + e.plan_idx);
+    unsigned dirty = 0;
+    int errbits = 0;
+
+    const bool autoreset = io.flags & DMP_F_AUTORESET;
+    const bool normalise = io.flags & DMP_F_NORMALISE;
+    const bool need_draw = (io.actions == nullptr) || (io.step_sizes == nullptr);
+    const int tslot = (io.flags & DMP_F_TSLOT1) ? 1 : 0;
+    const uint64_t t0 = st.t_dev ? st.t_dev[tslot] : st.t;
+
+    for (int k = 0; k < K; ++k) {
+        const uint64_t t = t0 + (uint64_t)k;
+        const int64_t idx = (int64_t)k * n + env;
+        Draw d = Draw{0, 0, 0, 0};
+        if (need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
+        int a, s;
+        if (io.actions) a = live ? io.actions[idx] : 0; else a = draw_action(d, D1_ACT, st.action_dist);
+        if (io.step_sizes) s = live ? io.step_sizes[idx] : 1; else s = draw_step_size(d);
+        if ((unsigned)(s - 1) > 2u) errbits |= DMP_ERR_STEPSIZE;
+
+        // ---- step(): Env/1D/DMP_Env_1D_static.py:85-136 ---------------------------------------
+        e.cs += 1;
+        float reward = 0.f;
+        bool done;
+        if (a < 2) {                                        // (a) move left / right
+            stage_move1(e, a, s);
+            done = e.cs >= st.total_step;
+        } else if (a == 2) {                                // (b) drop + (d) reward
+            e.cb += 1;
+            const int h = stage_deposit1(g, e);
+            dirty |= 1u << ((e.pos - D1_HW) >> 3);          // 8 heights per 128-bit plane
+            if (e.cb >= total_brick) {                      // :107-114
+                done = true;
+            } else {                                        // :116-123
+                done = e.cs >= st.total_step;
+                const int p = plans[e.plan_idx * PLAN1D_BYTES + (e.pos - D1_HW)];
+                reward = (h > p) ? -1.f : (h == p ? 10.f : 1.f);
+            }
+        } else {
+            errbits |= DMP_ERR_ACTION;
+            done = e.cs >= st.total_step;
+        }
+        e.ret += reward;
+
+        if (io.obs) {
+            stage_observe1<ObsT>(g, e, tile + lane * D1_OBS, normalise, total_brick, st.total_step);
+            __syncwarp();
+            if (nvalid > 0)
+                warp_tile_store<ObsT>(reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * D1_OBS,
+                                      tile, nvalid * D1_OBS, lane);
+            __syncwarp();
+        }
+        if (live) {
+            if (io.reward) io.reward[idx] = reward;
+            if (io.done) io.done[idx] = done ? 1 : 0;
+        }
+
+        if (done && autoreset && live) {
+            uint32_t hw[15];
+#pragma unroll
+            for (int j = 0; j < 15; ++j) hw[j] = g[(j + 1) * B1];
+            const double iou = iou1_words(hw, plans + e.plan_idx * PLAN1D_BYTES);
+            st.ep_cnt[env] += 1;
+            st.ep_len[env] += (uint32_t)e.cs;
+            st.ep_ret[env] += (double)e.ret;
+            st.ep_iou[env] += iou;
+            if (io.next_plan) {
+                const int p = io.next_plan[idx];
+                if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
+            } else if (st.plan_mode == DMP_PLAN_PHILOX) {
+                if (!need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
+                e.plan_idx = draw_plan(d.x2, st.n_plans);
+            } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
+                e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
+            }
+            total_brick = __ldg(st.plan_total + e.plan_idx);
+#pragma unroll
+            for (int j = 1; j <= 15; ++j) g[j * B1] = 0;
+            e.pos = D1_LO; e.cb = e.cs = 0; e.ret = 0.f;
+            dirty = 0xFu;
+        }
+    }
+
+    if (live) {
+        if (dirty & 1u) cells[env] = make_uint4(g[1 * B1], g[2 * B1], g[3 * B1], g[4 * B1]);
+        if (dirty & 2u) cells[n + env] = make_uint4(g[5 * B1], g[6 * B1], g[7 * B1], g[8 * B1]);
+        if (dirty & 4u) cells[2 * n + env] = make_uint4(g[9 * B1], g[10 * B1], g[11 * B1], g[12 * B1]);
+        cells[3 * n + env] = make_uint4(g[13 * B1], g[14 * B1], g[15 * B1],
+                                        (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16));
+        aux[env] = make_uint2((uint32_t)e.pos | ((uint32_t)e.plan_idx << 16), __float_as_uint(e.ret));
+        if (errbits) atomicOr(st.err, errbits);
+    }
+    if (st.t_dev && blockIdx.x == 0 && tid == 0) st.t_dev[tslot ^ 1] = t0 + (uint64_t)K;
+}
+
+template <typename ObsT>
+__global__ void k1d_reset(const DmpState st, const uint8_t* __restrict__ mask, const int32_t* __restrict__ plan_idx,
+                          const uint64_t t_draw, ObsT* __restrict__ obs) {
+    const int64_t n = st.n_envs;
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n || (mask && !mask[env])) return;
+    uint4* cells = reinterpret_cast<uint4*>(st.cells);
+    uint2* aux = reinterpret_cast<uint2*>(st.aux);
+    int p;
+    if (plan_idx) {
+        p = plan_idx[env];
+        if ((unsigned)p >= (unsigned)st.n_plans) { atomicOr(st.err, DMP_ERR_PLANIDX); p = 0; }
+    } else if (st.plan_mode == DMP_PLAN_PHILOX) {
+        p = draw_plan(env_draw(st.seed, (uint64_t)(st.env_base + env), t_draw).x3, st.n_plans);
+    } else {
+        p = (int)(aux[env].x >> 16);
+        if (st.plan_mode == DMP_PLAN_SEQUENTIAL) p = (p + 1 >= st.n_plans) ? 0 : p + 1;
+        if ((unsigned)p >= (unsigned)st.n_plans) p = 0;
+    }
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    cells[env] = z; cells[n + env] = z; cells[2 * n + env] = z; cells[3 * n + env] = z;
+    aux[env] = make_uint2((uint32_t)D1_LO | ((uint32_t)p << 16), 0u);
+    if (obs) {                       // window at pos 2: [-1, -1, 0, 0, 0], counters 0 (:81-83)
+        ObsT* o = obs + env * D1_OBS;
+        o[0] = obs_from_int<ObsT>(-1); o[1] = obs_from_int<ObsT>(-1);
+        for (int j = 2; j < 7; ++j) o[j] = obs_from_int<ObsT>(0);
+    }
+}
+
+__device__ __forceinline__ uint32_t cell_word1(const DmpState& st, int64_t env, int w) {
+    return reinterpret_cast<const uint32_t*>(st.cells)[((int64_t)(w >> 2) * st.n_envs + env) * 4 + (w & 3)];
+}
+
+__global__ void k1d_iou(const DmpState st, double* __restrict__ out) {
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= st.n_envs) return;
+    uint32_t hw[15];
+#pragma unroll
+    for (int j = 0; j < 15; ++j) hw[j] = cell_word1(st, env, j);
+    const int p = (int)(reinterpret_cast<const uint2*>(st.aux)[env].x >> 16);
+    out[env] = iou1_words(hw, reinterpret_cast<const uint8_t*>(st.plans) + p * PLAN1D_BYTES);
+}
+
+__global__ void k1d_export(const DmpState st, int32_t* __restrict__ grid, int32_t* __restrict__ scalars, float* __restrict__ ret) {
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= st.n_envs) return;
+    if (grid) {
+        int32_t* g = grid + env * 34;
+        g[0] = g[1] = g[32] = g[33] = -1;
+        for (int j = 0; j < 15; ++j) {
+            const uint32_t x = cell_word1(st, env, j);
+            g[2 + 2 * j] = x & 0xFFFF;
+            g[3 + 2 * j] = x >> 16;
+        }
+    }
+    const uint2 ax = reinterpret_cast<const uint2*>(st.aux)[env];
+    if (scalars) {
+        int32_t* s = scalars + env * 8;
+        const uint32_t c = cell_word1(st, env, 15);
+        const int p = ax.x >> 16;
+        s[0] = ax.x & 0xFFFF; s[1] = 0; s[2] = c & 0xFFFF; s[3] = c >> 16; s[4] = p;
+        s[5] = st.plan_total[p]; s[6] = 0; s[7] = 0;
+    }
+    if (ret) ret[env] = __uint_as_float(ax.y);
+}
+
+__global__ void k1d_import(const DmpState st, const int32_t* __restrict__ grid, const int32_t* __restrict__ scalars,
+                           const float* __restrict__ ret) {
+    const int64_t n = st.n_envs;
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n) return;
+    uint32_t* cw = reinterpret_cast<uint32_t*>(st.cells);
+    uint2* aux = reinterpret_cast<uint2*>(st.aux);
+    auto wref = [&](int w) -> uint32_t& { return cw[((int64_t)(w >> 2) * n + env) * 4 + (w & 3)]; };
+    if (grid) {
+        const int32_t* g = grid + env * 34;
+        for (int j = 0; j < 15; ++j) wref(j) = (uint32_t)(g[2 + 2 * j] & 0xFFFF) | ((uint32_t)(g[3 + 2 * j] & 0xFFFF) << 16);
+    }
+    uint2 ax = aux[env];
+    if (scalars) {
+        const int32_t* s = scalars + env * 8;
+        wref(15) = (uint32_t)(s[2] & 0xFFFF) | ((uint32_t)s[3] << 16);
+        ax.x = (uint32_t)s[0] | ((uint32_t)s[4] << 16);
+    }
+    if (ret) ax.y = __float_as_uint(ret[env]);
+    aux[env] = ax;
+}
+
+template <typename ObsT>
+int launch_rollout1(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    const size_t smem = (size_t)S1_WORDS * B1 * 4 + (size_t)(B1 / 32) * 32 * D1_OBS * sizeof(ObsT);
+    const unsigned blocks = (unsigned)((st.n_envs + B1 - 1) / B1);
+    k1d_rollout<ObsT><<<blocks, B1, smem, s>>>(st, io, K);
+    return dmp_set_error(cudaGetLastError());
+}
+
+}  // namespace
+
+int dmp1d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    switch (io.obs_kind) {
+        case DMP_OBS_F32: return launch_rollout1<float>(st, io, K, s);
+        case DMP_OBS_F64: return launch_rollout1<double>(st, io, K, s);
+        case DMP_OBS_I16: return launch_rollout1<int16_t>(st, io, K, s);
+    }
+    return DMP_EINVAL;
+}
+
+int dmp1d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs,
+                int obs_kind, cudaStream_t s) {
+    const unsigned blocks = (unsigned)((st.n_envs + 255) / 256);
+    switch (obs_kind) {
+        case DMP_OBS_F32: k1d_reset<float><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (float*)obs); break;
+        case DMP_OBS_F64: k1d_reset<double><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (double*)obs); break;
+        case DMP_OBS_I16: k1d_reset<int16_t><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (int16_t*)obs); break;
+        default: return DMP_EINVAL;
+    }
+    return dmp_set_error(cudaGetLastError());
+}
+
+int dmp1d_iou(const DmpState& st, double* out, cudaStream_t s) {
+    k1d_iou<<<(unsigned)((st.n_envs + 255) / 256), 256, 0, s>>>(st, out);
+    return dmp_set_error(cudaGetLastError());
+}
+int dmp1d_export(const DmpState& st, int32_t* grid, int32_t* scalars, float* ret, cudaStream_t s) {
+    k1d_export<<<(unsigned)((st.n_envs + 127) / 128), 128, 0, s>>>(st, grid, scalars, ret);
+    return dmp_set_error(cudaGetLastError());
+}
+int dmp1d_import(const DmpState& st, const int32_t* grid, const int32_t* scalars, const float* ret, cudaStream_t s) {
+    k1d_import<<<(unsigned)((st.n_envs + 127) / 128), 128, 0, s>>>(st, grid, scalars, ret);
+    return dmp_set_error(cudaGetLastError());
+}

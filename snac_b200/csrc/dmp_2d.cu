@@ -1,0 +1,398 @@
+// dmp_2d.cu -- 2D mobile-construction envs (20x20 occupancy grid, 7x7 window, 5 actions).
+//
+// Reference semantics: Env/2D/DMP_Env_2D_static.py:54-154 and
+// Env/2D/DMP_Env_2D_dynamic_usedata_plan.py:34-147 (identical step logic; the dynamic class
+// only changes where the plan comes from and normalises the two counter columns).
+//
+// Mapping: one env per thread.  The 64 B state record is fetched with four coalesced 128-bit
+// loads (SoA planes), the 400 occupancy bits are parked in shared memory ([word][thread], bank =
+// lane, so the data-dependent row select is conflict free), the step is applied, the 7x7 window is
+// cut out of the bit grid with funnel shifts, expanded into the warp's [32][51] observation tile in
+// shared memory and streamed out as one contiguous, 16 B aligned span with 128-bit stores.
+// K > 1 keeps the state on chip between steps (rollout mode).
+#include "dmp_common.cuh"
+
+namespace {
+
+constexpr int B2 = 128;                 // threads (= envs) per block
+constexpr int S2_WORDS = 18;            // smem words per env: 2 zero | 13 grid | 3 zero
+constexpr int S2_G0 = 2;                // first grid word
+constexpr uint32_t ROWMASK = 0xFFFFFu;  // 20 bits
+constexpr uint32_t COLVALID = 0x7FFFF8u;  // padded columns 3..22 are inside the plan area
+
+struct Env2 {
+    int pr, pc, plan_idx, cb, cs;
+    float ret;
+};
+
+__device__ __forceinline__ void unpack2(const uint4& v3, Env2& e) {
+    e.pr = v3.y & 0xFF;
+    e.pc = (v3.y >> 8) & 0xFF;
+    e.plan_idx = v3.y >> 16;
+    e.cb = v3.z & 0xFFFF;
+    e.cs = v3.z >> 16;
+    e.ret = __uint_as_float(v3.w);
+}
+__device__ __forceinline__ void pack2(const Env2& e, uint32_t word12, uint4& v3) {
+    v3.x = word12;
+    v3.y = (uint32_t)e.pr | ((uint32_t)e.pc << 8) | ((uint32_t)e.plan_idx << 16);
+    v3.z = (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16);
+    v3.w = __float_as_uint(e.ret);
+}
+
+// stage (a): move + clamp.  clip_position, Env/2D/DMP_Env_2D_static.py:84-93; action map :100-117
+__device__ __forceinline__ void stage_move2(Env2& e, int a, int s) {
+    int r = e.pr, c = e.pc;
+    if (a == 0) c -= s;
+    else if (a == 1) c += s;
+    else if (a == 2) r += s;
+    else r -= s;
+    e.pr = min(max(r, D2_LO), D2_HI);
+    e.pc = min(max(c, D2_LO), D2_HI);
+}
+
+// stage (b): brick deposition into the bit grid (g = this thread's smem column).  Returns the
+// previous occupancy of the cell (nonzero = was already occupied); :120-125, :129-130, :143-144
+// (increment then clip to 1 == OR of one bit).
+__device__ __forceinline__ uint32_t stage_deposit2(uint32_t* g, const Env2& e, int& word, uint32_t& bit) {
+    const int b = (e.pr - D2_HW) * D2_W + (e.pc - D2_HW);
+    word = b >> 5;
+    bit = 1u << (b & 31);
+    const uint32_t old = g[(S2_G0 + word) * B2];
+    g[(S2_G0 + word) * B2] = old | bit;
+    return old & bit;
+}
+
+// stage (c): observation window -> this thread's row of the warp tile.  observation_ :78-82 + hstack.
+template <typename ObsT>
+__device__ __forceinline__ void stage_observe2(const uint32_t* g, const Env2& e, ObsT* row,
+                                               bool normalise, int total_brick, int total_step) {
+    // rows pr-3 .. pr+3 of the padded grid are interior rows pr-6 .. pr; the grid words are stored
+    // behind 64 zero bits so that the 140-bit span [B0, B0+140) is always in range.
+    const int B0 = 64 + (e.pr - 2 * D2_HW) * D2_W;
+    const int w0 = B0 >> 5, off = B0 & 31;
+    const uint32_t x0 = g[(w0 + 0) * B2], x1 = g[(w0 + 1) * B2], x2 = g[(w0 + 2) * B2];
+    const uint32_t x3 = g[(w0 + 3) * B2], x4 = g[(w0 + 4) * B2], x5 = g[(w0 + 5) * B2];
+    const uint32_t q0 = __funnelshift_r(x0, x1, off), q1 = __funnelshift_r(x1, x2, off);
+    const uint32_t q2 = __funnelshift_r(x2, x3, off), q3 = __funnelshift_r(x3, x4, off);
+    const uint32_t q4 = __funnelshift_r(x4, x5, off);
+    uint32_t R[7];
+    R[0] = q0;
+    R[1] = __funnelshift_r(q0, q1, 20);
+    R[2] = q1 >> 8;
+    R[3] = __funnelshift_r(q1, q2, 28);
+    R[4] = __funnelshift_r(q2, q3, 16);
+    R[5] = q3 >> 4;
+    R[6] = __funnelshift_r(q3, q4, 24);
+    const int sh = e.pc - D2_HW;                       // window column 0 = padded column pc-3
+    const uint32_t colvalid = (COLVALID >> sh) & 0x7Fu;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const int p = e.pr - D2_HW + k;                // padded row of window row k
+        const bool rowvalid = (unsigned)(p - D2_HW) < (unsigned)D2_W;
+        const uint32_t occ = (((R[k] & ROWMASK) << D2_HW) >> sh) & 0x7Fu;
+        const uint32_t val = rowvalid ? colvalid : 0u;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            // inside: 0/1 ; frame: -1  (environment_memory[...] = -1, :61-64)
+            const int v = (int)((occ >> j) & 1u) + (int)((val >> j) & 1u) - 1;
+            row[k * 7 + j] = obs_from_int<ObsT>(v);
+        }
+    }
+    obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, total_step, row[49], row[50]);
+}
+
+// stage (d) helper: IoU = |G & P| / |G | P| over the interior (render :169-175) with warp-free popc.
+__device__ __forceinline__ double iou2(const uint32_t* g, const uint32_t* __restrict__ plan) {
+    int inter = 0, uni = 0;
+#pragma unroll
+    for (int w = 0; w < GRID2D_WORDS; ++w) {
+        const uint32_t gw = g[(S2_G0 + w) * B2], pw = __ldg(plan + w);
+        inter += __popc(gw & pw);
+        uni += __popc(gw | pw);
+    }
+    return __ddiv_rn((double)inter, (double)uni);
+}
+
+template <typename ObsT>
+__global__ void __launch_bounds__(B2) k2d_rollout(const DmpState st, const DmpIO io, const int K) {
+    extern __shared__ uint4 smem_raw[];
+    uint32_t* G = reinterpret_cast<uint32_t*>(smem_raw);                 // [S2_WORDS][B2]
+    ObsT* tiles = reinterpret_cast<ObsT*>(G + S2_WORDS * B2);            // [B2/32][32*51]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n = st.n_envs;
+    const int64_t env = (int64_t)blockIdx.x * B2 + tid;
+    const int64_t env0 = env - lane;                                     // first env of this warp
+    const int nvalid = (int)min((int64_t)32, n - env0);                  // <= 0: idle warp
+    const bool live = env < n;
+    ObsT* tile = tiles + warp * (32 * D2_OBS);
+    uint32_t* g = G + tid;
+
+    uint4* cells = reinterpret_cast<uint4*>(st.cells);
+    const uint32_t* __restrict__ plans = reinterpret_cast<const uint32_t*>(st.plans);
+    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
+    if (live) {
+        v0 = cells[env];
+        v1 = cells[n + env];
+        v2 = cells[2 * n + env];
+        v3 = cells[3 * n + env];
+    }
+    g[0] = 0; g[B2] = 0;
+    g[2 * B2] = v0.x;  g[3 * B2] = v0.y;  g[4 * B2] = v0.z;  g[5 * B2] = v0.w;
+    g[6 * B2] = v1.x;  g[7 * B2] = v1.y;  g[8 * B2] = v1.z;  g[9 * B2] = v1.w;
+    g[10 * B2] = v2.x; g[11 * B2] = v2.y; g[12 * B2] = v2.z; g[13 * B2] = v2.w;
+    g[14 * B2] = v3.x;
+    g[15 * B2] = 0; g[16 * B2] = 0; g[17 * B2] = 0;
+    Env2 e;
+    unpack2(v3, e);
+    if (!live) { e.pr = e.pc = D2_LO; e.plan_idx = 0; }
+    int total_brick = __ldg(st.plan_total + e.plan_idx);
+    unsigned dirty = 0;                                                   // bit v: plane v must be written back
+    int errbits = 0;
+
+    const bool autoreset = io.flags & DMP_F_AUTORESET;
+    const bool normalise = io.flags & DMP_F_NORMALISE;
+    const bool need_draw = (io.actions == nullptr) || (io.step_sizes == nullptr);
+    const int tslot = (io.flags & DMP_F_TSLOT1) ? 1 : 0;
+    const uint64_t t0 = st.t_dev ? st.t_dev[tslot] : st.t;
+
+    for (int k = 0; k < K; ++k) {
+        const uint64_t t = t0 + (uint64_t)k;
+        const int64_t idx = (int64_t)k * n + env;
+        Draw d = Draw{0, 0, 0, 0};
+        if (need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
+        int a, s;
+        if (io.actions) a = live ? io.actions[idx] : 0; else a = draw_action(d, D2_ACT, st.action_dist);
+        if (io.step_sizes) s = live ? io.step_sizes[idx] : 1; else s = draw_step_size(d);
+        if ((unsigned)(s - 1) > 2u) errbits |= DMP_ERR_STEPSIZE;
+
+        // ---- step(): Env/2D/DMP_Env_2D_static.py:95-154 ------------------------------------
+        e.cs += 1;
+        float reward = 0.f;
+        bool done;
+        if (a < 4) {                                        // (a) move
+            stage_move2(e, a, s);
+            done = e.cs >= st.total_step;
+        } else if (a == 4) {                                // (b) drop + (d) reward
+            e.cb += 1;
+            int word; uint32_t bit;
+            const uint32_t was = stage_deposit2(g, e, word, bit);
+            dirty |= 1u << (word >> 2);
+            if (e.cb >= total_brick) {                      // :127-135 budget exhausted: reward 0.0
+                done = true;
+            } else {                                        // :137-147
+                done = e.cs >= st.total_step;
+                const uint32_t pw = __ldg(plans + e.plan_idx * PLAN2D_WORDS + word);
+                reward = (!was && (pw & bit)) ? 5.f : 0.f;  // pre-clip value == plan  <=> first brick on a plan cell
+            }
+        } else {                                            // reference: UnboundLocalError
+            errbits |= DMP_ERR_ACTION;
+            done = e.cs >= st.total_step;
+        }
+        e.ret += reward;
+
+        // ---- (c) observation ------------------------------------------------------------------
+        if (io.obs) {
+            stage_observe2<ObsT>(g, e, tile + lane * D2_OBS, normalise, total_brick, st.total_step);
+            __syncwarp();
+            if (nvalid > 0)
+                warp_tile_store<ObsT>(reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * D2_OBS,
+                                      tile, nvalid * D2_OBS, lane);
+            __syncwarp();
+        }
+        if (live) {
+            if (io.reward) io.reward[idx] = reward;
+            if (io.done) io.done[idx] = done ? 1 : 0;
+        }
+
+        // ---- (e) done / auto-reset ------------------------------------------------------------
+        if (done && autoreset && live) {
+            const double iou = iou2(g, plans + e.plan_idx * PLAN2D_WORDS);
+            st.ep_cnt[env] += 1;
+            st.ep_len[env] += (uint32_t)e.cs;
+            st.ep_ret[env] += (double)e.ret;
+            st.ep_iou[env] += iou;
+            if (io.next_plan) {
+                const int p = io.next_plan[idx];
+                if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
+            } else if (st.plan_mode == DMP_PLAN_PHILOX) {
+                if (!need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
+                e.plan_idx = draw_plan(d.x2, st.n_plans);
+            } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
+                e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
+            }
+            total_brick = __ldg(st.plan_total + e.plan_idx);
+#pragma unroll
+            for (int w = 0; w < GRID2D_WORDS; ++w) g[(S2_G0 + w) * B2] = 0;
+            e.pr = e.pc = D2_LO;
+            e.cb = e.cs = 0;
+            e.ret = 0.f;
+            dirty = 0xFu;
+        }
+    }
+
+    if (live) {
+        if (dirty & 1u) cells[env] = make_uint4(g[2 * B2], g[3 * B2], g[4 * B2], g[5 * B2]);
+        if (dirty & 2u) cells[n + env] = make_uint4(g[6 * B2], g[7 * B2], g[8 * B2], g[9 * B2]);
+        if (dirty & 4u) cells[2 * n + env] = make_uint4(g[10 * B2], g[11 * B2], g[12 * B2], g[13 * B2]);
+        pack2(e, g[14 * B2], v3);
+        cells[3 * n + env] = v3;
+        if (errbits) atomicOr(st.err, errbits);
+    }
+    if (st.t_dev && blockIdx.x == 0 && tid == 0) st.t_dev[tslot ^ 1] = t0 + (uint64_t)K;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reset / iou / export / import: thread per env, no shared memory
+// ---------------------------------------------------------------------------------------------
+template <typename ObsT>
+__global__ void k2d_reset(const DmpState st, const uint8_t* __restrict__ mask, const int32_t* __restrict__ plan_idx,
+                          const uint64_t t_draw, ObsT* __restrict__ obs) {
+    const int64_t n = st.n_envs;
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n || (mask && !mask[env])) return;
+    uint4* cells = reinterpret_cast<uint4*>(st.cells);
+    int p;
+    if (plan_idx) {
+        p = plan_idx[env];
+        if ((unsigned)p >= (unsigned)st.n_plans) { atomicOr(st.err, DMP_ERR_PLANIDX); p = 0; }
+    } else if (st.plan_mode == DMP_PLAN_PHILOX) {
+        p = draw_plan(env_draw(st.seed, (uint64_t)(st.env_base + env), t_draw).x3, st.n_plans);
+    } else {
+        p = (int)(cells[3 * n + env].y >> 16);
+        if (st.plan_mode == DMP_PLAN_SEQUENTIAL) p = (p + 1 >= st.n_plans) ? 0 : p + 1;
+        if ((unsigned)p >= (unsigned)st.n_plans) p = 0;
+    }
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    cells[env] = z; cells[n + env] = z; cells[2 * n + env] = z;
+    Env2 e{D2_LO, D2_LO, p, 0, 0, 0.f};
+    uint4 v3; pack2(e, 0u, v3);
+    cells[3 * n + env] = v3;
+    if (obs) {                       // window at [3,3] of an empty grid: rows/cols 0..2 are frame
+        ObsT* o = obs + env * D2_OBS;
+        for (int k = 0; k < 7; ++k)
+            for (int j = 0; j < 7; ++j) o[k * 7 + j] = obs_from_int<ObsT>((k < 3 || j < 3) ? -1 : 0);
+        o[49] = obs_from_int<ObsT>(0);
+        o[50] = obs_from_int<ObsT>(0);
+    }
+}
+
+__global__ void k2d_iou(const DmpState st, double* __restrict__ out) {
+    const int64_t n = st.n_envs;
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n) return;
+    const uint4* cells = reinterpret_cast<const uint4*>(st.cells);
+    const uint4 v[4] = {cells[env], cells[n + env], cells[2 * n + env], cells[3 * n + env]};
+    const uint32_t gw[13] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w,
+                             v[2].x, v[2].y, v[2].z, v[2].w, v[3].x};
+    const uint32_t* plan = reinterpret_cast<const uint32_t*>(st.plans) + (v[3].y >> 16) * PLAN2D_WORDS;
+    int inter = 0, uni = 0;
+#pragma unroll
+    for (int w = 0; w < 13; ++w) {
+        inter += __popc(gw[w] & plan[w]);
+        uni += __popc(gw[w] | plan[w]);
+    }
+    out[env] = __ddiv_rn((double)inter, (double)uni);
+}
+
+__global__ void k2d_export(const DmpState st, int32_t* __restrict__ grid, int32_t* __restrict__ scalars, float* __restrict__ ret) {
+    const int64_t n = st.n_envs;
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n) return;
+    const uint32_t* cw = reinterpret_cast<const uint32_t*>(st.cells);
+    auto word = [&](int w) { return cw[((int64_t)(w >> 2) * n + env) * 4 + (w & 3)]; };
+    if (grid) {
+        int32_t* g = grid + env * 676;
+        for (int r = 0; r < 26; ++r)
+            for (int c = 0; c < 26; ++c) {
+                int v = -1;
+                if (r >= 3 && r < 23 && c >= 3 && c < 23) {
+                    const int b = (r - 3) * 20 + (c - 3);
+                    v = (word(b >> 5) >> (b & 31)) & 1;
+                }
+                g[r * 26 + c] = v;
+            }
+    }
+    const uint32_t w13 = word(13), w14 = word(14);
+    if (scalars) {
+        int32_t* s = scalars + env * 8;
+        const int p = w13 >> 16;
+        s[0] = w13 & 0xFF; s[1] = (w13 >> 8) & 0xFF; s[2] = w14 & 0xFFFF; s[3] = w14 >> 16; s[4] = p;
+        s[5] = st.plan_total[p]; s[6] = 0; s[7] = 0;
+    }
+    if (ret) ret[env] = __uint_as_float(word(15));
+}
+
+__global__ void k2d_import(const DmpState st, const int32_t* __restrict__ grid, const int32_t* __restrict__ scalars,
+                           const float* __restrict__ ret) {
+    const int64_t n = st.n_envs;
+    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n) return;
+    uint32_t* cw = reinterpret_cast<uint32_t*>(st.cells);
+    auto wref = [&](int w) -> uint32_t& { return cw[((int64_t)(w >> 2) * n + env) * 4 + (w & 3)]; };
+    if (grid) {
+        const int32_t* g = grid + env * 676;
+        for (int w = 0; w < 13; ++w) {
+            uint32_t acc = 0;
+            for (int b = w * 32; b < w * 32 + 32 && b < 400; ++b)
+                if (g[(b / 20 + 3) * 26 + (b % 20 + 3)] > 0) acc |= 1u << (b & 31);
+            wref(w) = acc;
+        }
+    }
+    if (scalars) {
+        const int32_t* s = scalars + env * 8;
+        wref(13) = (uint32_t)s[0] | ((uint32_t)s[1] << 8) | ((uint32_t)s[4] << 16);
+        wref(14) = (uint32_t)(s[2] & 0xFFFF) | ((uint32_t)s[3] << 16);
+    }
+    if (ret) wref(15) = __float_as_uint(ret[env]);
+}
+
+template <typename ObsT>
+int launch_rollout2(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    const size_t smem = (size_t)S2_WORDS * B2 * 4 + (size_t)(B2 / 32) * 32 * D2_OBS * sizeof(ObsT);
+    static bool attr_done = false;           // per instantiation
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k2d_rollout<ObsT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return dmp_set_error(e);
+        attr_done = true;
+    }
+    const unsigned blocks = (unsigned)((st.n_envs + B2 - 1) / B2);
+    k2d_rollout<ObsT><<<blocks, B2, smem, s>>>(st, io, K);
+    return dmp_set_error(cudaGetLastError());
+}
+
+}  // namespace
+
+int dmp2d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    switch (io.obs_kind) {
+        case DMP_OBS_F32: return launch_rollout2<float>(st, io, K, s);
+        case DMP_OBS_F64: return launch_rollout2<double>(st, io, K, s);
+        case DMP_OBS_I16: return launch_rollout2<int16_t>(st, io, K, s);
+    }
+    return DMP_EINVAL;
+}
+
+int dmp2d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs,
+                int obs_kind, cudaStream_t s) {
+    const unsigned blocks = (unsigned)((st.n_envs + 255) / 256);
+    switch (obs_kind) {
+        case DMP_OBS_F32: k2d_reset<float><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (float*)obs); break;
+        case DMP_OBS_F64: k2d_reset<double><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (double*)obs); break;
+        case DMP_OBS_I16: k2d_reset<int16_t><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (int16_t*)obs); break;
+        default: return DMP_EINVAL;
+    }
+    return dmp_set_error(cudaGetLastError());
+}
+
+int dmp2d_iou(const DmpState& st, double* out, cudaStream_t s) {
+    k2d_iou<<<(unsigned)((st.n_envs + 255) / 256), 256, 0, s>>>(st, out);
+    return dmp_set_error(cudaGetLastError());
+}
+int dmp2d_export(const DmpState& st, int32_t* grid, int32_t* scalars, float* ret, cudaStream_t s) {
+    k2d_export<<<(unsigned)((st.n_envs + 127) / 128), 128, 0, s>>>(st, grid, scalars, ret);
+    return dmp_set_error(cudaGetLastError());
+}
+int dmp2d_import(const DmpState& st, const int32_t* grid, const int32_t* scalars, const float* ret, cudaStream_t s) {
+    k2d_import<<<(unsigned)((st.n_envs + 127) / 128), 128, 0, s>>>(st, grid, scalars, ret);
+    return dmp_set_error(cudaGetLastError());
+}

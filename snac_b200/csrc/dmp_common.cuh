@@ -1,0 +1,121 @@
+// dmp_common.cuh -- shared device helpers for libdmp.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "dmp.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libdmp is written for sm_100a (B200) only"
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// geometry (reference __init__ constants; see include/dmp.h for the citations)
+// ---------------------------------------------------------------------------------------------
+constexpr int D1_W = 30, D1_HW = 2, D1_OBS = 7, D1_ACT = 3, D1_LO = 2, D1_HI = 31;
+constexpr int D2_W = 20, D2_HW = 3, D2_OBS = 51, D2_ACT = 5, D2_LO = 3, D2_HI = 22;
+constexpr int D3_OBS = 51, D3_ACT = 8;
+constexpr int PLAN2D_WORDS = 16;     // 13 used
+constexpr int GRID2D_WORDS = 13;
+constexpr int PLAN1D_BYTES = 32;     // 30 used
+constexpr int CELLS3D = 400;
+
+constexpr uint64_t DMP_T_INIT = 0xFFFFFFFFFFFFFFFFull;
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (stream definition: oracle/philox.py)
+// ---------------------------------------------------------------------------------------------
+struct Draw { uint32_t x0, x1, x2, x3; };
+
+__device__ __forceinline__ Draw philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += W0; k1 += W1;
+    }
+    return Draw{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ Draw env_draw(uint64_t seed, uint64_t env_id, uint64_t t) {
+    return philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), (uint32_t)t, (uint32_t)(t >> 32),
+                         (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+__device__ __forceinline__ int draw_step_size(const Draw& d) { return 1 + (int)__umulhi(d.x0, 3u); }
+__device__ __forceinline__ int draw_action(const Draw& d, int n_actions, int dist) {
+    if (dist == DMP_ACT_REF3D) {
+        const int v = (int)__umulhi(d.x1, 20u);
+        return v < 16 ? (v >> 2) : (v - 12);
+    }
+    return (int)__umulhi(d.x1, (uint32_t)n_actions);
+}
+__device__ __forceinline__ int draw_plan(uint32_t x, int n_plans) { return (int)__umulhi(x, (uint32_t)n_plans); }
+
+// ---------------------------------------------------------------------------------------------
+// observation element conversion.  Every raw observation value of the reference is a small
+// integer held in float64; the normalised counters are an fp64 quotient.
+// ---------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T obs_from_int(int v);
+template <> __device__ __forceinline__ float   obs_from_int<float>(int v)   { return (float)v; }
+template <> __device__ __forceinline__ double  obs_from_int<double>(int v)  { return (double)v; }
+template <> __device__ __forceinline__ int16_t obs_from_int<int16_t>(int v) { return (int16_t)v; }
+
+template <typename T> __device__ __forceinline__ T obs_from_ratio(int num, int den);
+template <> __device__ __forceinline__ float   obs_from_ratio<float>(int n, int d)   { return (float)__ddiv_rn((double)n, (double)d); }
+template <> __device__ __forceinline__ double  obs_from_ratio<double>(int n, int d)  { return __ddiv_rn((double)n, (double)d); }
+template <> __device__ __forceinline__ int16_t obs_from_ratio<int16_t>(int n, int)   { return (int16_t)n; }
+
+// counters -> the two trailing obs columns
+template <typename T>
+__device__ __forceinline__ void obs_counters(bool normalise, int cb, int cs, int total_brick, int total_step, T& o_cb, T& o_cs) {
+    if (normalise) {
+        o_cb = obs_from_ratio<T>(cb, total_brick);
+        o_cs = obs_from_ratio<T>(cs, total_step);
+    } else {
+        o_cb = obs_from_int<T>(cb);
+        o_cs = obs_from_int<T>(cs);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp-tile copy-out: a warp has staged `n_elems` contiguous T elements in shared memory at
+// `tile`; stream them to `dst` (global) with 128-bit stores where the alignment allows.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void warp_tile_store(T* __restrict__ dst, const T* tile, int n_elems, int lane) {
+    constexpr int PER16 = 16 / (int)sizeof(T);
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        const int n16 = n_elems / PER16;
+        const uint4* s4 = reinterpret_cast<const uint4*>(tile);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        for (int i = lane; i < n16; i += 32) __stcs(d4 + i, s4[i]);       // streaming: obs is write-once
+        for (int i = n16 * PER16 + lane; i < n_elems; i += 32) dst[i] = tile[i];
+    } else {
+        for (int i = lane; i < n_elems; i += 32) dst[i] = tile[i];
+    }
+}
+
+// host-side helpers ---------------------------------------------------------------------------
+int dmp_set_error(cudaError_t e);   // records e, returns DMP_OK / DMP_ECUDA
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// per-dimension entry points (defined in dmp_1d.cu / dmp_2d.cu / dmp_3d.cu)
+int dmp1d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);
+int dmp2d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);
+int dmp3d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);
+int dmp1d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs, int obs_kind, cudaStream_t s);
+int dmp2d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs, int obs_kind, cudaStream_t s);
+int dmp3d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs, int obs_kind, cudaStream_t s);
+int dmp1d_iou(const DmpState& st, double* out, cudaStream_t s);
+int dmp2d_iou(const DmpState& st, double* out, cudaStream_t s);
+int dmp3d_iou(const DmpState& st, double* out, cudaStream_t s);
+int dmp1d_export(const DmpState& st, int32_t* grid, int32_t* scalars, float* ret, cudaStream_t s);
+int dmp2d_export(const DmpState& st, int32_t* grid, int32_t* scalars, float* ret, cudaStream_t s);
+int dmp3d_export(const DmpState& st, int32_t* grid, int32_t* scalars, float* ret, cudaStream_t s);
+int dmp1d_import(const DmpState& st, const int32_t* grid, const int32_t* scalars, const float* ret, cudaStream_t s);
+int dmp2d_import(const DmpState& st, const int32_t* grid, const int32_t* scalars, const float* ret, cudaStream_t s);
+int dmp3d_import(const DmpState& st, const int32_t* grid, const int32_t* scalars, const float* ret, cudaStream_t s);

@@ -1,0 +1,360 @@
+"""Device-resident vector environment for SNAC's mobile-construction tasks.
+
+``BatchedDMPEnv`` is the batched (tensor) form of the reference's gym-style surface
+``reset() -> obs`` / ``step(action) -> (obs, reward, done)`` (e.g. Env/2D/DMP_Env_2D_static.py:54,95)
+and replaces ``multiprocess.VectorizedEnvWrapper`` (multiprocess.py:15-32).  All state lives in
+PyTorch CUDA tensors laid out as described in include/dmp.h; every method is a thin wrapper over one
+C-ABI call into libdmp.so.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+_TORCH_OBS = {torch.float32: L.OBS_F32, torch.float64: L.OBS_F64, torch.int16: L.OBS_I16}
+
+# reference constants exposed as attributes (Env/*/…__init__)
+_SPEC = {
+    1: dict(plan_width=30, plan_height=20, HALF_WINDOW_SIZE=2, action_dim=3, state_dim=7),
+    2: dict(plan_width=20, plan_height=20, HALF_WINDOW_SIZE=3, action_dim=5, state_dim=51),
+    3: dict(plan_width=20, plan_height=20, HALF_WINDOW_SIZE=3, action_dim=8, state_dim=51, z=6, plan_length=10),
+}
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def load_plan_dataset(data_path: str, dim: int, key: Optional[str] = None) -> np.ndarray:
+    """Load a plan dataset in the reference's format: a joblib ``.pkl`` list of float64 arrays
+    (Env/*/data_*_envplan_500_*.pkl), or this repo's compact ``.npz`` re-encoding (``key`` selects
+    the array, see tests/golden/make_golden.py:pack_plans).  Returns float64 [n,30] / [n,26,26]."""
+    if data_path.endswith(".npz"):
+        z = np.load(data_path)
+        if key is None:
+            raise ValueError("npz plan files need key=, one of %s" % list(z.keys()))
+        a = z[key]
+        if dim == 1:
+            return a.astype(np.float64)
+        bits = np.unpackbits(a, axis=1)[:, :400].reshape(len(a), 20, 20).astype(np.float64)
+        out = np.zeros((len(a), 26, 26))
+        out[:, 3:23, 3:23] = bits * (6.0 if dim == 3 else 1.0)
+        return out
+    import joblib
+    return np.asarray(joblib.load(data_path), dtype=np.float64)
+
+
+class BatchedDMPEnv:
+    """N independent DMP environments on one GPU.
+
+    dim               1, 2 or 3
+    plan_choose       static plan selector (1D: 0 sine / 1 Gaussian / 2 step; 2D, 3D: 0 dense / 1 sparse)
+    plans             dynamic envs: float64 array of plans in the reference's format ([n,30] or [n,26,26])
+    random_choose_paln  (sic, reference spelling) True: random plan per reset; False: sequential with wrap
+    auto_reset        fold finished episodes into the per-env statistics and reset them inside step()
+    obs_dtype         torch.float32 (default), torch.float64 (the reference's dtype) or torch.int16
+    normalise         emit the dynamic classes' normalised counter columns (default: False = raw counters)
+    env_base          global index of env 0 (multi-GPU sharding; keeps Philox streams shard-independent)
+    """
+
+    def __init__(self, dim: int, *, dynamic: bool = False, plan_choose: int = 0,
+                 plans: Optional[np.ndarray] = None, num_envs: int = 1, device="cuda",
+                 random_choose_paln: bool = True, auto_reset: bool = False,
+                 obs_dtype: torch.dtype = torch.float32, normalise: bool = False,
+                 seed: int = L.SEED_DEFAULT, env_base: int = 0, action_dist: str = "uniform",
+                 total_step: Optional[int] = None):
+        if dim not in (1, 2, 3):
+            raise ValueError("dim must be 1, 2 or 3")
+        if obs_dtype not in _TORCH_OBS:
+            raise ValueError("obs_dtype must be float32, float64 or int16")
+        if normalise and obs_dtype == torch.int16:
+            raise ValueError("normalised counters need a floating obs_dtype")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("snac_b200 has no CPU path; device must be a CUDA device")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dim, self.dynamic = dim, bool(dynamic)
+        self.num_envs = int(num_envs)
+        self.auto_reset = bool(auto_reset)
+        self.obs_dtype, self.normalise = obs_dtype, bool(normalise)
+        for k, v in _SPEC[dim].items():
+            setattr(self, k, v)
+        lay = L.DmpLayout()
+        L.check(L.lib.dmp_layout(dim, self.num_envs, C.byref(lay)), "dmp_layout")
+        self._lay = lay
+        self.total_step = int(total_step) if total_step is not None else (
+            lay.total_step_dynamic if self.dynamic else lay.total_step_static)
+        self.environment_width = self.plan_width + 2 * self.HALF_WINDOW_SIZE
+        self.plan_choose = plan_choose
+
+        dev, n = self.device, self.num_envs
+        with torch.cuda.device(dev):
+            u8 = dict(dtype=torch.uint8, device=dev)
+            self._cells = torch.zeros(lay.cells_bytes, **u8)
+            self._aux = torch.zeros(max(lay.aux_bytes, 16), **u8)
+            self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._ep_cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+            self._ep_len = torch.zeros(n, dtype=torch.int32, device=dev)
+            self._ep_ret = torch.zeros(n, dtype=torch.float64, device=dev)
+            self._ep_iou = torch.zeros(n, dtype=torch.float64, device=dev)
+            self._t_dev = torch.zeros(2, dtype=torch.int64, device=dev)
+            self._stats = torch.zeros(4, dtype=torch.float64, device=dev)
+            self._stats_scratch = torch.zeros(int(L.lib.dmp_stats_scratch_bytes(n)), **u8)
+            # ---- plan table -----------------------------------------------------------------
+            if self.dynamic:
+                if plans is None:
+                    raise ValueError("dynamic envs need plans= (see load_plan_dataset)")
+                raw = torch.as_tensor(np.ascontiguousarray(plans, dtype=np.float64), device=dev)
+                want = (30,) if dim == 1 else (26, 26)
+                if tuple(raw.shape[1:]) != want:
+                    raise ValueError("plans must have shape [n,%s]" % ",".join(map(str, want)))
+                self.n_plans = int(raw.shape[0])
+                self._plans = torch.zeros(self.n_plans * lay.plan_row_bytes, **u8)
+                self._plan_total = torch.zeros(self.n_plans, dtype=torch.int32, device=dev)
+                L.check(L.lib.dmp_plans_pack(dim, raw.data_ptr(), self.n_plans, self._plans.data_ptr(),
+                                             self._plan_total.data_ptr(), self._stream()), "dmp_plans_pack")
+                self._plans_raw = raw
+            else:
+                self.n_plans = 1
+                self._plans = torch.zeros(lay.plan_row_bytes, **u8)
+                self._plan_total = torch.zeros(1, dtype=torch.int32, device=dev)
+                rc = L.lib.dmp_plan_static(dim, int(plan_choose), self._plans.data_ptr(),
+                                           self._plan_total.data_ptr(), self._stream())
+                if rc == L.EINVAL:       # the reference raises at reset(); we raise at construction
+                    raise ValueError('0: Sin, 1: Gaussian, 2: Step' if dim == 1 else '0: Dense circle, 1: Sparse circle')
+                L.check(rc, "dmp_plan_static")
+                self._plans_raw = None
+            # ---- output buffers (reused by step(); rollout() allocates [K,...] on demand) -----
+            D = lay.obs_dim
+            self._obs = torch.zeros((n, D), dtype=obs_dtype, device=dev)
+            self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
+            self._done = torch.zeros(n, dtype=torch.uint8, device=dev)
+
+        st = L.DmpState()
+        st.dim, st.dynamic, st.n_plans, st.total_step = dim, int(self.dynamic), self.n_plans, self.total_step
+        st.plan_mode = (L.PLAN_KEEP if not self.dynamic else
+                        (L.PLAN_PHILOX if random_choose_paln else L.PLAN_SEQUENTIAL))
+        st.action_dist = {"uniform": L.ACT_UNIFORM, "ref3d": L.ACT_REF3D}[action_dist]
+        st.n_envs, st.env_base, st.seed, st.t = n, int(env_base), int(seed), 0
+        st.t_dev = None
+        st.cells, st.aux = self._cells.data_ptr(), self._aux.data_ptr()
+        st.plans, st.plan_total = self._plans.data_ptr(), self._plan_total.data_ptr()
+        st.ep_cnt, st.ep_len = self._ep_cnt.data_ptr(), self._ep_len.data_ptr()
+        st.ep_ret, st.ep_iou = self._ep_ret.data_ptr(), self._ep_iou.data_ptr()
+        st.err = self._err.data_ptr()
+        self._st = st
+        self.random_choose_paln = bool(random_choose_paln)
+        self._needs_initial_reset = True
+
+    # ------------------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @property
+    def obs_dim(self) -> int:
+        return self._lay.obs_dim
+
+    @property
+    def t(self) -> int:
+        return int(self._st.t)
+
+    def _flags(self) -> int:
+        return (L.F_AUTORESET if self.auto_reset else 0) | (L.F_NORMALISE if self.normalise else 0)
+
+    def _u8(self, x, shape, what) -> torch.Tensor:
+        if not torch.is_tensor(x):
+            x = torch.as_tensor(np.asarray(x), device=self.device)
+        if x.device != self.device:
+            x = x.to(self.device, non_blocking=True)
+        if x.dtype != torch.uint8:
+            x = x.to(torch.uint8)
+        if tuple(x.shape) != tuple(shape):
+            raise ValueError("%s must have shape %s, got %s" % (what, tuple(shape), tuple(x.shape)))
+        return x.contiguous()
+
+    def _i32(self, x, shape, what) -> torch.Tensor:
+        if not torch.is_tensor(x):
+            x = torch.as_tensor(np.asarray(x), device=self.device)
+        x = x.to(device=self.device, dtype=torch.int32)
+        if tuple(x.shape) != tuple(shape):
+            raise ValueError("%s must have shape %s, got %s" % (what, tuple(shape), tuple(x.shape)))
+        return x.contiguous()
+
+    # ------------------------------------------------------------------------------------------
+    def reset(self, mask=None, plan_idx=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Reset all envs (or those with mask != 0).  Returns the observation buffer [N, D]
+        (rows of envs that were not reset keep their previous content).
+        Dynamic envs: ``plan_idx`` (int32 [N]) injects the reference's ``index_random`` draw
+        (Env/2D/DMP_Env_2D_dynamic_usedata_plan.py:36); default is a Philox draw, or -- with
+        random_choose_paln=False -- plan 0 on the first reset and +1 (wrapping) afterwards."""
+        n = self.num_envs
+        m = None if mask is None else self._u8(mask, (n,), "mask")
+        p = None if plan_idx is None else self._i32(plan_idx, (n,), "plan_idx")
+        if p is None and self._needs_initial_reset and self.dynamic and not self.random_choose_paln:
+            p = torch.zeros(n, dtype=torch.int32, device=self.device)      # index_for_non_random = 0
+        obs = self._obs if out is None else out
+        with torch.cuda.device(self.device):
+            L.check(L.lib.dmp_reset(C.byref(self._st), _ptr(m), _ptr(p), C.c_uint64(L.T_INIT - self._st.t),
+                                    obs.data_ptr(), _TORCH_OBS[obs.dtype], self._stream()), "dmp_reset")
+        if mask is None:
+            self._needs_initial_reset = False
+        self._keep = (m, p)
+        return obs
+
+    def reset_at(self, env_index: int) -> torch.Tensor:
+        """multiprocess.py:22-23 -- reset one env, return its observation row [D]."""
+        m = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+        m[env_index] = 1
+        return self.reset(mask=m)[env_index]
+
+    def step(self, actions, step_sizes=None, next_plan=None):
+        """One step of every env.  ``actions`` uint8 [N] (None: Philox synthetic actions).
+        ``step_sizes`` uint8 [N] in {1,2,3} injects the reference's ``np.random.randint(1, 4)``
+        draw (the *_hindsight_replay ``step(action, step_size)`` form); None = Philox.
+        Returns (obs [N,D], reward f32 [N], done bool [N]) -- views of internal buffers that the
+        next call overwrites."""
+        obs, rew, done = self.rollout(1, actions=None if actions is None else self._u8(actions, (self.num_envs,), "actions")[None],
+                                      step_sizes=None if step_sizes is None else self._u8(step_sizes, (self.num_envs,), "step_sizes")[None],
+                                      next_plan=None if next_plan is None else self._i32(next_plan, (self.num_envs,), "next_plan")[None],
+                                      out=(self._obs[None], self._reward[None], self._done[None]))
+        return obs[0], rew[0], done[0]
+
+    def rollout(self, K: int, actions=None, step_sizes=None, next_plan=None, out=None,
+                materialise_obs: bool = True, use_device_t: bool = False, t_slot: int = 0):
+        """Advance every env K steps in ONE kernel launch (state stays on chip between steps).
+        actions / step_sizes: uint8 [K,N] or None (Philox).  Returns (obs [K,N,D], reward [K,N], done [K,N])."""
+        n, D = self.num_envs, self._lay.obs_dim
+        if self._needs_initial_reset:
+            raise RuntimeError("call reset() before step()/rollout()")
+        a = None if actions is None else self._u8(actions, (K, n), "actions")
+        s = None if step_sizes is None else self._u8(step_sizes, (K, n), "step_sizes")
+        p = None if next_plan is None else self._i32(next_plan, (K, n), "next_plan")
+        if out is None:
+            obs = torch.empty((K, n, D), dtype=self.obs_dtype, device=self.device) if materialise_obs else None
+            rew = torch.empty((K, n), dtype=torch.float32, device=self.device)
+            done = torch.empty((K, n), dtype=torch.uint8, device=self.device)
+        else:
+            obs, rew, done = out
+        io = L.DmpIO()
+        io.actions, io.step_sizes, io.next_plan = _ptr(a), _ptr(s), _ptr(p)
+        io.obs, io.reward, io.done = _ptr(obs), _ptr(rew), _ptr(done)
+        io.obs_kind = _TORCH_OBS[self.obs_dtype if obs is None else obs.dtype]
+        io.flags = self._flags() | (L.F_TSLOT1 if (use_device_t and t_slot) else 0)
+        self._st.t_dev = self._t_dev.data_ptr() if use_device_t else None
+        with torch.cuda.device(self.device):
+            L.check(L.lib.dmp_rollout(C.byref(self._st), C.byref(io), int(K), self._stream()), "dmp_rollout")
+        if not use_device_t:
+            self._st.t = self._st.t + K
+        self._keep_io = (a, s, p)
+        return obs, rew, (None if done is None else done.view(torch.bool))
+
+    # ------------------------------------------------------------------------------------------
+    def iou(self) -> torch.Tensor:
+        """Per-env IoU of the current grid vs. its plan, float64 [N]
+        (Env/1D/DMP_Env_1D_static.py:138-151, Env/2D/DMP_Env_2D_static.py:169-175,
+        Env/3D/DMP_simulator_3d_static_circle.py:257-276)."""
+        out = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(L.lib.dmp_iou(C.byref(self._st), out.data_ptr(), self._stream()), "dmp_iou")
+        return out
+
+    def stats(self, allreduce: bool = False) -> torch.Tensor:
+        """float64 [4] = (sum of episode returns, sum of final IoUs, episodes, steps) over the finished
+        episodes of this shard; ``allreduce=True`` sums it over all ranks (NCCL over NVLink)."""
+        with torch.cuda.device(self.device):
+            L.check(L.lib.dmp_stats_reduce(C.byref(self._st), self._stats.data_ptr(),
+                                           self._stats_scratch.data_ptr(), self._stream()), "dmp_stats_reduce")
+        if allreduce:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(self._stats, op=dist.ReduceOp.SUM)
+        return self._stats
+
+    def clear_stats(self) -> None:
+        with torch.cuda.device(self.device):
+            L.check(L.lib.dmp_stats_clear(C.byref(self._st), self._stream()), "dmp_stats_clear")
+
+    def episode_stats(self):
+        """Per-env (episodes, total length, sum of returns, sum of IoUs) tensors."""
+        return self._ep_cnt, self._ep_len, self._ep_ret, self._ep_iou
+
+    def errors(self) -> int:
+        """OR of DMP_ERR_* bits latched by the kernels so far (synchronises)."""
+        return int(self._err.item())
+
+    def check_errors(self) -> None:
+        e = self.errors()
+        if e & L.ERR_ACTION:
+            raise UnboundLocalError("an action outside the env's action set was stepped "
+                                    "(the reference leaves 'position' unbound, Env/1D/DMP_Env_1D_static.py:130-133)")
+        if e:
+            raise ValueError("libdmp latched error bits 0x%x" % e)
+
+    # ------------------------------------------------------------------------------------------
+    def export_state(self) -> dict:
+        """Dense copy of the state in the reference's own shapes (device tensors):
+        grid int32 [N,34] / [N,26,26] (environment_memory, -1 frame), scalars int32 [N,8]
+        (pos_row|pos, pos_col, count_brick, count_step, plan_idx, total_brick, 0, 0), ret f32 [N]."""
+        n, lay = self.num_envs, self._lay
+        grid = torch.empty((n, lay.grid_rows, lay.grid_cols), dtype=torch.int32, device=self.device)
+        sc = torch.empty((n, 8), dtype=torch.int32, device=self.device)
+        ret = torch.empty(n, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(L.lib.dmp_export_state(C.byref(self._st), grid.data_ptr(), sc.data_ptr(), ret.data_ptr(),
+                                           self._stream()), "dmp_export_state")
+        if self.dim == 1:
+            grid = grid.reshape(n, 1, lay.grid_cols)
+        return dict(grid=grid, scalars=sc, ret=ret)
+
+    def import_state(self, grid=None, scalars=None, ret=None) -> None:
+        """Inverse of export_state (any subset)."""
+        n, lay = self.num_envs, self._lay
+        g = None if grid is None else self._i32(torch.as_tensor(grid).reshape(n, lay.grid_rows, lay.grid_cols),
+                                                (n, lay.grid_rows, lay.grid_cols), "grid")
+        s = None if scalars is None else self._i32(scalars, (n, 8), "scalars")
+        r = None if ret is None else torch.as_tensor(ret, dtype=torch.float32, device=self.device).contiguous()
+        with torch.cuda.device(self.device):
+            L.check(L.lib.dmp_import_state(C.byref(self._st), _ptr(g), _ptr(s), _ptr(r), self._stream()),
+                    "dmp_import_state")
+        self._needs_initial_reset = False
+
+    def get_state(self) -> dict:
+        """Raw SoA snapshot (cheap clone of the packed tensors) -- the MCTS variants' state tuple
+        (Env/1D/DMP_Env_1D_static_MCTS.py:87) in batched form."""
+        return dict(cells=self._cells.clone(), aux=self._aux.clone(), t=int(self._st.t),
+                    ep=(self._ep_cnt.clone(), self._ep_len.clone(), self._ep_ret.clone(), self._ep_iou.clone()))
+
+    def set_state(self, state: dict) -> None:
+        self._cells.copy_(state["cells"])
+        self._aux.copy_(state["aux"])
+        self._st.t = int(state["t"])
+        for dst, src in zip((self._ep_cnt, self._ep_len, self._ep_ret, self._ep_iou), state["ep"]):
+            dst.copy_(src)
+        self._needs_initial_reset = False
+
+    # plan views ----------------------------------------------------------------------------------
+    def plan_table(self) -> torch.Tensor:
+        """The packed plan table as uploaded (uint8 view; layout in include/dmp.h)."""
+        return self._plans.view(self.n_plans, -1)
+
+    def plan_totals(self) -> torch.Tensor:
+        return self._plan_total
+
+    def plans_dense(self) -> np.ndarray:
+        """Plans in the reference's array format (float64 [n_plans,30] or [n_plans,26,26])."""
+        tab = self.plan_table().cpu().numpy()
+        if self.dim == 1:
+            return tab[:, :30].astype(np.float64)
+        out = np.zeros((self.n_plans, 26, 26))
+        if self.dim == 2:
+            bits = np.unpackbits(tab[:, :52].copy(), axis=1, bitorder="little")[:, :400]
+            out[:, 3:23, 3:23] = bits.reshape(-1, 20, 20)
+        else:
+            out[:, 3:23, 3:23] = tab[:, :400].reshape(-1, 20, 20)
+        return out

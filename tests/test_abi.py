@@ -1,0 +1,62 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/dmp.h declares."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "dmp.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"^\s*(?:int|int64_t)\s+(dmp_\w+)\s*\(", src, flags=re.M)))
+
+
+def test_header_symbols_exported():
+    names = declared_functions()
+    assert len(names) >= 19, names
+    lib = ctypes.CDLL(os.path.join(ROOT, "snac_b200", "libdmp.so"))
+    for n in names:
+        assert hasattr(lib, n), "libdmp.so does not export %s" % n
+
+
+def test_python_binding_covers_header():
+    from snac_b200 import _lib
+    assert sorted(_lib.EXPORTS) == declared_functions()
+    assert _lib.lib.dmp_abi_version() == _lib.ABI_VERSION
+
+
+def test_layout_and_argument_checks_without_gpu():
+    from snac_b200 import _lib as L
+    lay = L.DmpLayout()
+    assert L.lib.dmp_layout(1, 10, ctypes.byref(lay)) == L.OK
+    assert (lay.cells_bytes, lay.aux_bytes, lay.obs_dim, lay.n_actions, lay.grid_cols) == (640, 80, 7, 3, 34)
+    assert L.lib.dmp_layout(2, 10, ctypes.byref(lay)) == L.OK
+    assert (lay.cells_bytes, lay.aux_bytes, lay.obs_dim, lay.n_actions) == (640, 0, 51, 5)
+    assert L.lib.dmp_layout(3, 10, ctypes.byref(lay)) == L.OK
+    assert (lay.cells_bytes, lay.aux_bytes, lay.obs_dim, lay.n_actions) == (8000, 160, 51, 8)
+    assert (lay.total_step_static, lay.total_step_dynamic) == (1300, 1000)
+    assert L.lib.dmp_layout(4, 10, ctypes.byref(lay)) == L.EINVAL
+    # argument validation happens before any CUDA call
+    assert L.lib.dmp_plan_static(2, 2, 1, 1, None) == L.EINVAL          # reference: ValueError at reset()
+    assert L.lib.dmp_plan_static(1, 3, 1, 1, None) == L.EINVAL
+    st = L.DmpState()
+    assert L.lib.dmp_rollout(ctypes.byref(st), None, 1, None) == L.EINVAL
+    assert L.lib.dmp_stats_scratch_bytes(1 << 20) == 1024 * 32
+
+
+def test_struct_sizes_match_header():
+    """ctypes mirrors of the C structs (field order and padding)."""
+    from snac_b200 import _lib as L
+    assert ctypes.sizeof(L.DmpIO) == 6 * 8 + 8
+    assert ctypes.sizeof(L.DmpState) == 6 * 4 + 5 * 8 + 9 * 8
+    assert ctypes.sizeof(L.DmpLayout) == 3 * 8 + 6 * 4
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "snac_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f

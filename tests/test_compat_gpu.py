@@ -1,0 +1,125 @@
+"""The reference-facing classes (snac_b200.compat) replay the reference's golden traces when driven
+exactly like the reference: np.random.seed(s); env.reset(); env.step(a) -- same global-RNG draws."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TRACE_NAMES, load_plans, load_trace
+
+pytestmark = pytest.mark.gpu
+
+
+def make_compat(meta):
+    import snac_b200 as S
+    dim, kind, kw = meta["dim"], meta["kind"], meta["kw"]
+    if kind == "static":
+        cls = {"1D": S.deep_mobile_printing_1d1r, "2D": S.deep_mobile_printing_2d1r, "3D": S.deep_mobile_printing_3d1r}[dim]
+        return cls(plan_choose=kw["plan_choose"])
+    cls = {"1D": S.deep_mobile_printing_1d1r_dynamic, "2D": S.deep_mobile_printing_2d1r_dynamic,
+           "3D": S.deep_mobile_printing_3d1r_dynamic}[dim]
+    return cls(plans=load_plans(int(dim[0]), kw["density"], kw["split"]))
+
+
+@pytest.mark.parametrize("name", [n for n in TRACE_NAMES if "dropheavy" not in n and "refp" not in n])
+def test_scalar_classes_follow_global_numpy_rng(name):
+    tr = load_trace(name)
+    meta = tr["meta"]
+    dyn = meta["kind"] == "dynamic"
+    dim = meta["dim"]
+    env = make_compat(meta)
+    np.random.seed(meta["seed"])
+    rng = np.random.RandomState(meta["seed"] + 1)
+    ri = 0
+    o = env.reset()
+    if dyn:
+        assert env.index_random == tr["reset_plan_idx"][ri]
+    T = 700
+    for t in range(T):
+        a = int(rng.randint(env.action_dim))
+        assert a == tr["actions"][t]
+        o, r, d = env.step(a)
+        assert env.step_size == tr["step_sizes"][t]
+        raw = o if not dyn else (o[0] if dim == "1D" else None)
+        if raw is not None:
+            assert raw.dtype == np.float64 and raw.shape == (1, env.state_dim)
+            assert np.array_equal(raw[0], tr["obs"][t].astype(np.float64)), t
+        if dyn:
+            nrm = o[1] if dim == "1D" else o[0]
+            assert np.array_equal(nrm[0, :-2], tr["obs"][t, :-2].astype(np.float64))
+            assert np.array_equal(nrm[0, -2:], tr["obs_norm"][t]), (t, nrm[0, -2:], tr["obs_norm"][t])
+            if dim != "1D":
+                assert list(o[2]) == list(tr["pos"][t]) and o[1].shape == (20, 20)
+        assert r == tr["reward"][t] and isinstance(r, int) == bool(tr["reward_is_int"][t]), (t, r)
+        assert d == bool(tr["done"][t]) and isinstance(d, bool)
+        assert env.count_step == tr["count_step"][t] and env.count_brick == tr["count_brick"][t]
+        assert env.total_brick == tr["total_brick"][t]
+        if dim == "1D":
+            assert env.conut_brick == env.count_brick and env.position_memory[-1] == tr["pos"][t][0]
+        else:
+            assert list(env.position_memory[-1]) == list(tr["pos"][t])
+        if t % 50 == 0 and dim != "2D":
+            assert env.iou() == tr["iou"][t] or np.isnan(tr["iou"][t])
+        if d:
+            ri += 1
+            env.reset()
+            if dyn:
+                assert env.index_random == tr["reset_plan_idx"][ri]
+
+
+def test_vectorized_wrapper_shapes_like_multiprocess_py():
+    """multiprocess.py:78-87 prints (N,1,D), (N,), (N,) -- SURVEY.md 3.1."""
+    import snac_b200 as S
+    for cls, D in ((S.deep_mobile_printing_1d1r, 7), (S.deep_mobile_printing_2d1r, 51), (S.deep_mobile_printing_3d1r, 51)):
+        env = S.VectorizedEnvWrapper(cls(plan_choose=0), num_envs=5)
+        o = env.reset()
+        assert o.shape == (5, 1, D) and o.dtype == np.float64
+        for _ in range(20):
+            o, r, d = env.step(np.random.randint(3, size=5))
+        assert o.shape == (5, 1, D) and r.shape == (5,) and d.shape == (5,) and d.dtype == bool
+        one = env.reset_at(2)
+        assert one.shape == (1, D)
+
+
+def test_vectorized_wrapper_equals_independent_reference_style_envs():
+    """N wrapper envs == N independent scalar envs fed the same per-env step sizes (App. C.6)."""
+    import snac_b200 as S
+    from oracle import dmp_oracle as O
+    n = 7
+    env = S.VectorizedEnvWrapper(S.deep_mobile_printing_2d1r(plan_choose=1), num_envs=n)
+    orcs = [O.make_env(2, False, plan_choose=1) for _ in range(n)]
+    np.random.seed(11)
+    o = env.reset()
+    for i, e in enumerate(orcs):
+        assert np.array_equal(o[i], e.reset())
+    rng = np.random.RandomState(5)
+    for t in range(300):
+        acts = rng.randint(5, size=n)
+        state = np.random.get_state()
+        sizes = np.random.randint(1, 4, size=n)
+        np.random.set_state(state)
+        o, r, d = env.step(acts)
+        for i, e in enumerate(orcs):
+            oo, rr, dd = e.step(int(acts[i]), int(sizes[i]))
+            assert np.array_equal(o[i], oo) and r[i] == rr and d[i] == dd
+            if dd:
+                e.reset()
+                env.reset_at(i)
+
+
+def test_multiprocess_cli_config1():
+    """BASELINE config 1: --env 1DStatic --plan_type 2 --num_envs 5."""
+    from snac_b200.compat import main
+    o, r, d = main(["--env", "1DStatic", "--plan_type", "2", "--num_envs", "5"])
+    assert o.shape == (5, 1, 7) and r.shape == (5,) and d.shape == (5,)
+    assert main([]) is None and main(["--env", "2DStatic"]) is None
+
+
+def test_invalid_action_raises_unboundlocalerror():
+    import snac_b200 as S
+    env = S.deep_mobile_printing_2d1r(plan_choose=0)
+    env.reset()
+    with pytest.raises(UnboundLocalError):
+        env.step(5)
+    assert env.count_step == 1          # the reference increments before it fails
+    o, r, d = env.step(4)
+    assert r == 5.0 or r == 0

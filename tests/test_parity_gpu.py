@@ -1,0 +1,230 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden traces.
+Bit-exact: grids, positions, counters, observations, done flags, rewards (small integers in f32).
+IoU / normalised counters: IEEE fp64 division on both sides -> compared exactly, with a 1e-6
+relative fallback stated in BASELINE.json's north_star."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TRACE_NAMES, load_plans, load_trace, trace_env_spec
+from oracle import dmp_oracle as O
+from oracle import philox
+from oracle_batch import OracleBatch, philox_rollout
+
+pytestmark = pytest.mark.gpu
+
+SEED = 0x534E4143
+
+
+def make_gpu(dim, dynamic, n, plan_choose=0, plans=None, **kw):
+    from snac_b200.vecenv import BatchedDMPEnv
+    return BatchedDMPEnv(dim, dynamic=dynamic, plan_choose=plan_choose, plans=plans, num_envs=n, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# 1. golden traces of the unmodified reference, replayed step by step (caller-side reset, N = 1)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", TRACE_NAMES)
+def test_reference_trace_step_mode(name):
+    tr = load_trace(name)
+    dim, dynamic, plan_choose, plans = trace_env_spec(tr["meta"])
+    env = make_gpu(dim, dynamic, 1, plan_choose, plans, obs_dtype=torch.float64)
+    resets = tr["reset_plan_idx"]
+    ri = 0
+    o = env.reset(plan_idx=[resets[ri]])
+    assert np.array_equal(o.cpu().numpy()[0], tr["reset_obs"][ri].astype(np.float64))
+    T = min(len(tr["actions"]), 1200)
+    ep = 0
+    for t in range(T):
+        o, r, d = env.step([tr["actions"][t]], [tr["step_sizes"][t]])
+        o, r, d = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy()
+        assert o.dtype == np.float64
+        assert np.array_equal(o[0], tr["obs"][t].astype(np.float64)), (t, o[0], tr["obs"][t])
+        assert r[0] == tr["reward"][t], (t, r, tr["reward"][t])
+        assert bool(d[0]) == bool(tr["done"][t]), t
+        if t % 97 == 0 or d[0]:
+            iou = env.iou().cpu().numpy()[0]
+            assert iou == tr["iou"][t] or (np.isnan(iou) and np.isnan(tr["iou"][t])), (t, iou, tr["iou"][t])
+            st = env.export_state()
+            sc = st["scalars"].cpu().numpy()[0]
+            assert list(sc[:2]) == list(tr["pos"][t]) and sc[2] == tr["count_brick"][t] and sc[3] == tr["count_step"][t]
+            assert sc[5] == tr["total_brick"][t]
+        if d[0]:
+            g = env.export_state()["grid"].cpu().numpy()[0]
+            assert np.array_equal(g.reshape(tr["final_grids"][ep].shape), tr["final_grids"][ep])
+            ep += 1
+            ri += 1
+            o = env.reset(plan_idx=[resets[ri]])
+            assert np.array_equal(o.cpu().numpy()[0], tr["reset_obs"][ri].astype(np.float64))
+    env.check_errors()
+
+
+# ------------------------------------------------------------------------------------------------
+# 2. the same traces in ONE rollout launch with in-kernel auto-reset (K = T), all obs dtypes
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", TRACE_NAMES)
+@pytest.mark.parametrize("obs_dtype", [torch.float32, torch.int16, torch.float64])
+def test_reference_trace_rollout_mode(name, obs_dtype):
+    tr = load_trace(name)
+    dim, dynamic, plan_choose, plans = trace_env_spec(tr["meta"])
+    env = make_gpu(dim, dynamic, 1, plan_choose, plans, obs_dtype=obs_dtype, auto_reset=True)
+    T = len(tr["actions"])
+    resets = tr["reset_plan_idx"]
+    nxt = np.zeros((T, 1), np.int32)
+    nd = np.cumsum(tr["done"])                      # number of dones up to and including t
+    for t in range(T):
+        if tr["done"][t]:
+            nxt[t, 0] = resets[nd[t]]
+    env.reset(plan_idx=[resets[0]])
+    obs, rew, done = env.rollout(T, actions=tr["actions"][:, None], step_sizes=tr["step_sizes"][:, None], next_plan=nxt)
+    obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+    assert np.array_equal(obs[:, 0, :].astype(np.float64), tr["obs"].astype(np.float64))
+    assert np.array_equal(rew[:, 0].astype(np.float64), tr["reward"])
+    assert np.array_equal(done[:, 0], tr["done"])
+    # per-env episode statistics == what the reference trace implies
+    cnt, ln, ret, iou = [x.cpu().numpy() for x in env.episode_stats()]
+    n_ep = int(tr["done"].sum())
+    assert cnt[0] == n_ep
+    ends = np.nonzero(tr["done"])[0]
+    assert ln[0] == int(tr["count_step"][ends].sum())
+    starts = np.concatenate([[0], ends[:-1] + 1])
+    want_ret = sum(tr["reward"][s:e + 1].sum() for s, e in zip(starts, ends))
+    assert ret[0] == want_ret
+    want_iou = 0.0
+    for e in ends:
+        want_iou += tr["iou"][e]
+    if np.isnan(want_iou):
+        assert np.isnan(iou[0])
+    else:
+        assert iou[0] == want_iou
+    g = env.export_state()["grid"].cpu().numpy()[0]
+    assert np.array_equal(g.reshape(tr["final_grids"][-1].shape), tr["final_grids"][-1])
+    stats = env.stats().cpu().numpy()
+    assert stats[2] == n_ep and stats[3] == ln[0] and stats[0] == want_ret
+    env.check_errors()
+
+
+# ------------------------------------------------------------------------------------------------
+# 3. vector runs with in-kernel Philox draws vs N independent oracle envs
+# ------------------------------------------------------------------------------------------------
+CASES = [
+    # dim, dynamic, plan_choose, density, ref3d, n, K
+    (1, False, 2, None, False, 200, 800),
+    (1, True, 0, "dense", False, 200, 800),
+    (2, False, 0, None, False, 200, 700),
+    (2, False, 1, None, False, 131, 400),
+    (2, True, 0, "dense", False, 200, 700),
+    (2, True, 0, "sparse", False, 97, 400),
+    (3, False, 0, None, False, 150, 300),
+    (3, False, 1, None, True, 100, 1400),
+    (3, True, 0, "dense", False, 150, 300),
+    (3, True, 0, "sparse", True, 100, 1100),
+]
+
+
+@pytest.mark.parametrize("dim,dynamic,plan_choose,density,ref3d,n,K", CASES)
+def test_philox_vector_rollout_matches_oracle(dim, dynamic, plan_choose, density, ref3d, n, K):
+    plans = load_plans(dim, density, "train") if dynamic else None
+    env_base = 12345
+    env = make_gpu(dim, dynamic, n, plan_choose, plans, auto_reset=True, env_base=env_base, seed=SEED,
+                   action_dist="ref3d" if ref3d else "uniform", normalise=dynamic, obs_dtype=torch.float64)
+    ob = OracleBatch(dim, dynamic, n, plan_choose, plans)
+    # initial reset: Philox plan draw on the device, replayed on the host
+    p0 = philox.reset_draw(SEED, np.arange(env_base, env_base + n), 0, ob.n_plans) if dynamic else None
+    o_gpu = env.reset().cpu().numpy()
+    o_ref = ob.reset(p0)
+    assert np.array_equal(o_gpu, o_ref)
+    # K steps: half in one rollout launch, half step by step (exercises the host-side t counter)
+    K1 = K // 2
+    A = O.SPEC[dim]["actions"]
+    r_obs, r_rew, r_done, _, _ = philox_rollout(ob, K, SEED, env_base, 0, A, ref3d, normalise=dynamic)
+    obs, rew, done = env.rollout(K1)
+    assert np.array_equal(obs.cpu().numpy(), r_obs[:K1])
+    assert np.array_equal(rew.cpu().numpy(), r_rew[:K1])
+    assert np.array_equal(done.cpu().numpy(), r_done[:K1])
+    for k in range(K1, K):
+        o, r, d = env.step(None)
+        if k % 50 == 0 or k == K - 1:
+            assert np.array_equal(o.cpu().numpy(), r_obs[k]), k
+            assert np.array_equal(r.cpu().numpy(), r_rew[k]), k
+            assert np.array_equal(d.cpu().numpy(), r_done[k]), k
+    st = env.export_state()
+    g_ref, sc_ref = ob.export()
+    assert np.array_equal(st["grid"].cpu().numpy().reshape(g_ref.shape), g_ref)
+    assert np.array_equal(st["scalars"].cpu().numpy()[:, :6], sc_ref[:, :6])
+    assert np.array_equal(st["ret"].cpu().numpy().astype(np.float64), ob.ret)
+    cnt, ln, ret, iou = [x.cpu().numpy() for x in env.episode_stats()]
+    assert np.array_equal(cnt, ob.ep_cnt) and np.array_equal(ln, ob.ep_len)
+    assert np.array_equal(ret, ob.ep_ret)
+    assert np.array_equal(iou, ob.ep_iou, equal_nan=True)
+    assert ob.ep_cnt.sum() > 0
+    cur = env.iou().cpu().numpy()
+    assert np.array_equal(cur, ob.iou(), equal_nan=True)
+    stats = env.stats().cpu().numpy()
+    assert stats[2] == ob.ep_cnt.sum() and stats[3] == ob.ep_len.sum() and stats[0] == ob.ep_ret.sum()
+    if not np.isnan(ob.ep_iou.sum()):
+        assert abs(stats[1] - ob.ep_iou.sum()) <= 1e-9 * max(1.0, abs(ob.ep_iou.sum()))
+    env.check_errors()
+
+
+def test_shard_independence_2d():
+    """Philox streams are keyed by the GLOBAL env id: two shards == one big vector env (8(e))."""
+    n, K = 256, 300
+    full = make_gpu(2, False, n, 0, auto_reset=True, env_base=0)
+    a = make_gpu(2, False, n // 2, 0, auto_reset=True, env_base=0)
+    b = make_gpu(2, False, n // 2, 0, auto_reset=True, env_base=n // 2)
+    for e in (full, a, b):
+        e.reset()
+    of, rf, df = full.rollout(K)
+    oa, ra, da = a.rollout(K)
+    ob_, rb, db = b.rollout(K)
+    assert torch.equal(of, torch.cat([oa, ob_], dim=1))
+    assert torch.equal(rf, torch.cat([ra, rb], dim=1)) and torch.equal(df, torch.cat([da, db], dim=1))
+    sf = full.stats().clone()
+    assert torch.equal(sf[[0, 2, 3]], (a.stats() + b.stats())[[0, 2, 3]])
+
+
+def test_static_plans_generated_on_device_match_oracle():
+    for dim, choices in ((1, (0, 1, 2)), (2, (0, 1)), (3, (0, 1))):
+        for pc in choices:
+            env = make_gpu(dim, False, 1, pc)
+            want = O.static_plan(dim, pc)
+            got = env.plans_dense()[0]
+            assert np.array_equal(got, want), (dim, pc)
+            assert env.plan_totals().cpu().numpy()[0] == O.total_brick_of(dim, want, False)
+    with pytest.raises(ValueError):
+        make_gpu(2, False, 1, 2)
+    with pytest.raises(ValueError):
+        make_gpu(1, False, 1, 3)
+
+
+def test_dataset_packing_matches_reference_budgets():
+    for dim, dens in ((1, "dense"), (2, "dense"), (2, "sparse"), (3, "dense"), (3, "sparse")):
+        plans = load_plans(dim, dens, "train")
+        env = make_gpu(dim, True, 1, plans=plans)
+        assert np.array_equal(env.plans_dense(), plans)
+        want = [O.total_brick_of(dim, p, True) for p in plans]
+        assert np.array_equal(env.plan_totals().cpu().numpy(), np.asarray(want))
+
+
+def test_out_of_range_action_latches_error():
+    env = make_gpu(2, False, 4, 0)
+    env.reset()
+    env.step([0, 1, 5, 4])
+    with pytest.raises(UnboundLocalError):
+        env.check_errors()
+
+
+def test_step_after_done_keeps_mutating_like_reference():
+    """No auto-reset: stepping past done is legal (multiprocess.py never resets, quirk Q3)."""
+    env = make_gpu(1, False, 1, 2, obs_dtype=torch.float64)
+    orc = O.make_env(1, False, plan_choose=2)
+    env.reset()
+    orc.reset()
+    rng = np.random.RandomState(3)
+    for t in range(900):
+        a, s = int(rng.randint(3)), int(rng.randint(1, 4))
+        o, r, d = env.step([a], [s])
+        oo, orr, od = orc.step(a, s)
+        if t % 25 == 0 or t > 740:
+            assert np.array_equal(o.cpu().numpy(), oo) and r.item() == orr and bool(d.item()) == od, t
