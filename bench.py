@@ -31,6 +31,7 @@ WORKLOADS = {
     "1d_dynamic": (1, True, 0, "dense", 65536, 67),
     "1d_static_step": (1, False, 2, None, 65536, 64),
     "2d_static_dense": (2, False, 0, None, 1048576, 262),
+    "2d_static_sparse": (2, False, 1, None, 1048576, 262),
     "2d_dynamic_dense": (2, True, 0, "dense", 1048576, 268),
     "3d_static_dense": (3, False, 0, None, 262144, 330),
     "3d_dynamic_dense": (3, True, 0, "dense", 262144, 336),
@@ -205,10 +206,14 @@ def run_ours(args):
     obs_ring = torch.empty((R, 1, n, D), dtype=torch.float32, device=dev)
     rew_ring = torch.empty((R, 1, n), dtype=torch.float32, device=dev)
     done_ring = torch.empty((R, 1, n), dtype=torch.uint8, device=dev)
-    RA = 16
+    RA = 64
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
-    act_ring = torch.randint(0, A, (RA, 1, n), dtype=torch.uint8, device=dev, generator=g)
+    act_ring = None
+    if args.actions == "buffer":
+        act_ring = torch.randint(0, A, (RA, 1, n), dtype=torch.uint8, device=dev, generator=g)
+    else:
+        b_alg -= 1                                           # no action byte when generated in-kernel
     env.reset()
     torch.cuda.synchronize()
 
@@ -216,7 +221,8 @@ def run_ours(args):
     G = max(32, R + (R & 1))
 
     def launch_step(i):
-        env.rollout(1, actions=act_ring[i % RA], out=(obs_ring[i % R], rew_ring[i % R], done_ring[i % R]),
+        env.rollout(1, actions=act_ring[i % RA] if act_ring is not None else None,
+                    out=(obs_ring[i % R], rew_ring[i % R], done_ring[i % R]),
                     use_device_t=True, t_slot=i & 1)
 
     stream = torch.cuda.Stream(device=dev)
@@ -291,7 +297,8 @@ def run_ours(args):
             "ms_per_step": ms / K_eff, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32 bit-grid / i32 counters, f32 observations", "data": "synthetic",
             "config": {"workload": wl, "total_envs": total_envs, "envs_per_gpu": n, "mode": "step (1 launch per vector step, CUDA graph of %d)" % G,
-                       "actions": "uniform random over %d actions, pre-generated in HBM" % A,
+                       "actions": ("uniform over %d actions, " % A) + ("ring of %d pre-generated vectors in HBM" % RA if act_ring is not None
+                                                                          else "Philox4x32-10 in-kernel, counter (global env id, step)"),
                        "step_size": "Philox4x32-10 in-kernel", "auto_reset": True,
                        "l2": "obs ring of %d x %.1f MB (> 2 x L2) + state %.1f MB" % (R, obs_bytes / 1e6, n * 64 / 1e6),
                        "parallelism": "env-sharded x%d, NCCL all-reduce of episode stats only" % world},
@@ -303,9 +310,9 @@ def run_ours(args):
             "episode_stats": {"sum_return": float(stats[0]), "sum_iou": float(stats[1]), "episodes": float(stats[2]),
                               "steps": float(stats[3])}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, total, wall = cpu_port_throughput(wl, 16, 1500)
+        v, cores, total, wall = cpu_port_throughput(wl, 64, 20000)
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                "sample": "%d procs x 16 envs x 1500 steps of %s, python oracle port, reset on done (%.1f s wall)" % (cores, wl, wall)}
+                                "sample": "%d procs x 64 envs x 20000 steps of %s, python oracle port, reset on done (%.1f s wall)" % (cores, wl, wall)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -315,8 +322,9 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2048)
-    ap.add_argument("--warmup", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=16384)
+    ap.add_argument("--warmup", type=int, default=1024)
+    ap.add_argument("--actions", default="philox", choices=["philox", "buffer"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="2d_static_dense", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="total envs over all GPUs (default: the BASELINE config's)")

@@ -330,7 +330,7 @@ def main(args=None):
     if args.env in need_plan and args.plan_type is None:
         print("please choose a shape from list: " + need_plan[args.env])
         return None
-    dens = ["dense", "sparse"][args.plan_type or 0]
+    dens = "sparse" if args.plan_type == 1 else "dense"
     if args.env == "1DStatic":
         env_input = deep_mobile_printing_1d1r(plan_choose=args.plan_type)
     elif args.env == "1DDynamic":
