@@ -144,9 +144,11 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
         if (io.obs) {
             stage_observe1<ObsT>(g, e, tile + lane * D1_OBS, normalise, total_brick, st.total_step);
             __syncwarp();
-            if (nvalid > 0)
-                warp_tile_store<ObsT>(reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * D1_OBS,
-                                      tile, nvalid * D1_OBS, lane);
+            {
+                ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * D1_OBS;
+                if (nvalid == 32) warp_tile_store_full<ObsT, 32 * D1_OBS>(dst, tile, lane);
+                else if (nvalid > 0) warp_tile_store<ObsT>(dst, tile, nvalid * D1_OBS, lane);
+            }
             __syncwarp();
         }
         if (live) {

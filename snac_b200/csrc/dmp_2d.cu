@@ -63,20 +63,39 @@ __device__ __forceinline__ uint32_t stage_deposit2(uint32_t* g, const Env2& e, i
     return old & bit;
 }
 
+// spread the 7 bits of x into the low bits of 7 bytes (byte j = bit j): the partial products of
+// x * 0x0002040810204081 never overlap, so one wide IMAD (FMA pipe) + one mask does it.
+__device__ __forceinline__ uint64_t spread7(uint32_t x) {
+    return ((uint64_t)x * 0x0002040810204081ull) & 0x0101010101010101ull;
+}
+
+// code byte (0 frame, 1 empty, 2 occupied) -> observation value code-1
+template <typename ObsT, int BYTE>
+__device__ __forceinline__ ObsT obs_from_code(uint32_t packed) {
+    if constexpr (sizeof(ObsT) == 4) {
+        // float: drop the byte into the mantissa of 2^23 (one PRMT), subtract 2^23 + 1 (one FADD): exact,
+        // and keeps the per-element work off the conversion (XU) pipe
+        return __uint_as_float(__byte_perm(packed, 0x4B000000u, 0x7650u + BYTE)) - 8388609.0f;
+    } else {
+        return obs_from_int<ObsT>((int)((packed >> (8 * BYTE)) & 0xFFu) - 1);
+    }
+}
+
 // stage (c): observation window -> this thread's row of the warp tile.  observation_ :78-82 + hstack.
 template <typename ObsT>
 __device__ __forceinline__ void stage_observe2(const uint32_t* g, const Env2& e, ObsT* row,
                                                bool normalise, int total_brick, int total_step) {
     // rows pr-3 .. pr+3 of the padded grid are interior rows pr-6 .. pr; the grid words are stored
-    // behind 64 zero bits so that the 140-bit span [B0, B0+140) is always in range.
-    const int B0 = 64 + (e.pr - 2 * D2_HW) * D2_W;
+    // behind 64 zero bits so that the 143-bit span [B0, B0+143) is always in range.  Starting 3 bits
+    // early puts interior column c of every row at bit c+3 = its padded column.
+    const int B0 = 64 + (e.pr - 2 * D2_HW) * D2_W - D2_HW;
     const int w0 = B0 >> 5, off = B0 & 31;
     const uint32_t x0 = g[(w0 + 0) * B2], x1 = g[(w0 + 1) * B2], x2 = g[(w0 + 2) * B2];
     const uint32_t x3 = g[(w0 + 3) * B2], x4 = g[(w0 + 4) * B2], x5 = g[(w0 + 5) * B2];
     const uint32_t q0 = __funnelshift_r(x0, x1, off), q1 = __funnelshift_r(x1, x2, off);
     const uint32_t q2 = __funnelshift_r(x2, x3, off), q3 = __funnelshift_r(x3, x4, off);
     const uint32_t q4 = __funnelshift_r(x4, x5, off);
-    uint32_t R[7];
+    uint32_t R[7];                                      // padded rows (bits 3..22 valid, rest garbage)
     R[0] = q0;
     R[1] = __funnelshift_r(q0, q1, 20);
     R[2] = q1 >> 8;
@@ -86,18 +105,23 @@ __device__ __forceinline__ void stage_observe2(const uint32_t* g, const Env2& e,
     R[6] = __funnelshift_r(q3, q4, 24);
     const int sh = e.pc - D2_HW;                       // window column 0 = padded column pc-3
     const uint32_t colvalid = (COLVALID >> sh) & 0x7Fu;
+    const uint64_t vcode = spread7(colvalid);          // 1 where the window column is inside the plan area
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
         const int p = e.pr - D2_HW + k;                // padded row of window row k
         const bool rowvalid = (unsigned)(p - D2_HW) < (unsigned)D2_W;
-        const uint32_t occ = (((R[k] & ROWMASK) << D2_HW) >> sh) & 0x7Fu;
-        const uint32_t val = rowvalid ? colvalid : 0u;
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            // inside: 0/1 ; frame: -1  (environment_memory[...] = -1, :61-64)
-            const int v = (int)((occ >> j) & 1u) + (int)((val >> j) & 1u) - 1;
-            row[k * 7 + j] = obs_from_int<ObsT>(v);
-        }
+        const uint32_t occ = (R[k] >> sh) & colvalid;
+        // inside: 0/1 ; frame: -1  (environment_memory[...] = -1, :61-64)  ->  code = value + 1
+        const uint64_t code = rowvalid ? spread7(occ) + vcode : 0ull;
+        const uint32_t lo = (uint32_t)code, hi = (uint32_t)(code >> 32);
+        ObsT* o = row + k * 7;
+        o[0] = obs_from_code<ObsT, 0>(lo);
+        o[1] = obs_from_code<ObsT, 1>(lo);
+        o[2] = obs_from_code<ObsT, 2>(lo);
+        o[3] = obs_from_code<ObsT, 3>(lo);
+        o[4] = obs_from_code<ObsT, 0>(hi);
+        o[5] = obs_from_code<ObsT, 1>(hi);
+        o[6] = obs_from_code<ObsT, 2>(hi);
     }
     obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, total_step, row[49], row[50]);
 }
@@ -195,9 +219,11 @@ __global__ void __launch_bounds__(B2) k2d_rollout(const DmpState st, const DmpIO
         if (io.obs) {
             stage_observe2<ObsT>(g, e, tile + lane * D2_OBS, normalise, total_brick, st.total_step);
             __syncwarp();
-            if (nvalid > 0)
-                warp_tile_store<ObsT>(reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * D2_OBS,
-                                      tile, nvalid * D2_OBS, lane);
+            {
+                ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * D2_OBS;
+                if (nvalid == 32) warp_tile_store_full<ObsT, 32 * D2_OBS>(dst, tile, lane);
+                else if (nvalid > 0) warp_tile_store<ObsT>(dst, tile, nvalid * D2_OBS, lane);
+            }
             __syncwarp();
         }
         if (live) {

@@ -99,6 +99,25 @@ __device__ __forceinline__ void warp_tile_store(T* __restrict__ dst, const T* ti
     }
 }
 
+// full-warp fast path: the element count is a compile-time constant (32 envs x D values), the span is
+// 16 B aligned by construction when `dst` is; fully unrolled 128-bit streaming stores.
+template <typename T, int N_ELEMS>
+__device__ __forceinline__ void warp_tile_store_full(T* __restrict__ dst, const T* tile, int lane) {
+    constexpr int PER16 = 16 / (int)sizeof(T);
+    static_assert(N_ELEMS % PER16 == 0, "tile must be a whole number of 16 B vectors");
+    constexpr int N16 = N_ELEMS / PER16;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) != 0) { warp_tile_store<T>(dst, tile, N_ELEMS, lane); return; }
+    const uint4* s4 = reinterpret_cast<const uint4*>(tile);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    uint4 v[(N16 + 31) / 32];
+#pragma unroll
+    for (int i = 0; i < (N16 + 31) / 32; ++i)
+        if (i * 32 + 31 < N16 || i * 32 + lane < N16) v[i] = s4[i * 32 + lane];
+#pragma unroll
+    for (int i = 0; i < (N16 + 31) / 32; ++i)
+        if (i * 32 + 31 < N16 || i * 32 + lane < N16) __stcs(d4 + i * 32 + lane, v[i]);
+}
+
 // host-side helpers ---------------------------------------------------------------------------
 int dmp_set_error(cudaError_t e);   // records e, returns DMP_OK / DMP_ECUDA
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

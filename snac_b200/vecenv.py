@@ -254,6 +254,38 @@ class BatchedDMPEnv:
         self._keep_io = (a, s, p)
         return obs, rew, (None if done is None else done.view(torch.bool))
 
+    STAGES = ("move", "deposit", "observe", "reward", "done_reset")
+
+    def step_staged(self, actions, step_sizes=None, next_plan=None, stages=STAGES):
+        """The same step as step(), executed as the five standalone stage kernels
+        (a) move, (b) deposit, (c) observe, (d) reward, (e) done/reset -- one launch each
+        (include/dmp.h "stage kernels").  For unit parity and per-stage timing; the fused
+        step()/rollout() is the production path."""
+        n = self.num_envs
+        if self._needs_initial_reset:
+            raise RuntimeError("call reset() before step_staged()")
+        a = None if actions is None else self._u8(actions, (n,), "actions")
+        s = None if step_sizes is None else self._u8(step_sizes, (n,), "step_sizes")
+        p = None if next_plan is None else self._i32(next_plan, (n,), "next_plan")
+        if not hasattr(self, "_stage_scratch"):
+            self._stage_scratch = torch.zeros((n, 4), dtype=torch.int32, device=self.device)
+        io = L.DmpIO()
+        io.actions, io.step_sizes, io.next_plan = _ptr(a), _ptr(s), _ptr(p)
+        io.obs, io.reward, io.done = self._obs.data_ptr(), self._reward.data_ptr(), self._done.data_ptr()
+        io.obs_kind, io.flags = _TORCH_OBS[self.obs_dtype], self._flags()
+        self._st.t_dev = None
+        fns = {"move": L.lib.dmp_stage_move, "deposit": L.lib.dmp_stage_deposit, "observe": L.lib.dmp_stage_observe,
+               "reward": L.lib.dmp_stage_reward, "done_reset": L.lib.dmp_stage_done_reset}
+        with torch.cuda.device(self.device):
+            for name in stages:
+                if name == "done_reset" and not self.auto_reset:
+                    continue
+                L.check(fns[name](C.byref(self._st), C.byref(io), self._stage_scratch.data_ptr(), self._stream()),
+                        "dmp_stage_" + name)
+        if "move" in stages:
+            self._st.t = self._st.t + 1
+        return self._obs, self._reward, self._done.view(torch.bool)
+
     # ------------------------------------------------------------------------------------------
     def iou(self) -> torch.Tensor:
         """Per-env IoU of the current grid vs. its plan, float64 [N]

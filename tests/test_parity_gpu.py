@@ -228,3 +228,35 @@ def test_step_after_done_keeps_mutating_like_reference():
         oo, orr, od = orc.step(a, s)
         if t % 25 == 0 or t > 740:
             assert np.array_equal(o.cpu().numpy(), oo) and r.item() == orr and bool(d.item()) == od, t
+
+
+# ------------------------------------------------------------------------------------------------
+# 4. the five standalone stage kernels (a)-(e) == the fused step, and == the oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim,dynamic,density,ref3d,n,K", [
+    (1, False, None, False, 70, 800), (1, True, "dense", False, 70, 800),
+    (2, False, None, False, 70, 700), (2, True, "sparse", False, 70, 400),
+    (3, False, None, True, 70, 400), (3, True, "dense", False, 70, 200), (3, True, "sparse", True, 40, 1100)])
+def test_stage_kernels_equal_fused_step_and_oracle(dim, dynamic, density, ref3d, n, K):
+    plans = load_plans(dim, density, "val") if dynamic else None
+    kw = dict(auto_reset=True, env_base=99, seed=SEED, action_dist="ref3d" if ref3d else "uniform",
+              normalise=dynamic, obs_dtype=torch.float64)
+    staged = make_gpu(dim, dynamic, n, 0, plans, **kw)
+    fused = make_gpu(dim, dynamic, n, 0, plans, **kw)
+    ob = OracleBatch(dim, dynamic, n, 0, plans)
+    p0 = philox.reset_draw(SEED, np.arange(99, 99 + n), 0, ob.n_plans) if dynamic else None
+    assert torch.equal(staged.reset(), fused.reset())
+    ob.reset(p0)
+    r_obs, r_rew, r_done, _, _ = philox_rollout(ob, K, SEED, 99, 0, O.SPEC[dim]["actions"], ref3d, normalise=dynamic)
+    for k in range(K):
+        o1, r1, d1 = staged.step_staged(None)
+        o2, r2, d2 = fused.step(None)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), k
+        if k % 40 == 0 or k == K - 1:
+            assert np.array_equal(o1.cpu().numpy(), r_obs[k]) and np.array_equal(d1.cpu().numpy(), r_done[k]), k
+    a, b = staged.export_state(), fused.export_state()
+    assert torch.equal(a["grid"], b["grid"]) and torch.equal(a["scalars"], b["scalars"]) and torch.equal(a["ret"], b["ret"])
+    for x, y in zip(staged.episode_stats(), fused.episode_stats()):
+        assert torch.equal(x, y)
+    assert np.array_equal(staged.episode_stats()[0].cpu().numpy(), ob.ep_cnt)
+    assert np.array_equal(staged.episode_stats()[3].cpu().numpy(), ob.ep_iou, equal_nan=True)
