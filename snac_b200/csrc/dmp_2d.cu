@@ -17,7 +17,6 @@ namespace {
 constexpr int B2 = 128;                 // threads (= envs) per block
 constexpr int S2_WORDS = 18;            // smem words per env: 2 zero | 13 grid | 3 zero
 constexpr int S2_G0 = 2;                // first grid word
-constexpr uint32_t ROWMASK = 0xFFFFFu;  // 20 bits
 constexpr uint32_t COLVALID = 0x7FFFF8u;  // padded columns 3..22 are inside the plan area
 
 struct Env2 {

@@ -11,6 +11,7 @@
 // the 7x7 window at the new position and write the 51 observation values as one coalesced row.
 // IoU of a finished episode is a warp reduction (128-bit loads, min, shuffle tree) fused with the
 // reset of the height map.
+#include <stdlib.h>
 #include "dmp_common.cuh"
 
 namespace {
@@ -309,7 +310,8 @@ inline unsigned blocks3(int64_t n) { return (unsigned)((n + WPB3 - 1) / WPB3); }
 
 }  // namespace
 
-int dmp3d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+// warp-per-env kernel (round-1 first version; kept as a cross-check and for DMP_3D_KERNEL=wpe)
+static int dmp3d_wpe_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
     const unsigned b = blocks3(st.n_envs);
     switch (io.obs_kind) {
         case DMP_OBS_F32: k3d_rollout<float><<<b, WPB3 * 32, 0, s>>>(st, io, K); break;
@@ -318,6 +320,11 @@ int dmp3d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
         default: return DMP_EINVAL;
     }
     return dmp_set_error(cudaGetLastError());
+}
+
+int dmp3d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    static const int use_wpe = []() { const char* v = getenv("DMP_3D_KERNEL"); return (v && v[0] == 'w') ? 1 : 0; }();
+    return use_wpe ? dmp3d_wpe_rollout(st, io, K, s) : dmp3d_tile_rollout(st, io, K, s);
 }
 
 int dmp3d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs,

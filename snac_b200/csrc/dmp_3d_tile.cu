@@ -1,0 +1,331 @@
+// dmp_3d_tile.cu -- 3D envs, tile kernel: 32 envs per warp, one env per lane, the warp's 32 height
+// maps staged in shared memory by bulk async copies (cp.async.bulk -> UBLKCP, completion on an mbarrier).
+//
+// Why: the step logic of a 3D env is scalar (Philox, check_sur, move_step, the termination rules); with
+// one env per warp (dmp_3d.cu) it is replicated 32x and the kernel is instruction bound.  Here every lane
+// runs its own env (SIMT-efficient like the 2D kernel) and only the data movement is cooperative:
+//   * state in : one 800 B bulk copy per env (issued by its lane, all 32 in flight at once), 16 B aux per lane;
+//   * step     : neighbours / walk cells / 7x7 window are shared-memory reads; a brick is written to shared
+//                memory and written through to HBM with a single 2-byte store;
+//   * obs out  : [32][51] tile in shared memory, streamed out as one contiguous span of 128-bit stores;
+//   * done     : ballot over the warp, then the whole warp computes that env's IoU (128-bit shared loads,
+//                min, shuffle tree) and clears its height map (coalesced 128-bit stores)  -- stage (d)/(e).
+// Semantics: identical to dmp_3d.cu (reference citations there); tests cross-check the two kernels.
+#include "dmp_common.cuh"
+
+namespace {
+
+constexpr int WPB = 2;                       // warps per block
+constexpr int ENV_STRIDE = 816;              // bytes per env in smem: 800 B map + 16 B guard (window over-read)
+constexpr int GUARD = 16;                    // leading guard before env 0 of a warp
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr uint32_t COLVALID = 0x7FFFF8u;     // padded columns 3..22 are inside the plan area
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t a = smem_u32(bar);
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    }
+}
+
+struct EnvT {
+    int pr, pc, plan_idx, cb, cs;
+    float ret;
+};
+
+__device__ __forceinline__ int dir_dr(int d) { return d == 2 ? 1 : (d == 3 ? -1 : 0); }
+__device__ __forceinline__ int dir_dc(int d) { return d == 0 ? -1 : (d == 1 ? 1 : 0); }
+
+// environment_memory[r][c] (padded coordinates) of this lane's env; -1 on the frame
+__device__ __forceinline__ int cell_s(const uint16_t* g, int r, int c) {
+    const unsigned ir = (unsigned)(r - 3), ic = (unsigned)(c - 3);
+    return (ir < 20u && ic < 20u) ? (int)g[ir * 20u + ic] : -1;
+}
+
+// two packed halfwords (biased: height+1, 0 = frame) -> two observation values
+template <typename ObsT>
+__device__ __forceinline__ void emit_pair(uint32_t u, ObsT& lo, ObsT& hi) {
+    if constexpr (sizeof(ObsT) == 4) {
+        lo = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7610u)) - 8388609.0f;
+        hi = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7632u)) - 8388609.0f;
+    } else {
+        lo = obs_from_int<ObsT>((int)(u & 0xFFFFu) - 1);
+        hi = obs_from_int<ObsT>((int)(u >> 16) - 1);
+    }
+}
+
+// stage (c): 7x7 window of this lane's env -> its row of the warp tile
+template <typename ObsT>
+__device__ __forceinline__ void observe_tile(const uint16_t* g, const EnvT& e, ObsT* row, bool normalise,
+                                             int total_brick, int total_step) {
+    const int ic0 = e.pc - 6;                           // interior column of window column 0 (may be negative)
+    const int w0 = ic0 >> 1;                            // first word of the row to fetch (floor)
+    const int sh16 = (ic0 & 1) * 16;
+    const int sh = e.pc - 3;
+    const uint32_t colvalid = (COLVALID >> sh) & 0x7Fu;
+    // per-pair validity masks (0xFFFF per valid halfword)
+    uint32_t m[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t lo = (colvalid >> (2 * q)) & 1u, hi = (q < 3) ? ((colvalid >> (2 * q + 1)) & 1u) : 0u;
+        m[q] = (lo ? 0x0000FFFFu : 0u) | (hi ? 0xFFFF0000u : 0u);
+    }
+    // bias (+1 per valid halfword), applied AFTER masking: a garbage 0xFFFF from the guard bytes must not
+    // carry into its valid neighbour
+    const uint32_t b0 = m[0] & 0x00010001u, b1 = m[1] & 0x00010001u, b2 = m[2] & 0x00010001u, b3 = m[3] & 0x00010001u;
+    const uint32_t* gw = reinterpret_cast<const uint32_t*>(g);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const int ir = e.pr - 6 + k;                    // interior row of window row k
+        const bool rowvalid = (unsigned)ir < 20u;
+        ObsT* o = row + k * 7;
+        uint32_t u0 = 0, u1 = 0, u2 = 0, u3 = 0;
+        if (rowvalid) {
+            const uint32_t* rw = gw + ir * 10 + w0;     // over-reads stay inside the 16 B guards
+            const uint32_t x0 = rw[0], x1 = rw[1], x2 = rw[2], x3 = rw[3], x4 = rw[4];
+            u0 = (__funnelshift_r(x0, x1, sh16) & m[0]) + b0;
+            u1 = (__funnelshift_r(x1, x2, sh16) & m[1]) + b1;
+            u2 = (__funnelshift_r(x2, x3, sh16) & m[2]) + b2;
+            u3 = (__funnelshift_r(x3, x4, sh16) & m[3]) + b3;
+        }
+        ObsT dummy;
+        emit_pair<ObsT>(u0, o[0], o[1]);
+        emit_pair<ObsT>(u1, o[2], o[3]);
+        emit_pair<ObsT>(u2, o[4], o[5]);
+        emit_pair<ObsT>(u3, o[6], dummy);
+    }
+    obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, total_step, row[49], row[50]);
+}
+
+template <typename ObsT>
+__global__ void __launch_bounds__(WPB * 32) k3d_tile_rollout(const DmpState st, const DmpIO io, const int K) {
+    extern __shared__ uint4 smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = st.n_envs;
+    const int64_t env0 = ((int64_t)blockIdx.x * WPB + warp) * 32;
+    if (env0 >= n) return;                                            // whole warp leaves together
+    const int64_t env = env0 + lane;
+    const bool live = env < n;
+    const int nvalid = (int)min((int64_t)32, n - env0);
+
+    // shared memory carve-up: per warp [GUARD | 32 x ENV_STRIDE] ... then tiles, then barriers
+    uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw);
+    constexpr int WARP_GRID_BYTES = GUARD + 32 * ENV_STRIDE;
+    uint8_t* wgrid = base + warp * WARP_GRID_BYTES + GUARD;
+    ObsT* tile = reinterpret_cast<ObsT*>(base + WPB * WARP_GRID_BYTES) + warp * (32 * D3_OBS);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base + WPB * WARP_GRID_BYTES + WPB * 32 * D3_OBS * sizeof(ObsT)) + warp;
+    uint16_t* g = reinterpret_cast<uint16_t*>(wgrid + lane * ENV_STRIDE);         // this lane's height map
+
+    uint16_t* cells = reinterpret_cast<uint16_t*>(st.cells);
+    uint4* aux = reinterpret_cast<uint4*>(st.aux);
+    const uint8_t* __restrict__ plans = reinterpret_cast<const uint8_t*>(st.plans);
+
+    // ---- state in: 32 bulk copies in flight, one per lane ------------------------------------------
+    if (lane == 0) mbar_init(bar, 32);
+    __syncwarp();
+    if (live) {
+        mbar_arrive_expect_tx(bar, CELLS3D * 2);
+        bulk_g2s(g, cells + env * CELLS3D, CELLS3D * 2, bar);
+    } else {
+        mbar_arrive(bar);
+    }
+    EnvT e{D2_LO, D2_LO, 0, 0, 0, 0.f};
+    if (live) {
+        const uint4 a = aux[env];
+        e.pr = a.x & 0xFF; e.pc = (a.x >> 8) & 0xFF; e.plan_idx = a.x >> 16;
+        e.cb = a.y & 0xFFFF; e.cs = a.y >> 16;
+        e.ret = __uint_as_float(a.z);
+    }
+    int total_brick = __ldg(st.plan_total + e.plan_idx);
+    int errbits = 0;
+    const bool dynamic = st.dynamic != 0;
+    const bool autoreset = io.flags & DMP_F_AUTORESET;
+    const bool normalise = io.flags & DMP_F_NORMALISE;
+    const bool need_draw = (io.actions == nullptr) || (io.step_sizes == nullptr);
+    const int tslot = (io.flags & DMP_F_TSLOT1) ? 1 : 0;
+    const uint64_t t0 = st.t_dev ? st.t_dev[tslot] : st.t;
+    mbar_wait(bar, 0);
+
+    for (int k = 0; k < K; ++k) {
+        const uint64_t t = t0 + (uint64_t)k;
+        const int64_t idx = (int64_t)k * n + env;
+        Draw d = Draw{0, 0, 0, 0};
+        if (need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
+        int a, s;
+        if (io.actions) a = live ? (int)io.actions[idx] : 0; else a = draw_action(d, D3_ACT, st.action_dist);
+        if (io.step_sizes) s = live ? (int)io.step_sizes[idx] : 1; else s = draw_step_size(d);
+        if ((unsigned)(s - 1) > 2u) errbits |= DMP_ERR_STEPSIZE;
+        if (a > 7) errbits |= DMP_ERR_ACTION;              // reference: an unbuilt brick (:187-208)
+
+        e.cs += 1;
+        // ---- check_sur (:88-102) --------------------------------------------------------------
+        int n1[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) n1[q] = cell_s(g, e.pr + dir_dr(q), e.pc + dir_dc(q));
+        const bool boxed = (n1[0] != 0) && (n1[1] != 0) && (n1[2] != 0) && (n1[3] != 0);
+
+        float reward = 0.f;
+        bool done = false, tail = true;
+        if (a <= 3) {
+            // (a) move_step (:104-134): consecutive empty cells, at most s
+            const int na = (a == 0) ? n1[0] : (a == 1) ? n1[1] : (a == 2) ? n1[2] : n1[3];
+            if (na == 0) {
+                const int dr = dir_dr(a), dc = dir_dc(a);
+                int nstep = 1;
+                if (s >= 2 && cell_s(g, e.pr + 2 * dr, e.pc + 2 * dc) == 0) {
+                    nstep = 2;
+                    if (s >= 3 && cell_s(g, e.pr + 3 * dr, e.pc + 3 * dc) == 0) nstep = 3;
+                }
+                e.pr = min(max(e.pr + dr * nstep, D2_LO), D2_HI);
+                e.pc = min(max(e.pc + dc * nstep, D2_LO), D2_HI);
+            }
+        } else {
+            // (b) build on neighbour a-4 unless it is frame
+            const int q = a - 4;
+            bool built = false;
+            int newh = 0, ti = 0;
+            int m1[4] = {n1[0], n1[1], n1[2], n1[3]};
+            if (a <= 7) {
+                const int nq = (q == 0) ? n1[0] : (q == 1) ? n1[1] : (q == 2) ? n1[2] : n1[3];
+                if (nq != -1) {
+                    built = true;
+                    newh = nq + 1;
+                    ti = (e.pr + dir_dr(q) - 3) * 20 + (e.pc + dir_dc(q) - 3);
+                    e.cb += 1;
+                    g[ti] = (uint16_t)newh;
+                    if (live) cells[env * CELLS3D + ti] = (uint16_t)newh;      // write-through
+#pragma unroll
+                    for (int z = 0; z < 4; ++z) if (z == q) m1[z] = newh;
+                }
+            }
+            if (dynamic) {
+                const bool boxed2 = (m1[0] != 0) && (m1[1] != 0) && (m1[2] != 0) && (m1[3] != 0);
+                if (boxed2) { reward = -100.f; done = true; tail = false; }
+                else if (e.cb >= total_brick) { done = true; tail = false; }
+                else if (built) { tail = false; }
+            } else {
+                if (e.cb >= total_brick || boxed) { done = true; tail = false; }
+                else if (built) { tail = false; }
+            }
+            if (!tail && !done) {
+                const int p = plans[e.plan_idx * CELLS3D + ti];
+                reward = (newh > p) ? -1.f : (newh == p ? 10.f : 1.f);
+            }
+        }
+        if (tail) done = (e.cs >= st.total_step) || (!dynamic && boxed);
+        e.ret += reward;
+
+        // ---- (c) observation --------------------------------------------------------------------
+        if (io.obs) {
+            observe_tile<ObsT>(g, e, tile + lane * D3_OBS, normalise, total_brick, st.total_step);
+            __syncwarp();
+            ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * D3_OBS;
+            if (nvalid == 32) warp_tile_store_full<ObsT, 32 * D3_OBS>(dst, tile, lane);
+            else warp_tile_store<ObsT>(dst, tile, nvalid * D3_OBS, lane);
+            __syncwarp();
+        }
+        if (live) {
+            if (io.reward) io.reward[idx] = reward;
+            if (io.done) io.done[idx] = done ? 1 : 0;
+        }
+
+        // ---- (d)/(e) finished episodes: warp-cooperative IoU + clear, then per-lane reset ----------
+        unsigned dm = __ballot_sync(FULL, done && autoreset && live);
+        while (dm) {
+            const int src = __ffs(dm) - 1;
+            dm &= dm - 1;
+            const int s_plan = __shfl_sync(FULL, e.plan_idx, src);
+            const int s_tb = __shfl_sync(FULL, total_brick, src);
+            const int s_cb = __shfl_sync(FULL, e.cb, src);
+            uint4* sg = reinterpret_cast<uint4*>(wgrid + src * ENV_STRIDE);
+            uint4* gg = reinterpret_cast<uint4*>(cells + (env0 + src) * CELLS3D);
+            int cross = 0;
+            if (lane < 25) {
+                const uint4 h0 = sg[2 * lane], h1 = sg[2 * lane + 1];
+                const uint4 pp = __ldg(reinterpret_cast<const uint4*>(plans + s_plan * CELLS3D) + lane);
+                const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                const uint32_t pw[4] = {pp.x, pp.y, pp.z, pp.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int ha = hw[i] & 0xFFFF, hb = hw[i] >> 16;
+                    const int pa = (pw[i >> 1] >> ((i & 1) * 16)) & 0xFF, pb = (pw[i >> 1] >> ((i & 1) * 16 + 8)) & 0xFF;
+                    cross += min(ha, pa) + min(hb, pb);
+                }
+                const uint4 z = make_uint4(0, 0, 0, 0);
+                sg[2 * lane] = z; sg[2 * lane + 1] = z;
+                gg[2 * lane] = z; gg[2 * lane + 1] = z;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cross += __shfl_xor_sync(FULL, cross, o);
+            if (lane == src) {
+                const double iou = __ddiv_rn((double)cross, (double)(s_tb + s_cb - cross));
+                st.ep_cnt[env] += 1;
+                st.ep_len[env] += (uint32_t)e.cs;
+                st.ep_ret[env] += (double)e.ret;
+                st.ep_iou[env] += iou;
+                if (io.next_plan) {
+                    const int p = io.next_plan[idx];
+                    if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
+                } else if (st.plan_mode == DMP_PLAN_PHILOX) {
+                    if (!need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
+                    e.plan_idx = draw_plan(d.x2, st.n_plans);
+                } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
+                    e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
+                }
+                total_brick = __ldg(st.plan_total + e.plan_idx);
+                e.pr = e.pc = D2_LO; e.cb = e.cs = 0; e.ret = 0.f;
+            }
+            __syncwarp();
+        }
+    }
+    if (live) {
+        aux[env] = make_uint4((uint32_t)e.pr | ((uint32_t)e.pc << 8) | ((uint32_t)e.plan_idx << 16),
+                              (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16), __float_as_uint(e.ret), 0u);
+        if (errbits) atomicOr(st.err, errbits);
+        if (st.t_dev && env == 0) st.t_dev[tslot ^ 1] = t0 + (uint64_t)K;
+    }
+}
+
+template <typename ObsT>
+int launch_tile(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    const size_t smem = (size_t)WPB * (GUARD + 32 * ENV_STRIDE) + (size_t)WPB * 32 * D3_OBS * sizeof(ObsT) + WPB * 8 + 16;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k3d_tile_rollout<ObsT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return dmp_set_error(e);
+        attr_done = true;
+    }
+    const int64_t warps = (st.n_envs + 31) / 32;
+    const unsigned blocks = (unsigned)((warps + WPB - 1) / WPB);
+    k3d_tile_rollout<ObsT><<<blocks, WPB * 32, smem, s>>>(st, io, K);
+    return dmp_set_error(cudaGetLastError());
+}
+
+}  // namespace
+
+int dmp3d_tile_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    switch (io.obs_kind) {
+        case DMP_OBS_F32: return launch_tile<float>(st, io, K, s);
+        case DMP_OBS_F64: return launch_tile<double>(st, io, K, s);
+        case DMP_OBS_I16: return launch_tile<int16_t>(st, io, K, s);
+    }
+    return DMP_EINVAL;
+}
