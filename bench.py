@@ -190,7 +190,8 @@ def run_ours(args):
     from snac_b200.vecenv import BatchedDMPEnv
 
     wl = args.workload
-    dim, dynamic, plan_choose, density, default_envs, b_alg = WORKLOADS[wl]
+    dim, dynamic, plan_choose, density, default_envs, b_alg_step = WORKLOADS[wl]
+    state_bytes = {1: 72, 2: 64, 3: 816}[dim]
     total_envs = args.envs or default_envs
     n = total_envs // world                              # strong scaling: the batch is sharded
     env = BatchedDMPEnv(dim, dynamic=dynamic, plan_choose=plan_choose,
@@ -200,73 +201,106 @@ def run_ours(args):
     D, A = env.obs_dim, env.action_dim
     K, W = args.steps, args.warmup
 
-    # rings: observations (rollout storage) sized past L2 so stores really go to HBM; actions pre-generated
-    obs_bytes = n * D * 4
-    R = min(256, max(2, -(-2 * L2_BYTES // obs_bytes)))
-    obs_ring = torch.empty((R, 1, n, D), dtype=torch.float32, device=dev)
-    rew_ring = torch.empty((R, 1, n), dtype=torch.float32, device=dev)
-    done_ring = torch.empty((R, 1, n), dtype=torch.uint8, device=dev)
-    RA = 64
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    act_ring = None
-    if args.actions == "buffer":
-        act_ring = torch.randint(0, A, (RA, 1, n), dtype=torch.uint8, device=dev, generator=g)
-    else:
-        b_alg -= 1                                           # no action byte when generated in-kernel
-    env.reset()
-    torch.cuda.synchronize()
-
-    # one CUDA graph of G steps (G even: the device-resident Philox step counter alternates slots)
-    G = max(32, R + (R & 1))
-
-    def launch_step(i):
-        env.rollout(1, actions=act_ring[i % RA] if act_ring is not None else None,
-                    out=(obs_ring[i % R], rew_ring[i % R], done_ring[i % R]),
-                    use_device_t=True, t_slot=i & 1)
-
-    stream = torch.cuda.Stream(device=dev)
-    with torch.cuda.stream(stream):
-        for i in range(4):
-            launch_step(i)                                   # sets func attributes before capture
-        stream.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=stream):
-            for i in range(G):
-                launch_step(i)
-        n_replay_w = max(1, -(-W // G))
-        n_replay = max(1, -(-K // G))
-        K_eff = n_replay * G                                 # EXACT number of timed steps
-        for _ in range(n_replay_w):
-            graph.replay()
-        stream.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local) as clk:
-            e0.record(stream)
-            for _ in range(n_replay):
-                graph.replay()
-            e1.record(stream)
-            stream.synchronize()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = e0.elapsed_time(e1)
-    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms = float(tmax.item())
-    stats = env.stats(allreduce=True).cpu().numpy()          # NCCL all-reduce of the 4-double stats vector
-    env.check_errors()
-    value = total_envs * K_eff / (ms * 1e-3)
-    per_gpu_steps_s = n * K_eff / (ms * 1e-3)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    RA = 64
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    act_pool = None
+    if args.actions == "buffer":
+        act_pool = torch.randint(0, A, (RA, n), dtype=torch.uint8, device=dev, generator=g)
+    env.reset()
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream(device=dev)
+
+    def timed_run(KL, K, W):
+        """Time K vector steps executed as launches of KL steps each (KL = 1: step mode, one dmp_step per
+        vector step; KL > 1: rollout mode, dmp_rollout keeps the state on chip for KL steps).  Returns
+        (ms, steps actually timed, warm-up steps, launches, ring description, clocks)."""
+        # rollout storage: a ring of [KL, n, D] observation buffers larger than 2 x L2, so stores reach HBM
+        obs_bytes = KL * n * D * 4
+        R = min(256, max(2, -(-2 * L2_BYTES // obs_bytes)))
+        obs_ring = torch.empty((R, KL, n, D), dtype=torch.float32, device=dev)
+        rew_ring = torch.empty((R, KL, n), dtype=torch.float32, device=dev)
+        done_ring = torch.empty((R, KL, n), dtype=torch.uint8, device=dev)
+        acts = None
+        if act_pool is not None:
+            acts = [act_pool[(torch.arange(KL) + 7 * j) % RA].contiguous() for j in range(8)]
+        G = max(16 if KL > 1 else 32, R + (R & 1))            # launches per graph (even: t_dev slots alternate)
+
+        def launch(i):
+            env.rollout(KL, actions=None if acts is None else acts[i % 8],
+                        out=(obs_ring[i % R], rew_ring[i % R], done_ring[i % R]), use_device_t=True, t_slot=i & 1)
+
+        with torch.cuda.stream(stream):
+            for i in range(4):
+                launch(i)                                    # sets func attributes before capture
+            stream.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                for i in range(G):
+                    launch(i)
+            per_replay = G * KL
+            n_replay_w = max(1, -(-W // per_replay))
+            n_replay = max(1, -(-K // per_replay))
+            for _ in range(n_replay_w):
+                graph.replay()
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with ClockSampler(local) as clk:
+                e0.record(stream)
+                for _ in range(n_replay):
+                    graph.replay()
+                e1.record(stream)
+                stream.synchronize()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ms = e0.elapsed_time(e1)
+        tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ring = "obs ring of %d x %.1f MB (> 2 x L2) + state %.1f MB" % (R, obs_bytes / 1e6, n * state_bytes / 1e6)
+        del graph, obs_ring, rew_ring, done_ring
+        return float(tm.item()), n_replay * per_replay, n_replay_w * per_replay, n_replay * G, ring, clk.summary()
+
+    def b_alg_of(KL, mean_len=None):
+        """algorithmic bytes per env-step with fp32 observations.
+        step mode: the table value (1D 64/67, 2D 262/268, 3D 330/336 + E); rollout mode:
+        D*4 + 5 + (2*S + 8 + 2*grid_bytes)/K + E.  The action byte is dropped when actions are drawn in-kernel;
+        E = 1600/L (IoU read + map clear per episode of mean length L) is counted for 3D only."""
+        act = 0 if act_pool is None else 1
+        E = (1600.0 / mean_len) if (dim == 3 and mean_len) else 0.0
+        if KL == 1:
+            return b_alg_step - 1 + act + E
+        S, grid = {1: (5, 60), 2: (6, 50), 3: (6, 800)}[dim]
+        return act + D * 4 + 5 + (2 * S + 8 + 2 * grid) / KL + E
+
+    KL = 1 if args.mode == "step" else args.rollout_k
+    ms, K_eff, W_eff, launches, ring, clocks = timed_run(KL, K, W)
+    other = None
+    if not args.single_mode:
+        oKL = args.rollout_k if KL == 1 else 1
+        oms, oK, _, olaunch, oring, _ = timed_run(oKL, max(K // 4, 256), max(W // 4, 64))
+        other = {"mode": "rollout K=%d" % oKL if oKL > 1 else "step", "ms_per_step": oms / oK,
+                 "value": total_envs * oK / (oms * 1e-3), "steps": oK, "gpu_launches": olaunch,
+                 }
+    stats = env.stats(allreduce=True).cpu().numpy()          # NCCL all-reduce of the 4-double stats vector
+    env.check_errors()
+    mean_len = float(stats[3] / stats[2]) if stats[2] > 0 else None
+    b_alg = b_alg_of(KL, mean_len)
+    if other is not None:
+        ob = b_alg_of(1 if KL > 1 else args.rollout_k, mean_len)
+        other["bytes_per_env_step"] = ob
+        other["roofline_frac"] = (other["value"] / world) * ob / 1e9 / peak
+    value = total_envs * K_eff / (ms * 1e-3)
+    per_gpu_steps_s = n * K_eff / (ms * 1e-3)
     achieved = per_gpu_steps_s * b_alg / 1e9
 
     # ---- e2e: the reference-facing call with HOST buffers (actions in, obs/reward/done out) -------
@@ -293,22 +327,24 @@ def run_ours(args):
            "h2d_bytes_per_step": int(hs.h2d_bytes) * world, "d2h_bytes_per_step": int(hs.d2h_bytes) * world,
            "api": "HostStepper.step(actions: np.uint8[N]) -> (obs f32[N,%d], reward f32[N], done bool[N]) numpy, pinned" % D}
 
-    line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K_eff, "warmup": n_replay_w * G,
+    line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K_eff, "warmup": W_eff,
             "ms_per_step": ms / K_eff, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32 bit-grid / i32 counters, f32 observations", "data": "synthetic",
-            "config": {"workload": wl, "total_envs": total_envs, "envs_per_gpu": n, "mode": "step (1 launch per vector step, CUDA graph of %d)" % G,
-                       "actions": ("uniform over %d actions, " % A) + ("ring of %d pre-generated vectors in HBM" % RA if act_ring is not None
+            "config": {"workload": wl, "total_envs": total_envs, "envs_per_gpu": n, "mode": ("step: one dmp_step launch per vector step" if KL == 1 else "rollout: dmp_rollout, %d steps per launch, every step's obs/reward/done materialised" % KL) + ", CUDA-graph replay",
+                       "actions": ("uniform over %d actions, " % A) + ("pool of %d pre-generated vectors in HBM" % RA if act_pool is not None
                                                                           else "Philox4x32-10 in-kernel, counter (global env id, step)"),
                        "step_size": "Philox4x32-10 in-kernel", "auto_reset": True,
-                       "l2": "obs ring of %d x %.1f MB (> 2 x L2) + state %.1f MB" % (R, obs_bytes / 1e6, n * 64 / 1e6),
+                       "l2": ring,
                        "parallelism": "env-sharded x%d, NCCL all-reduce of episode stats only" % world},
-            "clocks": clk.summary(),
-            "e2e": e2e, "gpu_launches": K_eff,
+            "clocks": clocks,
+            "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k%dd_rollout<float> (K=1)" % dim,
+                         "traffic": None, "peak_source": peak_src, "kernel": "k%dd%s_rollout<float> (K=%d)" % (dim, "_tile" if dim == 3 else "", KL),
                          "bytes_per_env_step": b_alg, "envs_per_launch": n},
             "episode_stats": {"sum_return": float(stats[0]), "sum_iou": float(stats[1]), "episodes": float(stats[2]),
                               "steps": float(stats[3])}}
+    if other is not None:
+        line["other_mode"] = other
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, total, wall = cpu_port_throughput(wl, 64, 20000)
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
@@ -325,6 +361,10 @@ def main():
     ap.add_argument("--steps", type=int, default=16384)
     ap.add_argument("--warmup", type=int, default=1024)
     ap.add_argument("--actions", default="philox", choices=["philox", "buffer"])
+    ap.add_argument("--mode", default="rollout", choices=["rollout", "step"],
+                    help="rollout: K steps per launch (dmp_rollout); step: one launch per vector step (dmp_step)")
+    ap.add_argument("--rollout-k", type=int, default=16)
+    ap.add_argument("--single-mode", action="store_true", help="skip the secondary measurement of the other mode")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="2d_static_dense", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="total envs over all GPUs (default: the BASELINE config's)")

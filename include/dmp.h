@@ -61,6 +61,7 @@ extern "C" {
                                 (the dynamic envs' format, e.g. Env/2D/DMP_Env_2D_dynamic_usedata_plan.py:64-65);
                                 computed as an IEEE fp64 division, then cast to the obs type. f32/f64 only */
 #define DMP_F_TSLOT1     4   /* read the step counter from t_dev[1] (see DmpState.t_dev) */
+#define DMP_F_NO_L2_HINT 8   /* tuning switch: plain loads/stores for the env state instead of L2 evict_last */
 
 /* DmpState.plan_mode: which plan an env gets when it auto-resets and DmpIO.next_plan is NULL */
 #define DMP_PLAN_PHILOX      0   /* random_choose_paln=True : counter-based draw                */

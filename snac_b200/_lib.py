@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(PKG, "libdmp.so")
 ABI_VERSION = 1
 OK, EINVAL, ECUDA = 0, 1, 2
 OBS_F32, OBS_F64, OBS_I16 = 0, 1, 2
-F_AUTORESET, F_NORMALISE, F_TSLOT1 = 1, 2, 4
+F_AUTORESET, F_NORMALISE, F_TSLOT1, F_NO_L2_HINT = 1, 2, 4, 8
 PLAN_PHILOX, PLAN_SEQUENTIAL, PLAN_KEEP = 0, 1, 2
 ACT_UNIFORM, ACT_REF3D = 0, 1
 ERR_ACTION, ERR_STEPSIZE, ERR_PLANIDX = 1, 2, 4

@@ -154,11 +154,17 @@ __global__ void __launch_bounds__(B2) k2d_rollout(const DmpState st, const DmpIO
     uint4* cells = reinterpret_cast<uint4*>(st.cells);
     const uint32_t* __restrict__ plans = reinterpret_cast<const uint32_t*>(st.plans);
     uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
+    const uint64_t keep = l2_policy_keep();
+    const bool hint = !(io.flags & DMP_F_NO_L2_HINT);
     if (live) {
-        v0 = cells[env];
-        v1 = cells[n + env];
-        v2 = cells[2 * n + env];
-        v3 = cells[3 * n + env];
+        if (hint) {
+            v0 = ldg_keep(cells + env, keep);
+            v1 = ldg_keep(cells + n + env, keep);
+            v2 = ldg_keep(cells + 2 * n + env, keep);
+            v3 = ldg_keep(cells + 3 * n + env, keep);
+        } else {
+            v0 = cells[env]; v1 = cells[n + env]; v2 = cells[2 * n + env]; v3 = cells[3 * n + env];
+        }
     }
     g[0] = 0; g[B2] = 0;
     g[2 * B2] = v0.x;  g[3 * B2] = v0.y;  g[4 * B2] = v0.z;  g[5 * B2] = v0.w;
@@ -257,11 +263,18 @@ __global__ void __launch_bounds__(B2) k2d_rollout(const DmpState st, const DmpIO
     }
 
     if (live) {
-        if (dirty & 1u) cells[env] = make_uint4(g[2 * B2], g[3 * B2], g[4 * B2], g[5 * B2]);
-        if (dirty & 2u) cells[n + env] = make_uint4(g[6 * B2], g[7 * B2], g[8 * B2], g[9 * B2]);
-        if (dirty & 4u) cells[2 * n + env] = make_uint4(g[10 * B2], g[11 * B2], g[12 * B2], g[13 * B2]);
         pack2(e, g[14 * B2], v3);
-        cells[3 * n + env] = v3;
+        if (hint) {
+            if (dirty & 1u) stg_keep(cells + env, make_uint4(g[2 * B2], g[3 * B2], g[4 * B2], g[5 * B2]), keep);
+            if (dirty & 2u) stg_keep(cells + n + env, make_uint4(g[6 * B2], g[7 * B2], g[8 * B2], g[9 * B2]), keep);
+            if (dirty & 4u) stg_keep(cells + 2 * n + env, make_uint4(g[10 * B2], g[11 * B2], g[12 * B2], g[13 * B2]), keep);
+            stg_keep(cells + 3 * n + env, v3, keep);
+        } else {
+            if (dirty & 1u) cells[env] = make_uint4(g[2 * B2], g[3 * B2], g[4 * B2], g[5 * B2]);
+            if (dirty & 2u) cells[n + env] = make_uint4(g[6 * B2], g[7 * B2], g[8 * B2], g[9 * B2]);
+            if (dirty & 4u) cells[2 * n + env] = make_uint4(g[10 * B2], g[11 * B2], g[12 * B2], g[13 * B2]);
+            cells[3 * n + env] = v3;
+        }
         if (errbits) atomicOr(st.err, errbits);
     }
     if (st.t_dev && blockIdx.x == 0 && tid == 0) st.t_dev[tslot ^ 1] = t0 + (uint64_t)K;

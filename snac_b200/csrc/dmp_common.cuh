@@ -118,6 +118,28 @@ __device__ __forceinline__ void warp_tile_store_full(T* __restrict__ dst, const 
         if (i * 32 + 31 < N16 || i * 32 + lane < N16) __stcs(d4 + i * 32 + lane, v[i]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// L2 residency hints.  Env state is re-read every step while observations are written once and never
+// read back by these kernels: state accesses carry an evict_last policy, observation stores are
+// streaming (__stcs), so that on B200's 126 MB L2 the state of ~10^6 2D envs (67 MB) stays on chip and
+// only the observation stream goes to HBM.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ldg_keep(const uint4* p, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stg_keep(uint4* p, const uint4& v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
+                 ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+
 // host-side helpers ---------------------------------------------------------------------------
 int dmp_set_error(cudaError_t e);   // records e, returns DMP_OK / DMP_ECUDA
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

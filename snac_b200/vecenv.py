@@ -9,6 +9,7 @@ C-ABI call into libdmp.so.  There is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -80,6 +81,7 @@ class BatchedDMPEnv:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.dim, self.dynamic = dim, bool(dynamic)
+        self.l2_hints = os.environ.get("SNAC_B200_L2_HINTS", "1") != "0"
         self.num_envs = int(num_envs)
         self.auto_reset = bool(auto_reset)
         self.obs_dtype, self.normalise = obs_dtype, bool(normalise)
@@ -164,8 +166,13 @@ class BatchedDMPEnv:
     def t(self) -> int:
         return int(self._st.t)
 
-    def _flags(self) -> int:
-        return (L.F_AUTORESET if self.auto_reset else 0) | (L.F_NORMALISE if self.normalise else 0)
+    def _flags(self, K: int = 1) -> int:
+        # L2 evict_last hints for the state pay off when the state can actually stay resident: measured on
+        # B200 (profiles/README.md) they help K>1 rollouts and shards <= ~40 MB, and cost ~4 % on a 67 MB
+        # state stepped one launch at a time (the two L2 partitions hold less than 126 MB of distinct lines).
+        hint = self.l2_hints and (K > 1 or self._cells.numel() <= 40 * 1024 * 1024)
+        return ((L.F_AUTORESET if self.auto_reset else 0) | (L.F_NORMALISE if self.normalise else 0)
+                | (0 if hint else L.F_NO_L2_HINT))
 
     def _u8(self, x, shape, what) -> torch.Tensor:
         if not torch.is_tensor(x):
@@ -245,7 +252,7 @@ class BatchedDMPEnv:
         io.actions, io.step_sizes, io.next_plan = _ptr(a), _ptr(s), _ptr(p)
         io.obs, io.reward, io.done = _ptr(obs), _ptr(rew), _ptr(done)
         io.obs_kind = _TORCH_OBS[self.obs_dtype if obs is None else obs.dtype]
-        io.flags = self._flags() | (L.F_TSLOT1 if (use_device_t and t_slot) else 0)
+        io.flags = self._flags(K) | (L.F_TSLOT1 if (use_device_t and t_slot) else 0)
         self._st.t_dev = self._t_dev.data_ptr() if use_device_t else None
         with torch.cuda.device(self.device):
             L.check(L.lib.dmp_rollout(C.byref(self._st), C.byref(io), int(K), self._stream()), "dmp_rollout")
