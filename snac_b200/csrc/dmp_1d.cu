@@ -161,10 +161,10 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
 #pragma unroll
             for (int j = 0; j < 15; ++j) hw[j] = g[(j + 1) * B1];
             const double iou = iou1_words(hw, plans + e.plan_idx * PLAN1D_BYTES);
-            st.ep_cnt[env] += 1;
-            st.ep_len[env] += (uint32_t)e.cs;
-            st.ep_ret[env] += (double)e.ret;
-            st.ep_iou[env] += iou;
+            atomicAdd(st.ep_cnt + env, 1u);                 // fire-and-forget REDs: no read-modify-write stall
+            atomicAdd(st.ep_len + env, (uint32_t)e.cs);
+            atomicAdd(st.ep_ret + env, (double)e.ret);
+            atomicAdd(st.ep_iou + env, iou);
             if (io.next_plan) {
                 const int p = io.next_plan[idx];
                 if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;

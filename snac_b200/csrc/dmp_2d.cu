@@ -239,10 +239,10 @@ __global__ void __launch_bounds__(B2) k2d_rollout(const DmpState st, const DmpIO
         // ---- (e) done / auto-reset ------------------------------------------------------------
         if (done && autoreset && live) {
             const double iou = iou2(g, plans + e.plan_idx * PLAN2D_WORDS);
-            st.ep_cnt[env] += 1;
-            st.ep_len[env] += (uint32_t)e.cs;
-            st.ep_ret[env] += (double)e.ret;
-            st.ep_iou[env] += iou;
+            atomicAdd(st.ep_cnt + env, 1u);                 // fire-and-forget REDs: no read-modify-write stall
+            atomicAdd(st.ep_len + env, (uint32_t)e.cs);
+            atomicAdd(st.ep_ret + env, (double)e.ret);
+            atomicAdd(st.ep_iou + env, iou);
             if (io.next_plan) {
                 const int p = io.next_plan[idx];
                 if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;

@@ -196,10 +196,10 @@ __global__ void __launch_bounds__(WPB3 * 32) k3d_rollout(const DmpState st, cons
             __syncwarp();
             const double iou = warp_iou3(grid, plans + e.plan_idx * CELLS3D, total_brick, e.cb, lane, true);
             if (lane == 0) {
-                st.ep_cnt[env] += 1;
-                st.ep_len[env] += (uint32_t)e.cs;
-                st.ep_ret[env] += (double)e.ret;
-                st.ep_iou[env] += iou;
+                atomicAdd(st.ep_cnt + env, 1u);                 // fire-and-forget REDs: no read-modify-write stall
+                atomicAdd(st.ep_len + env, (uint32_t)e.cs);
+                atomicAdd(st.ep_ret + env, (double)e.ret);
+                atomicAdd(st.ep_iou + env, iou);
             }
             if (io.next_plan) {
                 const int p = io.next_plan[idx];

@@ -277,10 +277,10 @@ __global__ void __launch_bounds__(WPB * 32) k3d_tile_rollout(const DmpState st, 
             for (int o = 16; o > 0; o >>= 1) cross += __shfl_xor_sync(FULL, cross, o);
             if (lane == src) {
                 const double iou = __ddiv_rn((double)cross, (double)(s_tb + s_cb - cross));
-                st.ep_cnt[env] += 1;
-                st.ep_len[env] += (uint32_t)e.cs;
-                st.ep_ret[env] += (double)e.ret;
-                st.ep_iou[env] += iou;
+                atomicAdd(st.ep_cnt + env, 1u);                 // fire-and-forget REDs: no read-modify-write stall
+                atomicAdd(st.ep_len + env, (uint32_t)e.cs);
+                atomicAdd(st.ep_ret + env, (double)e.ret);
+                atomicAdd(st.ep_iou + env, iou);
                 if (io.next_plan) {
                     const int p = io.next_plan[idx];
                     if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
