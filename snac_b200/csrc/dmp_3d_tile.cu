@@ -15,7 +15,6 @@
 
 namespace {
 
-constexpr int WPB = 2;                       // warps per block
 constexpr int ENV_STRIDE = 816;              // bytes per env in smem: 800 B map + 16 B guard (window over-read)
 constexpr int GUARD = 16;                    // leading guard before env 0 of a warp
 constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -97,15 +96,15 @@ __device__ __forceinline__ void observe_tile(const uint16_t* g, const EnvT& e, O
         const int ir = e.pr - 6 + k;                    // interior row of window row k
         const bool rowvalid = (unsigned)ir < 20u;
         ObsT* o = row + k * 7;
-        uint32_t u0 = 0, u1 = 0, u2 = 0, u3 = 0;
-        if (rowvalid) {
-            const uint32_t* rw = gw + ir * 10 + w0;     // over-reads stay inside the 16 B guards
-            const uint32_t x0 = rw[0], x1 = rw[1], x2 = rw[2], x3 = rw[3], x4 = rw[4];
-            u0 = (__funnelshift_r(x0, x1, sh16) & m[0]) + b0;
-            u1 = (__funnelshift_r(x1, x2, sh16) & m[1]) + b1;
-            u2 = (__funnelshift_r(x2, x3, sh16) & m[2]) + b2;
-            u3 = (__funnelshift_r(x3, x4, sh16) & m[3]) + b3;
-        }
+        // branch-free: rows outside the plan area read a clamped (valid) row and are masked to "frame"
+        const int irc = min(max(ir, 0), 19);
+        const uint32_t rm = rowvalid ? 0xFFFFFFFFu : 0u;
+        const uint32_t* rw = gw + irc * 10 + w0;        // over-reads stay inside the 16 B guards
+        const uint32_t x0 = rw[0], x1 = rw[1], x2 = rw[2], x3 = rw[3], x4 = rw[4];
+        const uint32_t u0 = ((__funnelshift_r(x0, x1, sh16) & m[0]) + b0) & rm;
+        const uint32_t u1 = ((__funnelshift_r(x1, x2, sh16) & m[1]) + b1) & rm;
+        const uint32_t u2 = ((__funnelshift_r(x2, x3, sh16) & m[2]) + b2) & rm;
+        const uint32_t u3 = ((__funnelshift_r(x3, x4, sh16) & m[3]) + b3) & rm;
         ObsT dummy;
         emit_pair<ObsT>(u0, o[0], o[1]);
         emit_pair<ObsT>(u1, o[2], o[3]);
@@ -115,7 +114,10 @@ __device__ __forceinline__ void observe_tile(const uint16_t* g, const EnvT& e, O
     obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, total_step, row[49], row[50]);
 }
 
-template <typename ObsT>
+// WPB = warps per block.  Rollout launches use the largest block that fits the 227 KB of shared memory
+// (7 warps for f32/i16 observations: 7 x (26 128 B maps + 6 528 B tile) = 228.6 KB, one block per SM);
+// single-step launches use 2-warp blocks (3 per SM), which schedule and drain better.
+template <typename ObsT, int WPB>
 __global__ void __launch_bounds__(WPB * 32) k3d_tile_rollout(const DmpState st, const DmpIO io, const int K) {
     extern __shared__ uint4 smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -304,28 +306,34 @@ __global__ void __launch_bounds__(WPB * 32) k3d_tile_rollout(const DmpState st, 
     }
 }
 
-template <typename ObsT>
-int launch_tile(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+template <typename ObsT, int WPB>
+int launch_tile_wpb(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
     const size_t smem = (size_t)WPB * (GUARD + 32 * ENV_STRIDE) + (size_t)WPB * 32 * D3_OBS * sizeof(ObsT) + WPB * 8 + 16;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k3d_tile_rollout<ObsT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k3d_tile_rollout<ObsT, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return dmp_set_error(e);
         attr_done = true;
     }
     const int64_t warps = (st.n_envs + 31) / 32;
     const unsigned blocks = (unsigned)((warps + WPB - 1) / WPB);
-    k3d_tile_rollout<ObsT><<<blocks, WPB * 32, smem, s>>>(st, io, K);
+    k3d_tile_rollout<ObsT, WPB><<<blocks, WPB * 32, smem, s>>>(st, io, K);
     return dmp_set_error(cudaGetLastError());
+}
+
+template <typename ObsT, int WPB_ROLLOUT>
+int launch_tile(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    if (K == 1 || st.n_envs < 32 * WPB_ROLLOUT * 148) return launch_tile_wpb<ObsT, 2>(st, io, K, s);
+    return launch_tile_wpb<ObsT, WPB_ROLLOUT>(st, io, K, s);
 }
 
 }  // namespace
 
 int dmp3d_tile_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
     switch (io.obs_kind) {
-        case DMP_OBS_F32: return launch_tile<float>(st, io, K, s);
-        case DMP_OBS_F64: return launch_tile<double>(st, io, K, s);
-        case DMP_OBS_I16: return launch_tile<int16_t>(st, io, K, s);
+        case DMP_OBS_F32: return launch_tile<float, 7>(st, io, K, s);
+        case DMP_OBS_F64: return launch_tile<double, 5>(st, io, K, s);
+        case DMP_OBS_I16: return launch_tile<int16_t, 7>(st, io, K, s);
     }
     return DMP_EINVAL;
 }
