@@ -51,6 +51,15 @@ CASES = [
     ("3d_dynamic_dense", "3D", "dynamic", dict(density="dense", split="train"), 304, 2400, "uniform"),
     ("3d_dynamic_sparse_refp", "3D", "dynamic", dict(density="sparse", split="train"), 305, 3000, "ref3d"),
     ("3d_dynamic_dense_refp", "3D", "dynamic", dict(density="dense", split="val"), 306, 3000, "ref3d"),
+    # directed, closed-loop scripted policies: they read the reference env's own state
+    ("1d_static_p0_greedy", "1D", "static", dict(plan_choose=0), 401, 1800, "greedy"),
+    ("1d_dynamic_greedy", "1D", "dynamic", dict(density="dense", split="val"), 402, 1800, "greedy"),
+    ("2d_static_dense_greedy", "2D", "static", dict(plan_choose=0), 403, 1500, "greedy"),
+    ("2d_dynamic_sparse_greedy", "2D", "dynamic", dict(density="sparse", split="test"), 404, 1500, "greedy"),
+    ("3d_static_dense_builder", "3D", "static", dict(plan_choose=0), 405, 4000, "builder"),
+    ("3d_static_sparse_builder", "3D", "static", dict(plan_choose=1), 406, 4000, "builder"),
+    ("3d_dynamic_dense_builder", "3D", "dynamic", dict(density="dense", split="test"), 407, 4000, "builder"),
+    ("3d_dynamic_sparse_builder", "3D", "dynamic", dict(density="sparse", split="val"), 408, 4000, "builder"),
 ]
 
 
@@ -69,6 +78,39 @@ def make_env(dim, kind, kw):
     if kind == "static":
         return cls(plan_choose=kw["plan_choose"])
     return cls(data_path=refload.dataset_path(dim, kw["density"], kw["split"]))
+
+
+def scripted_action(env, dim, rng, mode):
+    """Closed-loop policies for the directed traces.  They only READ the reference env's public state
+    (position_memory, environment_memory, plan) -- the env itself is untouched."""
+    if dim == "1D":
+        # fill each column to its plan height (rewards 1 ... 1, 10), sometimes overbuild (-1), sweep right/left
+        pos = env.position_memory[-1]
+        h, p = env.environment_memory[0, pos], env.plan[pos - 2]
+        if h < p or rng.rand() < 0.02:
+            return 2
+        return int(rng.choice([0, 1], p=[0.3, 0.7])) if pos < 31 else 0
+    if dim == "2D":
+        r, c = env.position_memory[-1]
+        on_plan = env.plan[r, c] > 0
+        if (on_plan and env.environment_memory[r, c] == 0 and rng.rand() < 0.9) or rng.rand() < 0.03:
+            return 4                                   # first brick (5.0), double drops and off-plan drops (0)
+        return int(rng.randint(4))
+    # 3D builder: build on adjacent plan cells below target, occasionally overbuild / build at random,
+    # otherwise move in a random direction (legal or not: collisions and walls get exercised)
+    r, c = env.position_memory[-1]
+    g, plan = env.environment_memory, env.plan
+    nbr = [(r, c - 1), (r, c + 1), (r + 1, c), (r - 1, c)]
+    cand = [i for i, (a, b) in enumerate(nbr) if g[a, b] != -1 and g[a, b] < plan[a, b]]
+    free = [i for i, (a, b) in enumerate(nbr) if g[a, b] == 0]
+    u = rng.rand()
+    if cand and len(free) > 1 and u < 0.55:
+        return 4 + int(rng.choice(cand))
+    if u > 0.985:
+        return 4 + int(rng.randint(4))                 # stray build: overbuild (-1), off-plan, against the wall
+    if free and u < 0.97:
+        return int(rng.choice(free))
+    return int(rng.randint(4))
 
 
 def draw_action(rng, mode, n_actions):
@@ -120,7 +162,7 @@ def record(name, dim, kind, kw, seed, T, mode):
 
     do_reset()
     for t in range(T):
-        a = draw_action(rng, mode, A)
+        a = scripted_action(env, dim, rng, mode) if mode in ("greedy", "builder") else draw_action(rng, mode, A)
         o, r, d = env.step(a)
         out["actions"][t], out["step_sizes"][t] = a, env.step_size
         out["obs"][t] = raw_obs(o)
@@ -142,7 +184,10 @@ def record(name, dim, kind, kw, seed, T, mode):
     out["final_grids"] = np.asarray(final_grids, np.int16)
     out["meta"] = np.asarray(json.dumps(dict(name=name, dim=dim, kind=kind, kw=kw, seed=seed, T=T, mode=mode)))
     np.savez_compressed(os.path.join(HERE, "trace_%s.npz" % name), **out)
-    print("%-28s T=%d episodes=%d return=%.1f" % (name, T, int(out["done"].sum()), out["reward"].sum()))
+    rv, rc = np.unique(out["reward"], return_counts=True)
+    print("%-28s T=%d episodes=%d return=%.1f rewards=%s maxh=%d" % (
+        name, T, int(out["done"].sum()), out["reward"].sum(), dict(zip(rv.tolist(), rc.tolist())),
+        int(out["final_grids"].max())))
 
 
 def pack_plans():

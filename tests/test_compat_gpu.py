@@ -20,7 +20,10 @@ def make_compat(meta):
     return cls(plans=load_plans(int(dim[0]), kw["density"], kw["split"]))
 
 
-@pytest.mark.parametrize("name", [n for n in TRACE_NAMES if "dropheavy" not in n and "refp" not in n])
+UNIFORM_TRACES = [n for n in TRACE_NAMES if not any(k in n for k in ("dropheavy", "refp", "greedy", "builder"))]
+
+
+@pytest.mark.parametrize("name", UNIFORM_TRACES)
 def test_scalar_classes_follow_global_numpy_rng(name):
     tr = load_trace(name)
     meta = tr["meta"]
