@@ -138,6 +138,29 @@ def cpu_port_throughput(wl, n_envs_per_proc, n_steps, procs=None):
     return total / max(max(r[1] for r in res), 1e-9), cores, total, wall
 
 
+def cpu_c_port_throughput(wl, n_envs=65536, K=2000):
+    """The same algorithm as a compiled, OpenMP-parallel C port (oracle/dmp_oracle.c) on all host cores:
+    a much stronger CPU baseline than the python port; observations are materialised like on the GPU."""
+    import numpy as np
+    from oracle.c_oracle import COracleBatch
+    dim, dynamic, plan_choose, density, _, _ = WORKLOADS[wl]
+    plans = load_plans_fixture(dim, density) if dynamic else None
+    cb = COracleBatch(dim, dynamic, n_envs, plan_choose, plans)
+    rng = np.random.RandomState(5)
+    cb.reset(rng.randint(cb.n_plans, size=n_envs).astype(np.int32) if dynamic else None)
+    from oracle import dmp_oracle as O
+    A = O.SPEC[dim]["actions"]
+    acts = rng.randint(A, size=(K, n_envs)).astype(np.uint8)
+    sizes = rng.randint(1, 4, size=(K, n_envs)).astype(np.uint8)
+    nxt = rng.randint(cb.n_plans, size=(K, n_envs)).astype(np.int32) if dynamic else None
+    cb.rollout(acts[:20], sizes[:20], None if nxt is None else nxt[:20], want_obs=False)     # warm-up
+    t0 = time.perf_counter()
+    cb.rollout(acts, sizes, nxt, want_obs=False)
+    dt = time.perf_counter() - t0
+    return {"value": n_envs * K / dt, "unit": "env-steps/s", "cores": len(os.sched_getaffinity(0)), "kind": "port-c",
+            "sample": "%d envs x %d steps of %s, C/OpenMP oracle port, reset on done, no obs copy-out (%.2f s)" % (n_envs, K, wl, dt)}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (oracle port, kind "port": the reference is Python
     and cannot travel to the GPU box), all host cores, same metric/config; rank 0 only."""
@@ -165,6 +188,10 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    try:
+        line["cpu_baseline_c"] = cpu_c_port_throughput(wl)
+    except Exception as e:                                  # gcc missing etc.: report, do not fail the arm
+        line["cpu_baseline_c"] = {"unavailable": repr(e)}
     print(json.dumps(line), flush=True)
 
 
@@ -193,10 +220,11 @@ def run_ours(args):
     dim, dynamic, plan_choose, density, default_envs, b_alg_step = WORKLOADS[wl]
     state_bytes = {1: 72, 2: 64, 3: 816}[dim]
     total_envs = args.envs or default_envs
-    n = total_envs // world                              # strong scaling: the batch is sharded
+    from snac_b200.sharding import shard_bounds
+    env_base, n = shard_bounds(total_envs, rank, world)  # strong scaling: the batch is sharded
     env = BatchedDMPEnv(dim, dynamic=dynamic, plan_choose=plan_choose,
                         plans=load_plans_fixture(dim, density) if dynamic else None,
-                        num_envs=n, device=dev, auto_reset=True, env_base=rank * n,
+                        num_envs=n, device=dev, auto_reset=True, env_base=env_base,
                         obs_dtype=torch.float32)
     D, A = env.obs_dim, env.action_dim
     K, W = args.steps, args.warmup
@@ -349,6 +377,10 @@ def run_ours(args):
         v, cores, total, wall = cpu_port_throughput(wl, 64, 20000)
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                 "sample": "%d procs x 64 envs x 20000 steps of %s, python oracle port, reset on done (%.1f s wall)" % (cores, wl, wall)}
+        try:
+            line["cpu_baseline_c"] = cpu_c_port_throughput(wl)
+        except Exception as e:
+            line["cpu_baseline_c"] = {"unavailable": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -310,9 +310,8 @@ class BatchedDMPEnv:
             L.check(L.lib.dmp_stats_reduce(C.byref(self._st), self._stats.data_ptr(),
                                            self._stats_scratch.data_ptr(), self._stream()), "dmp_stats_reduce")
         if allreduce:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                dist.all_reduce(self._stats, op=dist.ReduceOp.SUM)
+            from .sharding import allreduce_stats
+            allreduce_stats(self._stats)
         return self._stats
 
     def clear_stats(self) -> None:
