@@ -81,6 +81,10 @@ _MODULES = {
     ("2D", "dynamic"): ("2D", "DMP_Env_2D_dynamic_usedata_plan", "deep_mobile_printing_2d1r"),
     ("3D", "static"): ("3D", "DMP_simulator_3d_static_circle", "deep_mobile_printing_3d1r"),
     ("3D", "dynamic"): ("3D", "DMP_simulator_3d_dynamic_triangle_usedata", "deep_mobile_printing_3d1r"),
+    # observation-format variants used by the representation-learning baselines
+    ("1D", "lnet"): ("1D", "DMP_Env_1D_static_Lnet", "deep_mobile_printing_1d1r"),
+    ("2D", "lnet"): ("2D", "DMP_Env_2D_static_Lnet", "deep_mobile_printing_2d1r"),
+    ("3D", "lnet"): ("3D", "DMP_simulator_3d_static_circle_Lnet", "deep_mobile_printing_3d1r"),
 }
 
 

@@ -7,9 +7,11 @@ from .vecenv import BatchedDMPEnv, load_plan_dataset  # noqa: F401
 from .compat import (HostStepper, VectorizedEnvWrapper, deep_mobile_printing_1d1r,  # noqa: F401
                      deep_mobile_printing_1d1r_dynamic, deep_mobile_printing_2d1r,
                      deep_mobile_printing_2d1r_dynamic, deep_mobile_printing_3d1r,
-                     deep_mobile_printing_3d1r_dynamic)
+                     deep_mobile_printing_3d1r_dynamic, deep_mobile_printing_1d1r_Lnet,
+                     deep_mobile_printing_2d1r_Lnet, deep_mobile_printing_3d1r_Lnet)
 
 __all__ = ["BatchedDMPEnv", "load_plan_dataset", "HostStepper", "VectorizedEnvWrapper",
            "deep_mobile_printing_1d1r", "deep_mobile_printing_1d1r_dynamic",
            "deep_mobile_printing_2d1r", "deep_mobile_printing_2d1r_dynamic",
-           "deep_mobile_printing_3d1r", "deep_mobile_printing_3d1r_dynamic"]
+           "deep_mobile_printing_3d1r", "deep_mobile_printing_3d1r_dynamic",
+           "deep_mobile_printing_1d1r_Lnet", "deep_mobile_printing_2d1r_Lnet", "deep_mobile_printing_3d1r_Lnet"]

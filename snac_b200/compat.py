@@ -74,6 +74,7 @@ class _ScalarDMP:
     """One reference-style env (N = 1 on the device)."""
     _dim = 0
     _dynamic = False
+    _lnet = False              # *_Lnet observation-format variants (SURVEY.md 8(f) row 2)
 
     def _setup(self, plan_choose=0, data_path=None, random_choose_paln=True, device="cuda", plans=None):
         self.plan_choose = plan_choose
@@ -122,13 +123,16 @@ class _ScalarDMP:
         if self._env is None:
             self._env = BatchedDMPEnv(self._dim, dynamic=self._dynamic, plan_choose=self.plan_choose,
                                       plans=self._plans_arg, num_envs=1, device=self._device,
-                                      obs_dtype=torch.float64, random_choose_paln=self.random_choose_paln)
+                                      obs_dtype=torch.float64, random_choose_paln=self.random_choose_paln,
+                                      dynamic_rules=True if (self._lnet and self._dim == 3) else None)
             self._dense_plans = self._env.plans_dense()
 
     def _sync_attrs(self):
         st = self._env.export_state()
         sc = st["scalars"][0].cpu().numpy()
         self.environment_memory = st["grid"][0].cpu().numpy().astype(np.float64)
+        if self._lnet and self._dim == 2:                    # frame value 2 (Env/2D/DMP_Env_2D_static_Lnet.py:61-64)
+            self.environment_memory[self.environment_memory == -1] = 2
         self._set_count_brick(int(sc[2]))
         self.count_step = int(sc[3])
         pos = int(sc[0]) if self._dim == 1 else [int(sc[0]), int(sc[1])]
@@ -204,6 +208,14 @@ class _ScalarDMP:
         return o
 
     def _format_obs(self, obs, pos, reset):
+        if self._lnet:
+            if self._dim == 1:                               # Env/1D/DMP_Env_1D_static_Lnet.py:83 (+position)
+                return np.hstack((obs, np.array([[pos]], dtype=np.float64)))
+            if self._dim == 2:
+                obs = obs.copy()
+                w = obs[:, :49]
+                w[w == -1] = 2
+            return [self._normalised(obs), pos]              # Env/2D/DMP_Env_2D_static_Lnet.py:75-76
         if not self._dynamic:
             return obs
         if self._dim == 1:                                   # Env/1D/DMP_Env_1D_dynamic_usedata_plan.py:66-70, :114-118
@@ -260,6 +272,22 @@ class deep_mobile_printing_3d1r_dynamic(_ScalarDMP):
 
     def __init__(self, data_path=None, random_choose_paln=True, device="cuda", plans=None):
         self._setup(data_path=data_path, random_choose_paln=random_choose_paln, device=device, plans=plans)
+
+
+class deep_mobile_printing_1d1r_Lnet(deep_mobile_printing_1d1r):
+    """Env/1D/DMP_Env_1D_static_Lnet.py: observation (1,8) = window, count_brick, count_step, position."""
+    _lnet = True
+
+
+class deep_mobile_printing_2d1r_Lnet(deep_mobile_printing_2d1r):
+    """Env/2D/DMP_Env_2D_static_Lnet.py: frame value 2, normalised counters, returns [obs, position]."""
+    _lnet = True
+
+
+class deep_mobile_printing_3d1r_Lnet(deep_mobile_printing_3d1r):
+    """Env/3D/DMP_simulator_3d_static_circle_Lnet.py: static plan, the dynamic class's termination rules
+    (-100 when boxed in), normalised counters, returns [obs, position]."""
+    _lnet = True
 
 
 # --------------------------------------------------------------------------------------------------

@@ -61,6 +61,9 @@ class BatchedDMPEnv:
     obs_dtype         torch.float32 (default), torch.float64 (the reference's dtype) or torch.int16
     normalise         emit the dynamic classes' normalised counter columns (default: False = raw counters)
     env_base          global index of env 0 (multi-GPU sharding; keeps Philox streams shard-independent)
+    dynamic_rules     3D only: use the dataset classes' termination rules (re-check after placement, -100 when
+                      boxed in) independently of where the plan comes from -- the static *_Lnet class does that
+                      (Env/3D/DMP_simulator_3d_static_circle_Lnet.py:210-236).  Default: same as `dynamic`.
     """
 
     def __init__(self, dim: int, *, dynamic: bool = False, plan_choose: int = 0,
@@ -68,7 +71,7 @@ class BatchedDMPEnv:
                  random_choose_paln: bool = True, auto_reset: bool = False,
                  obs_dtype: torch.dtype = torch.float32, normalise: bool = False,
                  seed: int = L.SEED_DEFAULT, env_base: int = 0, action_dist: str = "uniform",
-                 total_step: Optional[int] = None):
+                 total_step: Optional[int] = None, dynamic_rules: Optional[bool] = None):
         if dim not in (1, 2, 3):
             raise ValueError("dim must be 1, 2 or 3")
         if obs_dtype not in _TORCH_OBS:
@@ -139,7 +142,8 @@ class BatchedDMPEnv:
             self._done = torch.zeros(n, dtype=torch.uint8, device=dev)
 
         st = L.DmpState()
-        st.dim, st.dynamic, st.n_plans, st.total_step = dim, int(self.dynamic), self.n_plans, self.total_step
+        self.dynamic_rules = self.dynamic if dynamic_rules is None else bool(dynamic_rules)
+        st.dim, st.dynamic, st.n_plans, st.total_step = dim, int(self.dynamic_rules), self.n_plans, self.total_step
         st.plan_mode = (L.PLAN_KEEP if not self.dynamic else
                         (L.PLAN_PHILOX if random_choose_paln else L.PLAN_SEQUENTIAL))
         st.action_dist = {"uniform": L.ACT_UNIFORM, "ref3d": L.ACT_REF3D}[action_dist]
@@ -375,6 +379,14 @@ class BatchedDMPEnv:
         for dst, src in zip((self._ep_cnt, self._ep_len, self._ep_ret, self._ep_iou), state["ep"]):
             dst.copy_(src)
         self._needs_initial_reset = False
+
+    def transition(self, state: dict, actions, step_sizes=None):
+        """Functional step of the MCTS variants, batched: (state, action) -> (state', obs, reward, done)
+        (Env/1D/DMP_Env_1D_static_MCTS.py:94-145, Env/2D/DMP_ENV_2D_static_MCTS.py:110-169).  `state` is a
+        get_state() snapshot; the env's own state is replaced by it, stepped, and the successor returned."""
+        self.set_state(state)
+        obs, rew, done = self.step(actions, step_sizes)
+        return self.get_state(), obs.clone(), rew.clone(), done.clone()
 
     # plan views ----------------------------------------------------------------------------------
     def plan_table(self) -> torch.Tensor:

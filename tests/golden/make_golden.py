@@ -190,6 +190,43 @@ def record(name, dim, kind, kw, seed, T, mode):
         int(out["final_grids"].max())))
 
 
+def record_lnet(name, dim, plan_choose, seed, T, mode):
+    """Traces of the *_Lnet observation-format variants: 1D appends the position,
+    2D uses 2 for the frame and returns [normalised obs, position], 3D adopts the dynamic termination rules."""
+    env = refload.load_class(dim, "lnet")(plan_choose=plan_choose)
+    np.random.seed(seed)
+    rng = np.random.RandomState(seed + 1)
+    D = 8 if dim == "1D" else 51
+    out = dict(actions=np.zeros(T, np.uint8), step_sizes=np.zeros(T, np.uint8), obs=np.zeros((T, D), np.float64),
+               reward=np.zeros(T, np.float64), done=np.zeros(T, bool), pos=np.zeros((T, 2), np.int16))
+    reset_obs = []
+
+    def flat(o):
+        return (o if dim == "1D" else o[0])[0].astype(np.float64)
+
+    reset_obs.append(flat(env.reset()))
+    for t in range(T):
+        a = scripted_action(env, dim, rng, mode) if mode in ("greedy", "builder") else draw_action(rng, mode, env.action_dim)
+        o, r, d = env.step(a)
+        out["actions"][t], out["step_sizes"][t] = a, env.step_size
+        out["obs"][t], out["reward"][t], out["done"][t] = flat(o), r, d
+        p = env.position_memory[-1]
+        out["pos"][t] = [p, 0] if dim == "1D" else p
+        if dim != "1D":
+            assert list(o[1]) == list(p)
+        if d:
+            reset_obs.append(flat(env.reset()))
+    out["reset_obs"] = np.asarray(reset_obs)
+    out["final_grid"] = env.environment_memory.astype(np.int16)
+    out["meta"] = np.asarray(json.dumps(dict(name=name, dim=dim, kind="lnet", kw=dict(plan_choose=plan_choose), seed=seed, T=T, mode=mode)))
+    np.savez_compressed(os.path.join(HERE, "lnet_%s.npz" % name), **out)
+    print("%-28s T=%d episodes=%d return=%.1f" % (name, T, int(out["done"].sum()), out["reward"].sum()))
+
+
+LNET_CASES = [("1d_p1", "1D", 1, 501, 1600, "greedy"), ("2d_dense", "2D", 0, 502, 1300, "greedy"),
+              ("3d_dense", "3D", 0, 503, 3000, "builder"), ("3d_sparse_uniform", "3D", 1, 504, 1200, "uniform")]
+
+
 def pack_plans():
     out = {}
     for split in ("train", "val", "test"):
@@ -253,4 +290,6 @@ if __name__ == "__main__":
     pack_plans()
     for c in CASES:
         record(*c)
+    for c in LNET_CASES:
+        record_lnet(*c)
     kat()

@@ -126,3 +126,30 @@ def test_invalid_action_raises_unboundlocalerror():
     assert env.count_step == 1          # the reference increments before it fails
     o, r, d = env.step(4)
     assert r == 5.0 or r == 0
+
+
+@pytest.mark.parametrize("name", ["1d_p1", "2d_dense", "3d_dense", "3d_sparse_uniform"])
+def test_lnet_observation_variants_replay_reference(name):
+    """*_Lnet classes vs traces of the unmodified reference Lnet classes."""
+    import json
+    import os
+    import snac_b200 as S
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "lnet_%s.npz" % name))
+    meta = json.loads(str(z["meta"]))
+    cls = {"1D": S.deep_mobile_printing_1d1r_Lnet, "2D": S.deep_mobile_printing_2d1r_Lnet,
+           "3D": S.deep_mobile_printing_3d1r_Lnet}[meta["dim"]]
+    env = cls(plan_choose=meta["kw"]["plan_choose"])
+    flat = lambda o: (o if meta["dim"] == "1D" else o[0])[0]
+    ri = 0
+    assert np.array_equal(flat(env.reset()), z["reset_obs"][ri])
+    for t in range(len(z["actions"])):
+        o, r, d = env.step(int(z["actions"][t]), int(z["step_sizes"][t]))
+        assert np.array_equal(flat(o), z["obs"][t]), (t, flat(o), z["obs"][t])
+        assert r == z["reward"][t] and d == bool(z["done"][t]), t
+        if meta["dim"] != "1D":
+            assert list(o[1]) == list(z["pos"][t])
+        if d:
+            ri += 1
+            assert np.array_equal(flat(env.reset()), z["reset_obs"][ri])
+    assert np.array_equal(env.environment_memory.astype(np.int16).reshape(z["final_grid"].shape), z["final_grid"])

@@ -260,3 +260,28 @@ def test_stage_kernels_equal_fused_step_and_oracle(dim, dynamic, density, ref3d,
         assert torch.equal(x, y)
     assert np.array_equal(staged.episode_stats()[0].cpu().numpy(), ob.ep_cnt)
     assert np.array_equal(staged.episode_stats()[3].cpu().numpy(), ob.ep_iou, equal_nan=True)
+
+
+def test_get_set_state_and_functional_transition():
+    """state snapshots + transition(state, action) (the MCTS variants' surface)."""
+    n = 64
+    env = make_gpu(3, False, n, 0, auto_reset=True, seed=SEED)
+    env.reset()
+    env.rollout(15)
+    s0 = env.get_state()
+    o1, r1, d1 = [x.clone() for x in env.rollout(10)]
+    s1 = env.get_state()
+    env.rollout(7)                                   # wander off, then come back
+    env.set_state(s0)
+    o2, r2, d2 = env.rollout(10)
+    assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+    assert torch.equal(env.get_state()["cells"], s1["cells"]) and torch.equal(env.get_state()["aux"], s1["aux"])
+    # functional transition from s0 with explicit actions == stepping an env that is in s0
+    acts = torch.randint(0, 8, (n,), dtype=torch.uint8, device=env.device)
+    sizes = torch.randint(1, 4, (n,), dtype=torch.uint8, device=env.device)
+    env.set_state(s1)                                # unrelated current state
+    ns, o, r, d = env.transition(s0, acts, sizes)
+    env.set_state(s0)
+    o_, r_, d_ = env.step(acts, sizes)
+    assert torch.equal(o, o_) and torch.equal(r, r_) and torch.equal(d, d_)
+    assert torch.equal(ns["cells"], env.get_state()["cells"])
