@@ -355,6 +355,11 @@ def run_ours(args):
            "h2d_bytes_per_step": int(hs.h2d_bytes) * world, "d2h_bytes_per_step": int(hs.d2h_bytes) * world,
            "api": "HostStepper.step(actions: np.uint8[N]) -> (obs f32[N,%d], reward f32[N], done bool[N]) numpy, pinned" % D}
 
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s|%d|K=%d" % (wl, n, KL))
+    except Exception:
+        pass
     line = {"metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K_eff, "warmup": W_eff,
             "ms_per_step": ms / K_eff, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32 bit-grid / i32 counters, f32 observations", "data": "synthetic",
@@ -367,7 +372,8 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k%dd%s_rollout<float> (K=%d)" % (dim, "_tile" if dim == 3 else "", KL),
+                         "traffic": traffic, "traffic_note": "bytes per launch from the committed ncu capture (profiles/), not measured live; algorithmic bytes per launch = %d" % int(b_alg * n * KL),
+                         "peak_source": peak_src, "kernel": "k%dd%s_rollout<float> (K=%d)" % (dim, "_tile" if dim == 3 else "", KL),
                          "bytes_per_env_step": b_alg, "envs_per_launch": n},
             "episode_stats": {"sum_return": float(stats[0]), "sum_iou": float(stats[1]), "episodes": float(stats[2]),
                               "steps": float(stats[3])}}
