@@ -23,7 +23,8 @@
  *       aux   : unused (NULL)
  *   3D  cells : u16 [n][400]   per-env contiguous 20x20 height map (row-major), 800 B, 16 B aligned
  *       aux   : uint4 [n]      .x = pos_row | pos_col << 8 | plan_idx << 16 ; .y = count_brick | count_step << 16 ;
- *                              .z = episode return (f32 bits) ; .w = reserved
+ *                              .z = episode return (f32 bits) ; .w = running sum(min(height, plan)), the IoU
+ *                              numerator, +1 for every brick laid at or below the plan height
  *   positions are stored in the reference's padded coordinates (1D: 2..31, 2D/3D: 3..22).
  * Plan tables (n_plans rows; static envs have exactly one row)
  *   1D  plans : u8  [n_plans][32]    target heights (30 used)

@@ -22,16 +22,18 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 struct Env3 {
     int pr, pc, plan_idx, cb, cs;
     float ret;
+    int cross;      // sum(min(height, plan)) maintained incrementally: +1 for every brick laid at or below the plan
 };
 
 __device__ __forceinline__ void unpack3(const uint4& a, Env3& e) {
     e.pr = a.x & 0xFF; e.pc = (a.x >> 8) & 0xFF; e.plan_idx = a.x >> 16;
     e.cb = a.y & 0xFFFF; e.cs = a.y >> 16;
     e.ret = __uint_as_float(a.z);
+    e.cross = (int)a.w;
 }
 __device__ __forceinline__ uint4 pack3(const Env3& e) {
     return make_uint4((uint32_t)e.pr | ((uint32_t)e.pc << 8) | ((uint32_t)e.plan_idx << 16),
-                      (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16), __float_as_uint(e.ret), 0u);
+                      (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16), __float_as_uint(e.ret), (uint32_t)e.cross);
 }
 
 // value of environment_memory[r][c] in padded coordinates: -1 on the 3-cell frame (:72-75)
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(WPB3 * 32) k3d_rollout(const DmpState st, cons
             // (b) build on the adjacent cell a-4 unless it is frame (:187-208)
             const int q = a - 4;
             bool built = false;
-            int newh = 0, tr = 0, tc = 0;
+            int newh = 0, tr = 0, tc = 0, pplan = 0;
             int m1[4] = {n1[0], n1[1], n1[2], n1[3]};
             if (a <= 7) {
                 const int nq = (q == 0) ? n1[0] : (q == 1) ? n1[1] : (q == 2) ? n1[2] : n1[3];
@@ -141,6 +143,8 @@ __global__ void __launch_bounds__(WPB3 * 32) k3d_rollout(const DmpState st, cons
                     newh = nq + 1;
                     tr = e.pr + dir_dr(q); tc = e.pc + dir_dc(q);
                     e.cb += 1;
+                    pplan = plans[e.plan_idx * CELLS3D + (tr - 3) * 20 + (tc - 3)];
+                    if (newh <= pplan) e.cross += 1;
                     if (lane == 0) grid[(tr - 3) * 20 + (tc - 3)] = (uint16_t)newh;
 #pragma unroll
                     for (int z = 0; z < 4; ++z) if (z == q) m1[z] = newh;
@@ -157,10 +161,8 @@ __global__ void __launch_bounds__(WPB3 * 32) k3d_rollout(const DmpState st, cons
                 if (e.cb >= total_brick || boxed) { reward = 0.f; done = true; tail = false; }
                 else if (built) { tail = false; done = false; }
             }
-            if (!tail && !done) {                           // reward_check :232-239
-                const int p = plans[e.plan_idx * CELLS3D + (tr - 3) * 20 + (tc - 3)];
-                reward = (newh > p) ? -1.f : (newh == p ? 10.f : 1.f);
-            }
+            if (!tail && !done)                             // reward_check :232-239
+                reward = (newh > pplan) ? -1.f : (newh == pplan ? 10.f : 1.f);
         }
         if (tail) {
             done = (e.cs >= st.total_step) || (!dynamic && boxed);       // static :226 / dynamic :226
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(WPB3 * 32) k3d_rollout(const DmpState st, cons
                 e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
             }
             total_brick = __ldg(st.plan_total + e.plan_idx);
-            e.pr = e.pc = D2_LO; e.cb = e.cs = 0; e.ret = 0.f;
+            e.pr = e.pc = D2_LO; e.cb = e.cs = 0; e.ret = 0.f; e.cross = 0;
             __syncwarp();
         }
     }
@@ -246,7 +248,7 @@ __global__ void k3d_reset(const DmpState st, const uint8_t* __restrict__ mask, c
     const uint4 z = make_uint4(0, 0, 0, 0);
     g4[lane] = z;
     if (lane < 18) g4[lane + 32] = z;
-    if (lane == 0) aux[env] = pack3(Env3{D2_LO, D2_LO, p, 0, 0, 0.f});
+    if (lane == 0) aux[env] = pack3(Env3{D2_LO, D2_LO, p, 0, 0, 0.f, 0});
     if (obs) {
         ObsT* o = obs + env * D3_OBS;
         for (int j = lane; j < D3_OBS; j += 32)
@@ -293,17 +295,23 @@ __global__ void k3d_import(const DmpState st, const int32_t* __restrict__ grid, 
     uint16_t* g = reinterpret_cast<uint16_t*>(st.cells) + env * CELLS3D;
     if (grid)
         for (int i = lane; i < CELLS3D; i += 32) g[i] = (uint16_t)grid[env * 676 + (i / 20 + 3) * 26 + (i % 20 + 3)];
-    if (lane == 0) {
-        uint4* aux = reinterpret_cast<uint4*>(st.aux);
-        Env3 e;
-        unpack3(aux[env], e);
-        if (scalars) {
-            const int32_t* s = scalars + env * 8;
-            e.pr = s[0]; e.pc = s[1]; e.cb = s[2]; e.cs = s[3]; e.plan_idx = s[4];
-        }
-        if (ret) e.ret = ret[env];
-        aux[env] = pack3(e);
+    __syncwarp();
+    uint4* aux = reinterpret_cast<uint4*>(st.aux);
+    Env3 e;
+    unpack3(aux[env], e);
+    if (scalars) {
+        const int32_t* s = scalars + env * 8;
+        e.pr = s[0]; e.pc = s[1]; e.cb = s[2]; e.cs = s[3]; e.plan_idx = s[4];
     }
+    if (ret) e.ret = ret[env];
+    // the running sum(min(height, plan)) must match the (possibly new) map and plan
+    const uint8_t* plan = reinterpret_cast<const uint8_t*>(st.plans) + e.plan_idx * CELLS3D;
+    int cross = 0;
+    for (int i = lane; i < CELLS3D; i += 32) cross += min((int)g[i], (int)plan[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cross += __shfl_xor_sync(FULL, cross, o);
+    e.cross = cross;
+    if (lane == 0) aux[env] = pack3(e);
 }
 
 inline unsigned blocks3(int64_t n) { return (unsigned)((n + WPB3 - 1) / WPB3); }

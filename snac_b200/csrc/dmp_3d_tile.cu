@@ -48,6 +48,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 struct EnvT {
     int pr, pc, plan_idx, cb, cs;
     float ret;
+    int cross;      // running sum(min(height, plan)): +1 per brick laid at or below the plan height
 };
 
 __device__ __forceinline__ int dir_dr(int d) { return d == 2 ? 1 : (d == 3 ? -1 : 0); }
@@ -149,12 +150,13 @@ __global__ void __launch_bounds__(WPB * 32) k3d_tile_rollout(const DmpState st, 
     } else {
         mbar_arrive(bar);
     }
-    EnvT e{D2_LO, D2_LO, 0, 0, 0, 0.f};
+    EnvT e{D2_LO, D2_LO, 0, 0, 0, 0.f, 0};
     if (live) {
         const uint4 a = aux[env];
         e.pr = a.x & 0xFF; e.pc = (a.x >> 8) & 0xFF; e.plan_idx = a.x >> 16;
         e.cb = a.y & 0xFFFF; e.cs = a.y >> 16;
         e.ret = __uint_as_float(a.z);
+        e.cross = (int)a.w;
     }
     int total_brick = __ldg(st.plan_total + e.plan_idx);
     int errbits = 0;
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(WPB * 32) k3d_tile_rollout(const DmpState st, 
             // (b) build on neighbour a-4 unless it is frame
             const int q = a - 4;
             bool built = false;
-            int newh = 0, ti = 0;
+            int newh = 0, ti = 0, pplan = 0;
             int m1[4] = {n1[0], n1[1], n1[2], n1[3]};
             if (a <= 7) {
                 const int nq = (q == 0) ? n1[0] : (q == 1) ? n1[1] : (q == 2) ? n1[2] : n1[3];
@@ -212,6 +214,8 @@ __global__ void __launch_bounds__(WPB * 32) k3d_tile_rollout(const DmpState st, 
                     newh = nq + 1;
                     ti = (e.pr + dir_dr(q) - 3) * 20 + (e.pc + dir_dc(q) - 3);
                     e.cb += 1;
+                    pplan = plans[e.plan_idx * CELLS3D + ti];
+                    if (newh <= pplan) e.cross += 1;
                     g[ti] = (uint16_t)newh;
                     if (live) cells[env * CELLS3D + ti] = (uint16_t)newh;      // write-through
 #pragma unroll
@@ -227,10 +231,7 @@ __global__ void __launch_bounds__(WPB * 32) k3d_tile_rollout(const DmpState st, 
                 if (e.cb >= total_brick || boxed) { done = true; tail = false; }
                 else if (built) { tail = false; }
             }
-            if (!tail && !done) {
-                const int p = plans[e.plan_idx * CELLS3D + ti];
-                reward = (newh > p) ? -1.f : (newh == p ? 10.f : 1.f);
-            }
+            if (!tail && !done) reward = (newh > pplan) ? -1.f : (newh == pplan ? 10.f : 1.f);
         }
         if (tail) done = (e.cs >= st.total_step) || (!dynamic && boxed);
         e.ret += reward;
@@ -249,58 +250,46 @@ __global__ void __launch_bounds__(WPB * 32) k3d_tile_rollout(const DmpState st, 
             if (io.done) io.done[idx] = done ? 1 : 0;
         }
 
-        // ---- (d)/(e) finished episodes: warp-cooperative IoU + clear, then per-lane reset ----------
-        unsigned dm = __ballot_sync(FULL, done && autoreset && live);
+        // ---- (d)/(e) finished episodes ---------------------------------------------------------------
+        // IoU = cross / (total_brick + count_brick - cross) (:257-276) needs no scan: `cross` is kept up to date
+        // by every build.  Each finished lane folds its episode into the statistics and resets its scalars; the
+        // warp then clears the finished envs' height maps cooperatively (ballot, 128-bit coalesced stores).
+        const bool fin = done && autoreset && live;
+        if (fin) {
+            const double iou = __ddiv_rn((double)e.cross, (double)(total_brick + e.cb - e.cross));
+            atomicAdd(st.ep_cnt + env, 1u);                 // fire-and-forget REDs: no read-modify-write stall
+            atomicAdd(st.ep_len + env, (uint32_t)e.cs);
+            atomicAdd(st.ep_ret + env, (double)e.ret);
+            atomicAdd(st.ep_iou + env, iou);
+            if (io.next_plan) {
+                const int p = io.next_plan[idx];
+                if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
+            } else if (st.plan_mode == DMP_PLAN_PHILOX) {
+                if (!need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
+                e.plan_idx = draw_plan(d.x2, st.n_plans);
+            } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
+                e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
+            }
+            total_brick = __ldg(st.plan_total + e.plan_idx);
+            e.pr = e.pc = D2_LO; e.cb = e.cs = 0; e.ret = 0.f; e.cross = 0;
+        }
+        unsigned dm = __ballot_sync(FULL, fin);
         while (dm) {
             const int src = __ffs(dm) - 1;
             dm &= dm - 1;
-            const int s_plan = __shfl_sync(FULL, e.plan_idx, src);
-            const int s_tb = __shfl_sync(FULL, total_brick, src);
-            const int s_cb = __shfl_sync(FULL, e.cb, src);
-            uint4* sg = reinterpret_cast<uint4*>(wgrid + src * ENV_STRIDE);
-            uint4* gg = reinterpret_cast<uint4*>(cells + (env0 + src) * CELLS3D);
-            int cross = 0;
             if (lane < 25) {
-                const uint4 h0 = sg[2 * lane], h1 = sg[2 * lane + 1];
-                const uint4 pp = __ldg(reinterpret_cast<const uint4*>(plans + s_plan * CELLS3D) + lane);
-                const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-                const uint32_t pw[4] = {pp.x, pp.y, pp.z, pp.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int ha = hw[i] & 0xFFFF, hb = hw[i] >> 16;
-                    const int pa = (pw[i >> 1] >> ((i & 1) * 16)) & 0xFF, pb = (pw[i >> 1] >> ((i & 1) * 16 + 8)) & 0xFF;
-                    cross += min(ha, pa) + min(hb, pb);
-                }
+                uint4* sg = reinterpret_cast<uint4*>(wgrid + src * ENV_STRIDE);
+                uint4* gg = reinterpret_cast<uint4*>(cells + (env0 + src) * CELLS3D);
                 const uint4 z = make_uint4(0, 0, 0, 0);
                 sg[2 * lane] = z; sg[2 * lane + 1] = z;
                 gg[2 * lane] = z; gg[2 * lane + 1] = z;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) cross += __shfl_xor_sync(FULL, cross, o);
-            if (lane == src) {
-                const double iou = __ddiv_rn((double)cross, (double)(s_tb + s_cb - cross));
-                atomicAdd(st.ep_cnt + env, 1u);                 // fire-and-forget REDs: no read-modify-write stall
-                atomicAdd(st.ep_len + env, (uint32_t)e.cs);
-                atomicAdd(st.ep_ret + env, (double)e.ret);
-                atomicAdd(st.ep_iou + env, iou);
-                if (io.next_plan) {
-                    const int p = io.next_plan[idx];
-                    if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
-                } else if (st.plan_mode == DMP_PLAN_PHILOX) {
-                    if (!need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
-                    e.plan_idx = draw_plan(d.x2, st.n_plans);
-                } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
-                    e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
-                }
-                total_brick = __ldg(st.plan_total + e.plan_idx);
-                e.pr = e.pc = D2_LO; e.cb = e.cs = 0; e.ret = 0.f;
-            }
-            __syncwarp();
         }
+        __syncwarp();
     }
     if (live) {
         aux[env] = make_uint4((uint32_t)e.pr | ((uint32_t)e.pc << 8) | ((uint32_t)e.plan_idx << 16),
-                              (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16), __float_as_uint(e.ret), 0u);
+                              (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16), __float_as_uint(e.ret), (uint32_t)e.cross);
         if (errbits) atomicOr(st.err, errbits);
         if (st.t_dev && env == 0) st.t_dev[tslot ^ 1] = t0 + (uint64_t)K;
     }

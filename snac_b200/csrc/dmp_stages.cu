@@ -14,7 +14,7 @@ namespace {
 constexpr int SB = 128;
 enum : int { F_PLACED = 1, F_BOXED_PRE = 2, F_BOXED_POST = 4, F_BAD_ACTION = 8, F_WAS_OCC = 16 };
 
-struct Sc { int pr, pc, plan_idx, cb, cs; float ret; };
+struct Sc { int pr, pc, plan_idx, cb, cs; float ret; int cross; };   // cross: 3D running sum(min(h, plan))
 
 __device__ __forceinline__ uint32_t& word_ref(const DmpState& st, int64_t env, int w) {
     return reinterpret_cast<uint32_t*>(st.cells)[((int64_t)(w >> 2) * st.n_envs + env) * 4 + (w & 3)];
@@ -24,15 +24,15 @@ __device__ void load_sc(const DmpState& st, int64_t env, Sc& s) {
     if (st.dim == 1) {
         const uint2 ax = reinterpret_cast<const uint2*>(st.aux)[env];
         const uint32_t c = word_ref(st, env, 15);
-        s = Sc{(int)(ax.x & 0xFFFF), 0, (int)(ax.x >> 16), (int)(c & 0xFFFF), (int)(c >> 16), __uint_as_float(ax.y)};
+        s = Sc{(int)(ax.x & 0xFFFF), 0, (int)(ax.x >> 16), (int)(c & 0xFFFF), (int)(c >> 16), __uint_as_float(ax.y), 0};
     } else if (st.dim == 2) {
         const uint32_t w13 = word_ref(st, env, 13), w14 = word_ref(st, env, 14);
         s = Sc{(int)(w13 & 0xFF), (int)((w13 >> 8) & 0xFF), (int)(w13 >> 16), (int)(w14 & 0xFFFF), (int)(w14 >> 16),
-               __uint_as_float(word_ref(st, env, 15))};
+               __uint_as_float(word_ref(st, env, 15)), 0};
     } else {
         const uint4 a = reinterpret_cast<const uint4*>(st.aux)[env];
         s = Sc{(int)(a.x & 0xFF), (int)((a.x >> 8) & 0xFF), (int)(a.x >> 16), (int)(a.y & 0xFFFF), (int)(a.y >> 16),
-               __uint_as_float(a.z)};
+               __uint_as_float(a.z), (int)a.w};
     }
 }
 
@@ -46,7 +46,7 @@ __device__ void store_sc(const DmpState& st, int64_t env, const Sc& s) {
         word_ref(st, env, 15) = __float_as_uint(s.ret);
     } else {
         reinterpret_cast<uint4*>(st.aux)[env] = make_uint4((uint32_t)s.pr | ((uint32_t)s.pc << 8) | ((uint32_t)s.plan_idx << 16),
-                                                          (uint32_t)(s.cb & 0xFFFF) | ((uint32_t)s.cs << 16), __float_as_uint(s.ret), 0u);
+                                                          (uint32_t)(s.cb & 0xFFFF) | ((uint32_t)s.cs << 16), __float_as_uint(s.ret), (uint32_t)s.cross);
     }
 }
 
@@ -172,6 +172,7 @@ __global__ void k_stage_deposit(const DmpState st, const DmpIO io, int32_t* __re
             if (v != -1) {
                 set_cell(st, env, tr, tc, v + 1);
                 e.cb += 1;
+                if (v + 1 <= plan_cell(st, e.plan_idx, tr, tc)) e.cross += 1;
                 flags |= F_PLACED; sc[1] = v + 1; sc[2] = tr; sc[3] = tc;
             }
         }
@@ -303,6 +304,7 @@ __global__ void k_stage_done_reset(const DmpState st, const DmpIO io) {
     e.pc = st.dim == 1 ? 0 : D2_LO;
     e.cb = e.cs = 0;
     e.ret = 0.f;
+    e.cross = 0;
     store_sc(st, env, e);
 }
 
