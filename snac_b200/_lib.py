@@ -78,7 +78,7 @@ class DmpError(RuntimeError):
 def _load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            "snac_b200: %s is missing -- build it with `python -m snac_b200.build` "
+            "snac_b200: %s is missing -- build it with `python snac_b200/build.py` "
             "(there is no CPU fallback)" % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():

@@ -1,6 +1,6 @@
 """In-tree build of libdmp.so (hand-written sm_100a kernels + the C ABI of include/dmp.h).
 
-    python -m snac_b200.build          # or: from snac_b200.build import build_lib; build_lib()
+    python snac_b200/build.py          # or: from snac_b200.build import build_lib; build_lib()
 
 nvcc cross-compiles for sm_100a without a GPU; the resulting snac_b200/libdmp.so is git-ignored but
 travels with gpurun snapshots.

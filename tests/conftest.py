@@ -32,8 +32,12 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session", autouse=True)
 def _built_library():
     """The C-ABI library must exist for every test session (nvcc cross-compiles without a GPU)."""
-    from snac_b200.build import build_lib
-    build_lib()
+    # loaded by path: importing the package needs libdmp.so to exist already
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_snac_b200_build", os.path.join(ROOT, "snac_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build_lib()
 
 
 TRACE_NAMES = sorted(f[len("trace_"):-len(".npz")] for f in os.listdir(GOLDEN) if f.startswith("trace_"))
