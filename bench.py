@@ -373,7 +373,7 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_note": "bytes per launch from the committed ncu capture (profiles/), not measured live; algorithmic bytes per launch = %d" % int(b_alg * n * KL),
-                         "peak_source": peak_src, "kernel": "k%dd%s_rollout<float> (K=%d)" % (dim, "_tile" if dim == 3 else "", KL),
+                         "peak_source": peak_src, "kernel": "k%dd%s_rollout<float> (K=%d)" % (dim, ("_cache" if KL > 1 else "_tile") if dim == 3 else "", KL),
                          "bytes_per_env_step": b_alg, "envs_per_launch": n},
             "episode_stats": {"sum_return": float(stats[0]), "sum_iou": float(stats[1]), "episodes": float(stats[2]),
                               "steps": float(stats[3])}}

@@ -331,8 +331,14 @@ static int dmp3d_wpe_rollout(const DmpState& st, const DmpIO& io, int K, cudaStr
 }
 
 int dmp3d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
-    static const int use_wpe = []() { const char* v = getenv("DMP_3D_KERNEL"); return (v && v[0] == 'w') ? 1 : 0; }();
-    return use_wpe ? dmp3d_wpe_rollout(st, io, K, s) : dmp3d_tile_rollout(st, io, K, s);
+    // DMP_3D_KERNEL = w (warp per env) | t (u16 tile, bulk async copies) | c (byte cache) forces one kernel;
+    // default: the byte-cache kernel for rollouts (K > 1), the tile kernel for single steps.
+    const char* v = getenv("DMP_3D_KERNEL");             // read per call: tests switch kernels in-process
+    const int forced = v ? (int)v[0] : 0;
+    if (forced == 'w') return dmp3d_wpe_rollout(st, io, K, s);
+    if (forced == 't') return dmp3d_tile_rollout(st, io, K, s);
+    if (forced == 'c') return dmp3d_cache_rollout(st, io, K, s);
+    return K > 1 ? dmp3d_cache_rollout(st, io, K, s) : dmp3d_tile_rollout(st, io, K, s);
 }
 
 int dmp3d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs,

@@ -1,0 +1,353 @@
+// dmp_3d_roll.cu -- 3D envs, rollout kernel (K steps per launch): one env per lane, the warp's 32 height
+// maps cached in shared memory as BYTES.
+//
+// Why a byte cache: the step logic only asks "is this cell -1 / 0 / > 0" and the observation wants the raw
+// height, which for every reachable state of the reference's plans is tiny (plan height 6; an env would have
+// to stack 254 bricks on one cell to leave the byte range).  Halving the cache (404 B instead of 816 B per env)
+// lifts the number of resident warps per SM from 7 to 11 (f32 observations; 14 with i16), which is what this
+// latency-bound kernel needs, and an odd word stride (101) makes same-offset accesses of the 32 lanes
+// bank-conflict free.  HBM keeps the canonical u16 maps; every brick is written through.
+//   * state in : the warp's 32 maps are one contiguous 25 600 B span: coalesced 128-bit loads, low bytes packed
+//                with PRMT, two 32-bit shared stores per 16 B.  An env that holds a height >= 254 anywhere is
+//                flagged "tall" and runs entirely from HBM (exact, slow, practically never).
+//   * step     : neighbours / walk cells / 7x7 window are shared-memory byte reads;
+//   * obs out  : window rows are cut out of the byte map with funnel shifts, biased by +1 (0 = frame), each byte
+//                is dropped into the mantissa of 2^23 (PRMT) and turned into -1/0/h by one FADD; the warp's
+//                [32][51] tile is streamed out as one contiguous span of 128-bit stores;
+//   * done     : IoU needs no scan (`cross` is maintained by every build); the warp clears a finished env's
+//                map cooperatively in shared memory and in HBM.
+// Semantics: Env/3D/DMP_simulator_3d_static_circle.py:67-276 and
+// Env/3D/DMP_simulator_3d_dynamic_triangle_usedata.py:45-277 (same citations as dmp_3d.cu, whose warp-per-env
+// kernel and dmp_3d_tile.cu's u16 tile kernel remain as cross-checks; tests compare all three).
+#include <stdlib.h>
+#include "dmp_common.cuh"
+
+namespace {
+
+constexpr int MAP_B = 404;                    // bytes per env in the cache: 400 cells + 4 pad = 101 words (odd)
+constexpr int FRONT = 16;                     // guard in front of env 0 of a warp (window over-read, alignment)
+constexpr int WARP_MAP_B = FRONT + 32 * MAP_B;  // 12 944 (multiple of 16)
+constexpr int TALL = 254;                     // heights >= TALL do not fit the byte cache (+1 bias included)
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr uint32_t COLVALID = 0x7FFFF8u;      // padded columns 3..22 are inside the plan area
+constexpr size_t SMEM_MAX = 232448;           // 227 KB opt-in limit per block
+
+struct EnvR {
+    int pr, pc, plan_idx, cb, cs;
+    float ret;
+    int cross;      // running sum(min(height, plan)): +1 per brick laid at or below the plan height
+};
+
+__device__ __forceinline__ int dir_dr(int d) { return d == 2 ? 1 : (d == 3 ? -1 : 0); }
+__device__ __forceinline__ int dir_dc(int d) { return d == 0 ? -1 : (d == 1 ? 1 : 0); }
+
+// environment_memory[r][c] (padded coordinates) from the byte cache; -1 on the frame (:72-75)
+__device__ __forceinline__ int cell_c(const uint8_t* gb, int r, int c) {
+    const unsigned ir = (unsigned)(r - 3), ic = (unsigned)(c - 3);
+    return (ir < 20u && ic < 20u) ? (int)gb[ir * 20u + ic] : -1;
+}
+// the same from HBM (tall envs only); .cg: other lanes of the warp clear maps with plain stores
+__device__ __forceinline__ int cell_g(const uint16_t* ge, int r, int c) {
+    const unsigned ir = (unsigned)(r - 3), ic = (unsigned)(c - 3);
+    return (ir < 20u && ic < 20u) ? (int)__ldcg(ge + ir * 20u + ic) : -1;
+}
+
+// out-of-line copy for the tall-env path (keeps the hot loop small)
+__device__ __noinline__ int cell_tall(const uint16_t* ge, int r, int c) { return cell_g(ge, r, c); }
+
+template <typename ObsT>
+__device__ __noinline__ void observe_tall(const uint16_t* ge, int pr, int pc, ObsT* row) {
+    for (int k = 0; k < 7; ++k)
+        for (int j = 0; j < 7; ++j) row[k * 7 + j] = obs_from_int<ObsT>(cell_g(ge, pr - 3 + k, pc - 3 + j));
+}
+
+__device__ __forceinline__ uint64_t spread7(uint32_t x) {       // bit j -> byte j (see dmp_2d.cu)
+    return ((uint64_t)x * 0x0002040810204081ull) & 0x0101010101010101ull;
+}
+
+// biased byte (height + 1, 0 = frame) -> observation value
+template <typename ObsT, int BYTE>
+__device__ __forceinline__ ObsT obs_from_biased(uint32_t packed) {
+    if constexpr (sizeof(ObsT) == 4) {
+        return __uint_as_float(__byte_perm(packed, 0x4B000000u, 0x7650u + BYTE)) - 8388609.0f;
+    } else {
+        return obs_from_int<ObsT>((int)((packed >> (8 * BYTE)) & 0xFFu) - 1);
+    }
+}
+
+// stage (c): 7x7 window of this lane's env (byte cache) -> its row of the warp tile
+template <typename ObsT>
+__device__ __forceinline__ void observe_cache(const uint8_t* gb, int pr, int pc, ObsT* row) {
+    const uint32_t cv = (COLVALID >> (pc - 3)) & 0x7Fu;           // window column j lies inside the plan area
+    const uint64_t one = spread7(cv);                              // 0x01 per valid byte
+    const uint32_t b0 = (uint32_t)one, b1 = (uint32_t)(one >> 32);
+    const uint32_t m0 = b0 * 0xFFu, m1 = b1 * 0xFFu;               // 0xFF per valid byte (no carries)
+    const int ob = pc - 6;                                         // byte offset of window column 0 inside a row
+    const uint32_t* gw = reinterpret_cast<const uint32_t*>(gb);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const int ir = pr - 6 + k;                                 // interior row of window row k
+        const bool rowvalid = (unsigned)ir < 20u;
+        const int o = min(max(ir, 0), 19) * 20 + ob;               // -3 .. 396; over-reads stay inside the pads
+        const uint32_t* rw = gw + (o >> 2);
+        const int shb = (o & 3) * 8;
+        const uint32_t x0 = rw[0], x1 = rw[1], x2 = rw[2];
+        const uint32_t q0 = __funnelshift_r(x0, x1, shb), q1 = __funnelshift_r(x1, x2, shb);
+        const uint32_t u0 = rowvalid ? ((q0 & m0) + b0) : 0u;
+        const uint32_t u1 = rowvalid ? ((q1 & m1) + b1) : 0u;
+        ObsT* o7 = row + k * 7;
+        o7[0] = obs_from_biased<ObsT, 0>(u0);
+        o7[1] = obs_from_biased<ObsT, 1>(u0);
+        o7[2] = obs_from_biased<ObsT, 2>(u0);
+        o7[3] = obs_from_biased<ObsT, 3>(u0);
+        o7[4] = obs_from_biased<ObsT, 0>(u1);
+        o7[5] = obs_from_biased<ObsT, 1>(u1);
+        o7[6] = obs_from_biased<ObsT, 2>(u1);
+    }
+}
+
+// shared memory: [WPB][WARP_MAP_B] byte maps | [WPB][32*51] ObsT tiles | [WPB] tall-env flag words
+template <typename ObsT>
+__host__ __device__ constexpr size_t warp_smem_bytes() { return (size_t)WARP_MAP_B + 32 * D3_OBS * sizeof(ObsT) + 4; }
+
+template <typename ObsT>
+__global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, const DmpIO io, const int K) {
+    extern __shared__ uint4 smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int64_t n = st.n_envs;
+    const int64_t env0 = ((int64_t)blockIdx.x * wpb + warp) * 32;
+    if (env0 >= n) return;                                            // whole warp leaves together
+    const int64_t env = env0 + lane;
+    const bool live = env < n;
+    const int nvalid = (int)min((int64_t)32, n - env0);
+
+    uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw);
+    uint8_t* wmap = base + (size_t)warp * WARP_MAP_B + FRONT;
+    ObsT* tile = reinterpret_cast<ObsT*>(base + (size_t)wpb * WARP_MAP_B) + warp * (32 * D3_OBS);
+    uint32_t* tallword = reinterpret_cast<uint32_t*>(base + (size_t)wpb * (WARP_MAP_B + 32 * D3_OBS * sizeof(ObsT))) + warp;
+    uint8_t* gb = wmap + lane * MAP_B;                                // this lane's byte map
+
+    uint16_t* cells = reinterpret_cast<uint16_t*>(st.cells);
+    uint16_t* ge = cells + (live ? env : env0) * CELLS3D;             // this lane's map in HBM
+    uint4* aux = reinterpret_cast<uint4*>(st.aux);
+    const uint8_t* __restrict__ plans = reinterpret_cast<const uint8_t*>(st.plans);
+
+    // ---- state in: coalesced 128-bit loads of the warp's contiguous maps, packed to bytes -------------
+    if (lane == 0) *tallword = 0u;
+    __syncwarp();
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(cells + env0 * CELLS3D);
+        const int nvec = nvalid * (CELLS3D / 8);                      // 50 vectors of 8 cells per env
+        constexpr int U = 10;
+#pragma unroll 1
+        for (int i0 = 0; i0 < CELLS3D / 8; i0 += U) {
+            uint4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = (i0 + u) * 32 + lane;
+                v[u] = (idx < nvec) ? src[idx] : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = (i0 + u) * 32 + lane;
+                const int el = idx / (CELLS3D / 8), j = idx - el * (CELLS3D / 8);
+                const uint32_t lo = __byte_perm(v[u].x, v[u].y, 0x6420u), hi = __byte_perm(v[u].z, v[u].w, 0x6420u);
+                const uint32_t any = v[u].x | v[u].y | v[u].z | v[u].w;
+                // conservative: true whenever one of the 8 heights is >= 254 (false positives only cost speed)
+                const bool tall = (any & 0xFF00FF00u) || ((any & 0xFEu) == 0xFEu) || ((any & 0xFE0000u) == 0xFE0000u);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(wmap + el * MAP_B + j * 8);
+                dst[0] = lo; dst[1] = hi;                             // lanes beyond nvec write zeros into their own slots
+                if (tall) atomicOr(tallword, 1u << el);
+            }
+        }
+    }
+    EnvR e{D2_LO, D2_LO, 0, 0, 0, 0.f, 0};
+    if (live) {
+        const uint4 a = aux[env];
+        e.pr = a.x & 0xFF; e.pc = (a.x >> 8) & 0xFF; e.plan_idx = a.x >> 16;
+        e.cb = a.y & 0xFFFF; e.cs = a.y >> 16;
+        e.ret = __uint_as_float(a.z);
+        e.cross = (int)a.w;
+    }
+    int total_brick = __ldg(st.plan_total + e.plan_idx);
+    int errbits = 0;
+    const bool dynamic = st.dynamic != 0;
+    const bool autoreset = io.flags & DMP_F_AUTORESET;
+    const bool normalise = io.flags & DMP_F_NORMALISE;
+    const bool need_draw = (io.actions == nullptr) || (io.step_sizes == nullptr);
+    const int tslot = (io.flags & DMP_F_TSLOT1) ? 1 : 0;
+    const uint64_t t0 = st.t_dev ? st.t_dev[tslot] : st.t;
+    __syncwarp();
+    bool tall = live && ((*tallword >> lane) & 1u);                   // this env runs from HBM
+
+    for (int k = 0; k < K; ++k) {
+        const uint64_t t = t0 + (uint64_t)k;
+        const int64_t idx = (int64_t)k * n + env;
+        Draw d = Draw{0, 0, 0, 0};
+        if (need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
+        int a, s;
+        if (io.actions) a = live ? (int)io.actions[idx] : 0; else a = draw_action(d, D3_ACT, st.action_dist);
+        if (io.step_sizes) s = live ? (int)io.step_sizes[idx] : 1; else s = draw_step_size(d);
+        if ((unsigned)(s - 1) > 2u) errbits |= DMP_ERR_STEPSIZE;
+        if (a > 7) errbits |= DMP_ERR_ACTION;              // reference: an unbuilt brick (:187-208)
+
+        e.cs += 1;
+        // ---- the six cells this step can depend on: the four neighbours (check_sur :88-102) and the second and
+        // third cell in the action's direction (move_step :104-134) -------------------------------------
+        const int dir = a & 3, dr = dir_dr(dir), dc = dir_dc(dir);
+        int c6[6];
+        if (!tall) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c6[q] = cell_c(gb, e.pr + dir_dr(q), e.pc + dir_dc(q));
+            c6[4] = cell_c(gb, e.pr + 2 * dr, e.pc + 2 * dc);
+            c6[5] = cell_c(gb, e.pr + 3 * dr, e.pc + 3 * dc);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c6[q] = cell_tall(ge, e.pr + dir_dr(q), e.pc + dir_dc(q));
+            c6[4] = cell_tall(ge, e.pr + 2 * dr, e.pc + 2 * dc);
+            c6[5] = cell_tall(ge, e.pr + 3 * dr, e.pc + 3 * dc);
+        }
+        const bool boxed = (c6[0] != 0) && (c6[1] != 0) && (c6[2] != 0) && (c6[3] != 0);     // check_sur
+        const int nsel = (dir == 0) ? c6[0] : (dir == 1) ? c6[1] : (dir == 2) ? c6[2] : c6[3];
+
+        float reward = 0.f;
+        bool done = false, tail = true;
+        if (a <= 3) {
+            // (a) move_step (:104-134): consecutive empty cells, at most s
+            int nstep = 0;
+            if (nsel == 0) nstep = (s >= 2 && c6[4] == 0) ? ((s >= 3 && c6[5] == 0) ? 3 : 2) : 1;
+            e.pr = min(max(e.pr + dr * nstep, D2_LO), D2_HI);
+            e.pc = min(max(e.pc + dc * nstep, D2_LO), D2_HI);
+        } else {
+            // (b) build on neighbour a-4 unless it is frame
+            bool built = false;
+            int newh = 0, pplan = 0;
+            bool open_after = (c6[0] == 0) || (c6[1] == 0) || (c6[2] == 0) || (c6[3] == 0);   // some neighbour still empty
+            if (a <= 7 && nsel != -1) {
+                built = true;
+                newh = nsel + 1;
+                const int ti = (e.pr + dr - 3) * 20 + (e.pc + dc - 3);
+                e.cb += 1;
+                pplan = plans[e.plan_idx * CELLS3D + ti];
+                if (newh <= pplan) e.cross += 1;
+                if (!tall) gb[ti] = (uint8_t)newh;
+                if (live) {
+                    ge[ti] = (uint16_t)newh;                                   // write-through
+                    if (newh >= TALL) tall = true;                             // the byte cache stops being exact
+                }
+                // neighbours after placement: only neighbour `dir` changed, and it is now > 0
+                open_after = ((dir != 0) && c6[0] == 0) || ((dir != 1) && c6[1] == 0) ||
+                             ((dir != 2) && c6[2] == 0) || ((dir != 3) && c6[3] == 0);
+            }
+            if (dynamic) {                                   // re-check after placement (:199-231)
+                if (!open_after) { reward = -100.f; done = true; tail = false; }
+                else if (e.cb >= total_brick) { done = true; tail = false; }
+                else if (built) { tail = false; }
+            } else {                                         // static (:210-230)
+                if (e.cb >= total_brick || boxed) { done = true; tail = false; }
+                else if (built) { tail = false; }
+            }
+            if (!tail && !done) reward = (newh > pplan) ? -1.f : (newh == pplan ? 10.f : 1.f);
+        }
+        if (tail) done = (e.cs >= st.total_step) || (!dynamic && boxed);
+        e.ret += reward;
+
+        // ---- (c) observation --------------------------------------------------------------------
+        if (io.obs) {
+            ObsT* row = tile + lane * D3_OBS;
+            if (!tall) observe_cache<ObsT>(gb, e.pr, e.pc, row);
+            else observe_tall<ObsT>(ge, e.pr, e.pc, row);
+            obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, st.total_step, row[49], row[50]);
+            __syncwarp();
+            ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * D3_OBS;
+            if (nvalid == 32) warp_tile_store_full<ObsT, 32 * D3_OBS>(dst, tile, lane);
+            else warp_tile_store<ObsT>(dst, tile, nvalid * D3_OBS, lane);
+            __syncwarp();
+        }
+        if (live) {
+            if (io.reward) io.reward[idx] = reward;
+            if (io.done) io.done[idx] = done ? 1 : 0;
+        }
+
+        // ---- (d)/(e) finished episodes ---------------------------------------------------------------
+        // IoU = cross / (total_brick + count_brick - cross) (:257-276); `cross` is kept up to date by every build.
+        const bool fin = done && autoreset && live;
+        if (fin) {
+            const double iou = __ddiv_rn((double)e.cross, (double)(total_brick + e.cb - e.cross));
+            atomicAdd(st.ep_cnt + env, 1u);                 // fire-and-forget REDs: no read-modify-write stall
+            atomicAdd(st.ep_len + env, (uint32_t)e.cs);
+            atomicAdd(st.ep_ret + env, (double)e.ret);
+            atomicAdd(st.ep_iou + env, iou);
+            if (io.next_plan) {
+                const int p = io.next_plan[idx];
+                if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
+            } else if (st.plan_mode == DMP_PLAN_PHILOX) {
+                if (!need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
+                e.plan_idx = draw_plan(d.x2, st.n_plans);
+            } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
+                e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
+            }
+            total_brick = __ldg(st.plan_total + e.plan_idx);
+            e.pr = e.pc = D2_LO; e.cb = e.cs = 0; e.ret = 0.f; e.cross = 0;
+            tall = false;
+        }
+        unsigned dm = __ballot_sync(FULL, fin);
+        while (dm) {                                        // the warp clears each finished env's map
+            const int src = __ffs(dm) - 1;
+            dm &= dm - 1;
+            uint32_t* sg = reinterpret_cast<uint32_t*>(wmap + src * MAP_B);
+            sg[lane] = 0u; sg[lane + 32] = 0u; sg[lane + 64] = 0u;
+            if (lane < 4) sg[lane + 96] = 0u;
+            if (lane < 25) {
+                uint4* gg = reinterpret_cast<uint4*>(cells + (env0 + src) * CELLS3D);
+                const uint4 z = make_uint4(0, 0, 0, 0);
+                gg[2 * lane] = z; gg[2 * lane + 1] = z;
+            }
+        }
+        __syncwarp();
+    }
+    if (live) {
+        aux[env] = make_uint4((uint32_t)e.pr | ((uint32_t)e.pc << 8) | ((uint32_t)e.plan_idx << 16),
+                              (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16), __float_as_uint(e.ret), (uint32_t)e.cross);
+        if (errbits) atomicOr(st.err, errbits);
+        if (st.t_dev && env == 0) st.t_dev[tslot ^ 1] = t0 + (uint64_t)K;
+    }
+}
+
+// Launch shape.  Every warp is an independent tile of 32 envs, so blocks are single warps unless DMP_3D_WPB
+// says otherwise: the block scheduler then refills an SM warp by warp instead of waiting for the slowest
+// warp of a big block.  Shared memory alone limits residency (11 warps per SM for f32 observations).
+template <typename ObsT>
+int launch_cache(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    const char* wv = getenv("DMP_3D_WPB");
+    const int wpb_env = wv ? atoi(wv) : 0;
+    const size_t per_warp = warp_smem_bytes<ObsT>();
+    const int wmax = (int)((SMEM_MAX - 16) / per_warp);
+    int wpb = wpb_env > 0 ? wpb_env : 1;
+    if (wpb > wmax) wpb = wmax;
+    if (wpb > 11) wpb = 11;                                  // __launch_bounds__(352)
+    const size_t smem = (size_t)wpb * per_warp + 16;
+    static size_t attr_smem = 0;                             // per instantiation
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(k3d_cache_rollout<ObsT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return dmp_set_error(e);
+        e = cudaFuncSetAttribute(k3d_cache_rollout<ObsT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e != cudaSuccess) return dmp_set_error(e);
+        attr_smem = smem;
+    }
+    const int64_t warps = (st.n_envs + 31) / 32;
+    const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
+    k3d_cache_rollout<ObsT><<<blocks, wpb * 32, smem, s>>>(st, io, K);
+    return dmp_set_error(cudaGetLastError());
+}
+
+}  // namespace
+
+int dmp3d_cache_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    switch (io.obs_kind) {
+        case DMP_OBS_F32: return launch_cache<float>(st, io, K, s);
+        case DMP_OBS_F64: return launch_cache<double>(st, io, K, s);
+        case DMP_OBS_I16: return launch_cache<int16_t>(st, io, K, s);
+    }
+    return DMP_EINVAL;
+}

@@ -2,6 +2,8 @@
 Bit-exact: grids, positions, counters, observations, done flags, rewards (small integers in f32).
 IoU / normalised counters: IEEE fp64 division on both sides -> compared exactly, with a 1e-6
 relative fallback stated in BASELINE.json's north_star."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -285,3 +287,92 @@ def test_get_set_state_and_functional_transition():
     o_, r_, d_ = env.step(acts, sizes)
     assert torch.equal(o, o_) and torch.equal(r, r_) and torch.equal(d, d_)
     assert torch.equal(ns["cells"], env.get_state()["cells"])
+
+
+# ------------------------------------------------------------------------------------------------
+# 7. the three 3D kernels (warp per env / u16 tile / byte cache) are interchangeable, and the byte-cache
+#    kernel's "tall env" path (a height >= 254 somewhere: the env runs from HBM) is exact
+# ------------------------------------------------------------------------------------------------
+def _with_kernel(kind, fn):
+    old = os.environ.get("DMP_3D_KERNEL")
+    os.environ["DMP_3D_KERNEL"] = kind
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ["DMP_3D_KERNEL"]
+        else:
+            os.environ["DMP_3D_KERNEL"] = old
+
+
+@pytest.mark.parametrize("dynamic", [False, True])
+@pytest.mark.parametrize("K", [1, 37])
+def test_3d_kernels_agree(dynamic, K):
+    plans = load_plans(3, "dense", "train") if dynamic else None
+    n = 333                                                   # ragged last warp
+    outs = {}
+    for kind in "wtc":
+        env = make_gpu(3, dynamic, n, 0, plans, auto_reset=True, env_base=99, seed=SEED, normalise=dynamic,
+                       obs_dtype=torch.float64 if dynamic else torch.float32)
+        env.reset()
+
+        def run():
+            res = [[x.clone() for x in env.rollout(K)] for _ in range(120 // K + 1)]
+            torch.cuda.synchronize()
+            return res
+        res = _with_kernel(kind, run)
+        st = env.get_state()
+        outs[kind] = (res, st["cells"].clone(), st["aux"].clone(), [x.clone() for x in env.episode_stats()])
+        env.check_errors()
+    for kind in "tc":
+        for a, b in zip(outs["w"][0], outs[kind][0]):
+            for x, y in zip(a, b):
+                assert torch.equal(x, y), kind
+        assert torch.equal(outs["w"][1], outs[kind][1]) and torch.equal(outs["w"][2], outs[kind][2]), kind
+        for x, y in zip(outs["w"][3], outs[kind][3]):
+            assert torch.equal(x, y), kind
+
+
+@pytest.mark.parametrize("kind", ["c", "t"])
+@pytest.mark.parametrize("dynamic", [False, True])
+def test_3d_tall_columns_match_oracle(kind, dynamic):
+    """Heights around and far beyond the byte range (252..256, 300, 40000) next to the agent: builds on top of
+    them, walks blocked by them and windows over them must equal the oracle's."""
+    plans = load_plans(3, "dense", "train") if dynamic else None
+    n, K = 70, 48
+    rng = np.random.RandomState(11)
+    env = make_gpu(3, dynamic, n, 0, plans, auto_reset=False, seed=SEED, obs_dtype=torch.float32)
+    ob = OracleBatch(3, dynamic, n, 0, plans)
+    p0 = rng.randint(ob.n_plans, size=n).astype(np.int32) if dynamic else None
+    env.reset(plan_idx=p0)
+    ob.reset(p0)
+    g, sc = ob.export()
+    tall_values = [252, 253, 254, 255, 256, 300, 40000]
+    for i, e in enumerate(ob.envs):
+        r, c = int(rng.randint(5, 21)), int(rng.randint(5, 21))
+        e.pos = [r, c]
+        if hasattr(e, "position_memory"):
+            e.position_memory = [[r, c]]
+        for _ in range(rng.randint(0, 4)):                    # some envs stay short
+            dr, dc = [(0, 1), (0, -1), (1, 0), (-1, 0), (1, 1), (2, 0)][rng.randint(6)]
+            e.grid[r + dr, c + dc] = tall_values[rng.randint(len(tall_values))]
+    g, sc = ob.export()
+    env.import_state(grid=g, scalars=sc)
+    acts = rng.choice(8, size=(K, n), p=[.08, .08, .08, .08, .17, .17, .17, .17]).astype(np.uint8)
+    sizes = rng.randint(1, 4, size=(K, n)).astype(np.uint8)
+    r_obs, r_rew, r_done, _, _ = philox_rollout(ob, K, SEED, 0, 0, 8, auto_reset=False, actions=acts, step_sizes=sizes)
+
+    def run():
+        out = env.rollout(K, actions=torch.as_tensor(acts, device=env.device), step_sizes=torch.as_tensor(sizes, device=env.device))
+        torch.cuda.synchronize()
+        return out
+    obs, rew, done = _with_kernel(kind, run)
+    assert np.array_equal(obs.cpu().numpy().astype(np.float64), r_obs)
+    assert np.array_equal(rew.cpu().numpy(), r_rew)
+    assert np.array_equal(done.cpu().numpy(), r_done)
+    g_ref, sc_ref = ob.export()
+    st = env.export_state()
+    assert np.array_equal(st["grid"].cpu().numpy().reshape(g_ref.shape), g_ref)
+    assert np.array_equal(st["scalars"].cpu().numpy()[:, :4], sc_ref[:, :4])
+    assert g_ref.max() > 40000 or g_ref.max() >= 254
+    assert np.array_equal(env.iou().cpu().numpy(), ob.iou(), equal_nan=True)
