@@ -25,8 +25,9 @@
 namespace {
 
 constexpr int MAP_B = 404;                    // bytes per env in the cache: 400 cells + 4 pad = 101 words (odd)
-constexpr int FRONT = 16;                     // guard in front of env 0 of a warp (window over-read, alignment)
-constexpr int WARP_MAP_B = FRONT + 32 * MAP_B;  // 12 944 (multiple of 16)
+constexpr int FRONT = 80;                     // guard in front of env 0 of a warp: unclamped reads reach 64 B back
+constexpr int WARP_MAP_B = FRONT + 32 * MAP_B;  // 13 008 (multiple of 16); reads past the end land in the next
+                                              // warp's guard or in the tiles
 constexpr int TALL = 254;                     // heights >= TALL do not fit the byte cache (+1 bias included)
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr uint32_t COLVALID = 0x7FFFF8u;      // padded columns 3..22 are inside the plan area
@@ -41,12 +42,8 @@ struct EnvR {
 __device__ __forceinline__ int dir_dr(int d) { return d == 2 ? 1 : (d == 3 ? -1 : 0); }
 __device__ __forceinline__ int dir_dc(int d) { return d == 0 ? -1 : (d == 1 ? 1 : 0); }
 
-// environment_memory[r][c] (padded coordinates) from the byte cache; -1 on the frame (:72-75)
-__device__ __forceinline__ int cell_c(const uint8_t* gb, int r, int c) {
-    const unsigned ir = (unsigned)(r - 3), ic = (unsigned)(c - 3);
-    return (ir < 20u && ic < 20u) ? (int)gb[ir * 20u + ic] : -1;
-}
-// the same from HBM (tall envs only); .cg: other lanes of the warp clear maps with plain stores
+// environment_memory[r][c] (padded coordinates) from HBM (tall envs only); -1 on the frame (:72-75).
+// .cg: other lanes of the warp clear maps with plain stores.
 __device__ __forceinline__ int cell_g(const uint16_t* ge, int r, int c) {
     const unsigned ir = (unsigned)(r - 3), ic = (unsigned)(c - 3);
     return (ir < 20u && ic < 20u) ? (int)__ldcg(ge + ir * 20u + ic) : -1;
@@ -75,23 +72,22 @@ __device__ __forceinline__ ObsT obs_from_biased(uint32_t packed) {
     }
 }
 
-// stage (c): 7x7 window of this lane's env (byte cache) -> its row of the warp tile
+// stage (c): 7x7 window of this lane's env (byte cache) -> its row of the warp tile.  The seven rows are
+// read at fixed word offsets from one base (rows outside the map land in the guards / the neighbouring
+// env and are masked), so no per-row clamping or address arithmetic is needed.
 template <typename ObsT>
 __device__ __forceinline__ void observe_cache(const uint8_t* gb, int pr, int pc, ObsT* row) {
     const uint32_t cv = (COLVALID >> (pc - 3)) & 0x7Fu;           // window column j lies inside the plan area
     const uint64_t one = spread7(cv);                              // 0x01 per valid byte
     const uint32_t b0 = (uint32_t)one, b1 = (uint32_t)(one >> 32);
     const uint32_t m0 = b0 * 0xFFu, m1 = b1 * 0xFFu;               // 0xFF per valid byte (no carries)
-    const int ob = pc - 6;                                         // byte offset of window column 0 inside a row
-    const uint32_t* gw = reinterpret_cast<const uint32_t*>(gb);
+    const int o0 = (pr - 6) * 20 + (pc - 6);                       // byte offset of window cell (0,0): -63 .. 336
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(gb + (o0 & ~3));
+    const int shb = (o0 & 3) * 8;                                  // the same for every row: 20 B = 5 words apart
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
-        const int ir = pr - 6 + k;                                 // interior row of window row k
-        const bool rowvalid = (unsigned)ir < 20u;
-        const int o = min(max(ir, 0), 19) * 20 + ob;               // -3 .. 396; over-reads stay inside the pads
-        const uint32_t* rw = gw + (o >> 2);
-        const int shb = (o & 3) * 8;
-        const uint32_t x0 = rw[0], x1 = rw[1], x2 = rw[2];
+        const bool rowvalid = (unsigned)(pr - 6 + k) < 20u;        // interior row of window row k
+        const uint32_t x0 = rw[5 * k], x1 = rw[5 * k + 1], x2 = rw[5 * k + 2];
         const uint32_t q0 = __funnelshift_r(x0, x1, shb), q1 = __funnelshift_r(x1, x2, shb);
         const uint32_t u0 = rowvalid ? ((q0 & m0) + b0) : 0u;
         const uint32_t u1 = rowvalid ? ((q1 & m1) + b1) : 0u;
@@ -117,9 +113,9 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
     const int64_t n = st.n_envs;
     const int64_t env0 = ((int64_t)blockIdx.x * wpb + warp) * 32;
     if (env0 >= n) return;                                            // whole warp leaves together
-    const int64_t env = env0 + lane;
-    const bool live = env < n;
     const int nvalid = (int)min((int64_t)32, n - env0);
+    const bool live = lane < nvalid;
+    const int64_t env = env0 + (live ? lane : 0);                     // idle lanes shadow env0 but never store
 
     uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw);
     uint8_t* wmap = base + (size_t)warp * WARP_MAP_B + FRONT;
@@ -128,16 +124,21 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
     uint8_t* gb = wmap + lane * MAP_B;                                // this lane's byte map
 
     uint16_t* cells = reinterpret_cast<uint16_t*>(st.cells);
-    uint16_t* ge = cells + (live ? env : env0) * CELLS3D;             // this lane's map in HBM
+    uint16_t* gwarp = cells + env0 * CELLS3D;                         // the warp's 32 maps in HBM (contiguous)
+    uint16_t* ge = cells + env * CELLS3D;                             // this lane's map in HBM
     uint4* aux = reinterpret_cast<uint4*>(st.aux);
     const uint8_t* __restrict__ plans = reinterpret_cast<const uint8_t*>(st.plans);
+    const bool autoreset = io.flags & DMP_F_AUTORESET;
 
     // ---- state in: coalesced 128-bit loads of the warp's contiguous maps, packed to bytes -------------
     if (lane == 0) *tallword = 0u;
     __syncwarp();
+    EnvR e{D2_LO, D2_LO, 0, 0, 0, 0.f, 0};
+    double acc_iou = 0.0;                                             // this env's sum of episode IoUs (sequential, exact)
     {
-        const uint4* src = reinterpret_cast<const uint4*>(cells + env0 * CELLS3D);
+        const uint4* src = reinterpret_cast<const uint4*>(gwarp);
         const int nvec = nvalid * (CELLS3D / 8);                      // 50 vectors of 8 cells per env
+        uint32_t tallbits = 0;
         constexpr int U = 10;
 #pragma unroll 1
         for (int i0 = 0; i0 < CELLS3D / 8; i0 += U) {
@@ -147,6 +148,14 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
                 const int idx = (i0 + u) * 32 + lane;
                 v[u] = (idx < nvec) ? src[idx] : make_uint4(0, 0, 0, 0);
             }
+            if (i0 == 0 && live) {                                    // scalar state rides along with the first batch
+                const uint4 a = aux[env];
+                e.pr = a.x & 0xFF; e.pc = (a.x >> 8) & 0xFF; e.plan_idx = a.x >> 16;
+                e.cb = a.y & 0xFFFF; e.cs = a.y >> 16;
+                e.ret = __uint_as_float(a.z);
+                e.cross = (int)a.w;
+                if (autoreset) acc_iou = st.ep_iou[env];
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int idx = (i0 + u) * 32 + lane;
@@ -154,37 +163,32 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
                 const uint32_t lo = __byte_perm(v[u].x, v[u].y, 0x6420u), hi = __byte_perm(v[u].z, v[u].w, 0x6420u);
                 const uint32_t any = v[u].x | v[u].y | v[u].z | v[u].w;
                 // conservative: true whenever one of the 8 heights is >= 254 (false positives only cost speed)
-                const bool tall = (any & 0xFF00FF00u) || ((any & 0xFEu) == 0xFEu) || ((any & 0xFE0000u) == 0xFE0000u);
+                const bool t8 = (any & 0xFF00FF00u) || ((any & 0xFEu) == 0xFEu) || ((any & 0xFE0000u) == 0xFE0000u);
+                tallbits |= t8 ? (1u << el) : 0u;
                 uint32_t* dst = reinterpret_cast<uint32_t*>(wmap + el * MAP_B + j * 8);
                 dst[0] = lo; dst[1] = hi;                             // lanes beyond nvec write zeros into their own slots
-                if (tall) atomicOr(tallword, 1u << el);
             }
         }
-    }
-    EnvR e{D2_LO, D2_LO, 0, 0, 0, 0.f, 0};
-    if (live) {
-        const uint4 a = aux[env];
-        e.pr = a.x & 0xFF; e.pc = (a.x >> 8) & 0xFF; e.plan_idx = a.x >> 16;
-        e.cb = a.y & 0xFFFF; e.cs = a.y >> 16;
-        e.ret = __uint_as_float(a.z);
-        e.cross = (int)a.w;
+        if (tallbits) atomicOr(tallword, tallbits);
     }
     int total_brick = __ldg(st.plan_total + e.plan_idx);
     int errbits = 0;
     const bool dynamic = st.dynamic != 0;
-    const bool autoreset = io.flags & DMP_F_AUTORESET;
     const bool normalise = io.flags & DMP_F_NORMALISE;
     const bool need_draw = (io.actions == nullptr) || (io.step_sizes == nullptr);
     const int tslot = (io.flags & DMP_F_TSLOT1) ? 1 : 0;
     const uint64_t t0 = st.t_dev ? st.t_dev[tslot] : st.t;
+    const uint64_t gid = (uint64_t)(st.env_base + env0) + (uint64_t)lane;
+    uint32_t acc_cnt = 0, acc_len = 0;                                // episodes finished by this env in this launch
+    float acc_ret = 0.f;                                              // (integer-valued: exact in any order)
     __syncwarp();
     bool tall = live && ((*tallword >> lane) & 1u);                   // this env runs from HBM
+    int64_t idx = env0 + lane;                                        // flat [k][env] index of this step's outputs
 
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < K; ++k, idx += n) {
         const uint64_t t = t0 + (uint64_t)k;
-        const int64_t idx = (int64_t)k * n + env;
         Draw d = Draw{0, 0, 0, 0};
-        if (need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
+        if (need_draw) d = env_draw(st.seed, gid, t);
         int a, s;
         if (io.actions) a = live ? (int)io.actions[idx] : 0; else a = draw_action(d, D3_ACT, st.action_dist);
         if (io.step_sizes) s = live ? (int)io.step_sizes[idx] : 1; else s = draw_step_size(d);
@@ -193,14 +197,22 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
 
         e.cs += 1;
         // ---- the six cells this step can depend on: the four neighbours (check_sur :88-102) and the second and
-        // third cell in the action's direction (move_step :104-134) -------------------------------------
+        // third cell in the action's direction (move_step :104-134).  Byte-cache reads are unconditional (the
+        // guards absorb them); whether a cell is frame follows from ONE coordinate, the other is the agent's.
         const int dir = a & 3, dr = dir_dr(dir), dc = dir_dc(dir);
+        const int o = (e.pr - 3) * 20 + (e.pc - 3);
         int c6[6];
         if (!tall) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) c6[q] = cell_c(gb, e.pr + dir_dr(q), e.pc + dir_dc(q));
-            c6[4] = cell_c(gb, e.pr + 2 * dr, e.pc + 2 * dc);
-            c6[5] = cell_c(gb, e.pr + 3 * dr, e.pc + 3 * dc);
+            const int dstep = dr * 20 + dc, sgn = dr + dc;
+            const int coord = (dir < 2 ? e.pc : e.pr) - 3;
+            const int vl = gb[o - 1], vr = gb[o + 1], vu = gb[o + 20], vd = gb[o - 20];
+            const int v2 = gb[o + 2 * dstep], v3 = gb[o + 3 * dstep];
+            c6[0] = (e.pc > D2_LO) ? vl : -1;
+            c6[1] = (e.pc < D2_HI) ? vr : -1;
+            c6[2] = (e.pr < D2_HI) ? vu : -1;
+            c6[3] = (e.pr > D2_LO) ? vd : -1;
+            c6[4] = ((unsigned)(coord + 2 * sgn) < 20u) ? v2 : -1;
+            c6[5] = ((unsigned)(coord + 3 * sgn) < 20u) ? v3 : -1;
         } else {
 #pragma unroll
             for (int q = 0; q < 4; ++q) c6[q] = cell_tall(ge, e.pr + dir_dr(q), e.pc + dir_dc(q));
@@ -210,8 +222,9 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
         const bool boxed = (c6[0] != 0) && (c6[1] != 0) && (c6[2] != 0) && (c6[3] != 0);     // check_sur
         const int nsel = (dir == 0) ? c6[0] : (dir == 1) ? c6[1] : (dir == 2) ? c6[2] : c6[3];
 
-        float reward = 0.f;
         bool done = false, tail = true;
+        bool built = false, boxed_penalty = false;
+        int newh = 0, pplan = 0;
         if (a <= 3) {
             // (a) move_step (:104-134): consecutive empty cells, at most s
             int nstep = 0;
@@ -220,16 +233,13 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
             e.pc = min(max(e.pc + dc * nstep, D2_LO), D2_HI);
         } else {
             // (b) build on neighbour a-4 unless it is frame
-            bool built = false;
-            int newh = 0, pplan = 0;
             bool open_after = (c6[0] == 0) || (c6[1] == 0) || (c6[2] == 0) || (c6[3] == 0);   // some neighbour still empty
             if (a <= 7 && nsel != -1) {
                 built = true;
                 newh = nsel + 1;
-                const int ti = (e.pr + dr - 3) * 20 + (e.pc + dc - 3);
+                const int ti = o + dr * 20 + dc;
                 e.cb += 1;
-                pplan = plans[e.plan_idx * CELLS3D + ti];
-                if (newh <= pplan) e.cross += 1;
+                pplan = plans[e.plan_idx * CELLS3D + ti];                      // consumed after the observation
                 if (!tall) gb[ti] = (uint8_t)newh;
                 if (live) {
                     ge[ti] = (uint16_t)newh;                                   // write-through
@@ -240,17 +250,15 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
                              ((dir != 2) && c6[2] == 0) || ((dir != 3) && c6[3] == 0);
             }
             if (dynamic) {                                   // re-check after placement (:199-231)
-                if (!open_after) { reward = -100.f; done = true; tail = false; }
+                if (!open_after) { boxed_penalty = true; done = true; tail = false; }
                 else if (e.cb >= total_brick) { done = true; tail = false; }
                 else if (built) { tail = false; }
             } else {                                         // static (:210-230)
                 if (e.cb >= total_brick || boxed) { done = true; tail = false; }
                 else if (built) { tail = false; }
             }
-            if (!tail && !done) reward = (newh > pplan) ? -1.f : (newh == pplan ? 10.f : 1.f);
         }
         if (tail) done = (e.cs >= st.total_step) || (!dynamic && boxed);
-        e.ret += reward;
 
         // ---- (c) observation --------------------------------------------------------------------
         if (io.obs) {
@@ -264,25 +272,33 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
             else warp_tile_store<ObsT>(dst, tile, nvalid * D3_OBS, lane);
             __syncwarp();
         }
+
+        // ---- (d) reward (reward_check :232-239); the plan byte requested above has arrived by now -------
+        float reward = 0.f;
+        if (built) {
+            if (newh <= pplan) e.cross += 1;
+            if (!tail && !done) reward = (newh > pplan) ? -1.f : (newh == pplan ? 10.f : 1.f);
+        }
+        if (boxed_penalty) reward = -100.f;
+        e.ret += reward;
         if (live) {
             if (io.reward) io.reward[idx] = reward;
             if (io.done) io.done[idx] = done ? 1 : 0;
         }
 
-        // ---- (d)/(e) finished episodes ---------------------------------------------------------------
+        // ---- (e) finished episodes --------------------------------------------------------------------
         // IoU = cross / (total_brick + count_brick - cross) (:257-276); `cross` is kept up to date by every build.
+        // Episode statistics accumulate in registers and are folded into HBM once, after the last step.
         const bool fin = done && autoreset && live;
         if (fin) {
-            const double iou = __ddiv_rn((double)e.cross, (double)(total_brick + e.cb - e.cross));
-            atomicAdd(st.ep_cnt + env, 1u);                 // fire-and-forget REDs: no read-modify-write stall
-            atomicAdd(st.ep_len + env, (uint32_t)e.cs);
-            atomicAdd(st.ep_ret + env, (double)e.ret);
-            atomicAdd(st.ep_iou + env, iou);
+            const int den = total_brick + e.cb - e.cross;
+            const double iou = (e.cross == 0 && den != 0) ? 0.0 : __ddiv_rn((double)e.cross, (double)den);
+            acc_cnt += 1u; acc_len += (uint32_t)e.cs; acc_ret += e.ret; acc_iou += iou;
             if (io.next_plan) {
                 const int p = io.next_plan[idx];
                 if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
             } else if (st.plan_mode == DMP_PLAN_PHILOX) {
-                if (!need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
+                if (!need_draw) d = env_draw(st.seed, gid, t);
                 e.plan_idx = draw_plan(d.x2, st.n_plans);
             } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
                 e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
@@ -295,13 +311,13 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
         while (dm) {                                        // the warp clears each finished env's map
             const int src = __ffs(dm) - 1;
             dm &= dm - 1;
-            uint32_t* sg = reinterpret_cast<uint32_t*>(wmap + src * MAP_B);
-            sg[lane] = 0u; sg[lane + 32] = 0u; sg[lane + 64] = 0u;
-            if (lane < 4) sg[lane + 96] = 0u;
+            uint32_t* sg = reinterpret_cast<uint32_t*>(wmap + src * MAP_B) + lane;
+            sg[0] = 0u; sg[32] = 0u; sg[64] = 0u;
+            if (lane < 4) sg[96] = 0u;
             if (lane < 25) {
-                uint4* gg = reinterpret_cast<uint4*>(cells + (env0 + src) * CELLS3D);
+                uint4* gg = reinterpret_cast<uint4*>(gwarp + src * CELLS3D) + 2 * lane;
                 const uint4 z = make_uint4(0, 0, 0, 0);
-                gg[2 * lane] = z; gg[2 * lane + 1] = z;
+                gg[0] = z; gg[1] = z;
             }
         }
         __syncwarp();
@@ -309,6 +325,12 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
     if (live) {
         aux[env] = make_uint4((uint32_t)e.pr | ((uint32_t)e.pc << 8) | ((uint32_t)e.plan_idx << 16),
                               (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16), __float_as_uint(e.ret), (uint32_t)e.cross);
+        if (acc_cnt) {                                      // this thread is the only writer of its env's statistics
+            atomicAdd(st.ep_cnt + env, acc_cnt);            // fire-and-forget REDs
+            atomicAdd(st.ep_len + env, acc_len);
+            atomicAdd(st.ep_ret + env, (double)acc_ret);
+            st.ep_iou[env] = acc_iou;
+        }
         if (errbits) atomicOr(st.err, errbits);
         if (st.t_dev && env == 0) st.t_dev[tslot ^ 1] = t0 + (uint64_t)K;
     }
