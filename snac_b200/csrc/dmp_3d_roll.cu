@@ -58,6 +58,14 @@ __device__ __noinline__ void observe_tall(const uint16_t* ge, int pr, int pc, Ob
         for (int j = 0; j < 7; ++j) row[k * 7 + j] = obs_from_int<ObsT>(cell_g(ge, pr - 3 + k, pc - 3 + j));
 }
 
+// plan byte as a bare 32-bit load result: nothing touches the register until the reward is computed, so the
+// load's latency hides behind the observation stage
+__device__ __forceinline__ int ldg_u8(const uint8_t* p) {
+    int v;
+    asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ uint64_t spread7(uint32_t x) {       // bit j -> byte j (see dmp_2d.cu)
     return ((uint64_t)x * 0x0002040810204081ull) & 0x0101010101010101ull;
 }
@@ -139,7 +147,7 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
         const uint4* src = reinterpret_cast<const uint4*>(gwarp);
         const int nvec = nvalid * (CELLS3D / 8);                      // 50 vectors of 8 cells per env
         uint32_t tallbits = 0;
-        constexpr int U = 10;
+        constexpr int U = 25;                                         // 25 x 16 B in flight per lane: two DRAM round trips per launch
 #pragma unroll 1
         for (int i0 = 0; i0 < CELLS3D / 8; i0 += U) {
             uint4 v[U];
@@ -239,7 +247,7 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
                 newh = nsel + 1;
                 const int ti = o + dr * 20 + dc;
                 e.cb += 1;
-                pplan = plans[e.plan_idx * CELLS3D + ti];                      // consumed after the observation
+                pplan = ldg_u8(plans + e.plan_idx * CELLS3D + ti);             // consumed after the observation
                 if (!tall) gb[ti] = (uint8_t)newh;
                 if (live) {
                     ge[ti] = (uint16_t)newh;                                   // write-through
