@@ -150,6 +150,7 @@ int dmp2d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);
 int dmp3d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);
 int dmp3d_tile_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);
 int dmp3d_cache_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);
+int dmp3d_step_rows(const DmpState& st, const DmpIO& io, cudaStream_t s);
 int dmp1d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs, int obs_kind, cudaStream_t s);
 int dmp2d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs, int obs_kind, cudaStream_t s);
 int dmp3d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs, int obs_kind, cudaStream_t s);

@@ -311,7 +311,7 @@ def test_3d_kernels_agree(dynamic, K):
     plans = load_plans(3, "dense", "train") if dynamic else None
     n = 333                                                   # ragged last warp
     outs = {}
-    for kind in "wtc":
+    for kind in "wtcs":                                      # "s": the default dispatch (window-rows kernel for K = 1)
         env = make_gpu(3, dynamic, n, 0, plans, auto_reset=True, env_base=99, seed=SEED, normalise=dynamic,
                        obs_dtype=torch.float64 if dynamic else torch.float32)
         env.reset()
@@ -324,7 +324,7 @@ def test_3d_kernels_agree(dynamic, K):
         st = env.get_state()
         outs[kind] = (res, st["cells"].clone(), st["aux"].clone(), [x.clone() for x in env.episode_stats()])
         env.check_errors()
-    for kind in "tc":
+    for kind in "tcs":
         for a, b in zip(outs["w"][0], outs[kind][0]):
             for x, y in zip(a, b):
                 assert torch.equal(x, y), kind
@@ -333,7 +333,7 @@ def test_3d_kernels_agree(dynamic, K):
             assert torch.equal(x, y), kind
 
 
-@pytest.mark.parametrize("kind", ["c", "t"])
+@pytest.mark.parametrize("kind", ["c", "t", "s1"])
 @pytest.mark.parametrize("dynamic", [False, True])
 def test_3d_tall_columns_match_oracle(kind, dynamic):
     """Heights around and far beyond the byte range (252..256, 300, 40000) next to the agent: builds on top of
@@ -363,10 +363,15 @@ def test_3d_tall_columns_match_oracle(kind, dynamic):
     r_obs, r_rew, r_done, _, _ = philox_rollout(ob, K, SEED, 0, 0, 8, auto_reset=False, actions=acts, step_sizes=sizes)
 
     def run():
-        out = env.rollout(K, actions=torch.as_tensor(acts, device=env.device), step_sizes=torch.as_tensor(sizes, device=env.device))
+        ta, ts = torch.as_tensor(acts, device=env.device), torch.as_tensor(sizes, device=env.device)
+        if kind == "s1":                                      # step by step through the default single-step kernel
+            outs = [[x.clone() for x in env.step(ta[k], ts[k])] for k in range(K)]
+            out = [torch.stack([o[i] for o in outs]) for i in range(3)]
+        else:
+            out = env.rollout(K, actions=ta, step_sizes=ts)
         torch.cuda.synchronize()
         return out
-    obs, rew, done = _with_kernel(kind, run)
+    obs, rew, done = _with_kernel(kind[0], run)
     assert np.array_equal(obs.cpu().numpy().astype(np.float64), r_obs)
     assert np.array_equal(rew.cpu().numpy(), r_rew)
     assert np.array_equal(done.cpu().numpy(), r_done)
