@@ -355,6 +355,31 @@ def run_ours(args):
            "h2d_bytes_per_step": int(hs.h2d_bytes) * world, "d2h_bytes_per_step": int(hs.d2h_bytes) * world,
            "api": "HostStepper.step(actions: np.uint8[N]) -> (obs f32[N,%d], reward f32[N], done bool[N]) numpy, pinned" % D}
 
+    # the same call with int16 observations (every raw observation value is a small integer, so i16 is exact;
+    # SURVEY.md 8(d) lists it as the compact obs_t): half the D2H bytes of the PCIe-bound f32 call
+    e2e_i16 = None
+    if not dynamic and not args.no_e2e_i16:
+        env16 = BatchedDMPEnv(dim, dynamic=dynamic, plan_choose=plan_choose, plans=None, num_envs=n, device=dev,
+                              auto_reset=True, env_base=env_base, obs_dtype=torch.int16)
+        env16.reset()
+        hs16 = HostStepper(env16)
+        for i in range(3):
+            hs16.step(host_actions[i % 4])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            hs16.step(host_actions[i % 4])
+        torch.cuda.synchronize()
+        t16 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t16, op=dist.ReduceOp.MAX)
+        e2e_i16 = {"value": total_envs * Ke / float(t16.item()), "unit": "env-steps/s", "steps": Ke,
+                   "h2d_bytes_per_step": int(hs16.h2d_bytes) * world, "d2h_bytes_per_step": int(hs16.d2h_bytes) * world,
+                   "api": "HostStepper.step on an env built with obs_dtype=int16"}
+        del hs16, env16
+
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s|%d|K=%d" % (wl, n, KL))
@@ -370,7 +395,7 @@ def run_ours(args):
                        "l2": ring,
                        "parallelism": "env-sharded x%d, NCCL all-reduce of episode stats only" % world},
             "clocks": clocks,
-            "e2e": e2e, "gpu_launches": launches,
+            "e2e": e2e, "e2e_i16": e2e_i16, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_note": "bytes per launch from the committed ncu capture (profiles/), not measured live; algorithmic bytes per launch = %d" % int(b_alg * n * KL),
                          "peak_source": peak_src, "kernel": "k%dd%s_rollout<float> (K=%d)" % (dim, ("_cache" if KL > 1 else "_tile") if dim == 3 else "", KL),
@@ -408,6 +433,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="total envs over all GPUs (default: the BASELINE config's)")
     ap.add_argument("--e2e-steps", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e-i16", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -251,3 +251,64 @@ void orc_reset_all(const OrcCfg* c, OrcEnv* envs, int64_t n, const int32_t* plan
 void orc_iou_all(const OrcCfg* c, const OrcEnv* envs, int64_t n, double* out) {
     for (int64_t i = 0; i < n; ++i) out[i] = orc_iou(&envs[i], c);
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Random triangle plans (oracle/plangen.py is the commented statement; this is its fast twin used for the
+ * exhaustive comparison with cv2 and for large GPU parity cases).
+ * create_plan: Env/2D/DMP_Env_2D_dynamic_hindsight_replay_usedata.py:37-59.
+ * rows[r] bit c = 1 where the reference image is black (row = y, column = x). */
+static void orc_line_rows(int x1, int y1, int x2, int y2, uint32_t* rows) {
+    int dx = x2 - x1, dy = y2 - y1, t;
+    if (dx < 0) { t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; dx = -dx; dy = -dy; }
+    int ystep = 1;
+    if (dy < 0) { dy = -dy; ystep = -1; }
+    int x = x1, y = y1;
+    if (dy > dx) {
+        int err = dy - 2 * dx;
+        for (int i = 0; i <= dy; ++i) {
+            rows[y] |= 1u << x;
+            const int neg = err < 0;
+            err += -2 * dx + (neg ? 2 * dy : 0);
+            y += ystep;
+            x += neg;
+        }
+    } else {
+        int err = dx - 2 * dy;
+        for (int i = 0; i <= dx; ++i) {
+            rows[y] |= 1u << x;
+            const int neg = err < 0;
+            err += -2 * dy + (neg ? 2 * dx : 0);
+            x += 1;
+            if (neg) y += ystep;
+        }
+    }
+}
+
+/* out: 13 words, bit r*20+c (the 2D grid's bit order); returns the area */
+int orc_triangle_mask(const int32_t* xs, const int32_t* ys, int dense, uint32_t* out13) {
+    uint32_t rows[20];
+    for (int r = 0; r < 20; ++r) rows[r] = 0;
+    for (int i = 0; i < 3; ++i) orc_line_rows(xs[i], ys[i], xs[(i + 1) % 3], ys[(i + 1) % 3], rows);
+    int area = 0;
+    for (int w = 0; w < 13; ++w) out13[w] = 0;
+    for (int r = 0; r < 20; ++r) {
+        uint32_t m = rows[r];
+        if (dense && m) {
+            const int lo = __builtin_ctz(m), hi = 31 - __builtin_clz(m);
+            m = (uint32_t)((2ull << hi) - (1ull << lo));
+        }
+        area += __builtin_popcount(m);
+        const int b = r * 20;
+        out13[b >> 5] |= m << (b & 31);
+        if ((b & 31) > 12) out13[(b >> 5) + 1] |= m >> (32 - (b & 31));
+    }
+    return area;
+}
+
+void orc_triangle_masks(int64_t n, const int32_t* xs, const int32_t* ys, int dense, uint32_t* out, int32_t* area) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        const int a = orc_triangle_mask(xs + 3 * i, ys + 3 * i, dense, out + 13 * i);
+        if (area) area[i] = a;
+    }
+}

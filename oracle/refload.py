@@ -85,6 +85,9 @@ _MODULES = {
     ("1D", "lnet"): ("1D", "DMP_Env_1D_static_Lnet", "deep_mobile_printing_1d1r"),
     ("2D", "lnet"): ("2D", "DMP_Env_2D_static_Lnet", "deep_mobile_printing_2d1r"),
     ("3D", "lnet"): ("3D", "DMP_simulator_3d_static_circle_Lnet", "deep_mobile_printing_3d1r"),
+    # classes that carry the random plan generators
+    ("1D", "hindsight_dynamic"): ("1D", "DMP_Env_1D_dynamic_hindsight_replay", "deep_mobile_printing_1d1r_hindsight"),
+    ("2D", "hindsight_dynamic"): ("2D", "DMP_Env_2D_dynamic_hindsight_replay_usedata", "deep_mobile_printing_2d1r_hindsight"),
 }
 
 

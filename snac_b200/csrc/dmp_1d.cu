@@ -12,7 +12,8 @@
 
 namespace {
 
-constexpr int B1 = 128;
+// B1 = threads (= envs) per block is a template parameter: 128 for large batches, 32 when the batch is too small
+// to give every SM several blocks (BASELINE config 2: 65 536 envs = 2 048 warps for 592 schedulers)
 constexpr int S1_WORDS = 17;          // padded 34 halfwords: word 0 and 16 are the -1 walls
 
 struct Env1 {
@@ -27,6 +28,7 @@ __device__ __forceinline__ void stage_move1(Env1& e, int a, int s) {
 }
 
 // stage (b): environment_memory[0, position] += 1 (:104); returns the new height
+template <int B1>
 __device__ __forceinline__ int stage_deposit1(uint32_t* g, const Env1& e) {
     const int w = e.pos >> 1, sh = (e.pos & 1) * 16;
     const uint32_t x = g[w * B1];
@@ -36,7 +38,7 @@ __device__ __forceinline__ int stage_deposit1(uint32_t* g, const Env1& e) {
 }
 
 // stage (c): window [pos-2, pos+2] + counters (:131-133)
-template <typename ObsT>
+template <typename ObsT, int B1>
 __device__ __forceinline__ void stage_observe1(const uint32_t* g, const Env1& e, ObsT* row, bool normalise,
                                                int total_brick, int total_step) {
     const int p0 = e.pos - D1_HW;
@@ -65,7 +67,7 @@ __device__ __forceinline__ double iou1_words(const uint32_t (&hw)[15], const uin
     return __ddiv_rn((double)cross, (double)(a1 + a2 - cross));
 }
 
-template <typename ObsT>
+template <typename ObsT, int B1>
 __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO io, const int K) {
     extern __shared__ uint4 smem_raw[];
     uint32_t* G = reinterpret_cast<uint32_t*>(smem_raw);                 // [S1_WORDS][B1]
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
             done = e.cs >= st.total_step;
         } else if (a == 2) {                                // (b) drop + (d) reward
             e.cb += 1;
-            const int h = stage_deposit1(g, e);
+            const int h = stage_deposit1<B1>(g, e);
             dirty |= 1u << ((e.pos - D1_HW) >> 3);          // 8 heights per 128-bit plane
             if (e.cb >= total_brick) {                      // :107-114
                 done = true;
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
         e.ret += reward;
 
         if (io.obs) {
-            stage_observe1<ObsT>(g, e, tile + lane * D1_OBS, normalise, total_brick, st.total_step);
+            stage_observe1<ObsT, B1>(g, e, tile + lane * D1_OBS, normalise, total_brick, st.total_step);
             __syncwarp();
             {
                 ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * D1_OBS;
@@ -282,12 +284,19 @@ __global__ void k1d_import(const DmpState st, const int32_t* __restrict__ grid, 
     aux[env] = ax;
 }
 
-template <typename ObsT>
-int launch_rollout1(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+template <typename ObsT, int B1>
+int launch_rollout1_b(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
     const size_t smem = (size_t)S1_WORDS * B1 * 4 + (size_t)(B1 / 32) * 32 * D1_OBS * sizeof(ObsT);
     const unsigned blocks = (unsigned)((st.n_envs + B1 - 1) / B1);
-    k1d_rollout<ObsT><<<blocks, B1, smem, s>>>(st, io, K);
+    k1d_rollout<ObsT, B1><<<blocks, B1, smem, s>>>(st, io, K);
     return dmp_set_error(cudaGetLastError());
+}
+
+template <typename ObsT>
+int launch_rollout1(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    // fewer than ~4 blocks of 128 per SM: single-warp blocks spread the warps evenly over the 148 SMs
+    if (st.n_envs < (int64_t)128 * 148 * 4) return launch_rollout1_b<ObsT, 32>(st, io, K, s);
+    return launch_rollout1_b<ObsT, 128>(st, io, K, s);
 }
 
 }  // namespace
