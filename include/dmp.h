@@ -144,6 +144,31 @@ int dmp_layout(int dim, int64_t n_envs, DmpLayout* out);
 int dmp_plan_static(int dim, int plan_choose, void* plans_row_out, int32_t* plan_total_out, void* stream);
 int dmp_plans_pack(int dim, const double* raw, int n_plans, void* plans_out, int32_t* plan_total_out, void* stream);
 
+/* ---- on-device random plan generators and hindsight relabelling (init path) --------------------------------
+ * dmp_plans_generate replaces create_plan() of the reference's generator classes:
+ *   dim 1: random sinusoid, Env/1D/DMP_Env_1D_dynamic_hindsight_replay.py:29-42
+ *          (k_1 = uniform(3,12), k_2 = randint(1,4), phase = uniform(-1,1)*pi; y = round(k_1 sin(2pi/30 (k_2 x + phase)) + 20))
+ *   dim 2: random triangle (plan_choose 0 dense: cv2.polylines + cv2.fillPoly, 1 sparse: outline only), redrawn until
+ *          area > 50 / 20, Env/2D/DMP_Env_2D_dynamic_hindsight_replay_usedata.py:37-59 (= DMP_ENV_2D_dynamic_MCTS.py:40-62);
+ *          budget = max(area, 30) (:70-71)
+ *   dim 3: the same masks times z = 6, budget = area * 6 (Env/3D/DMP_simulator_3d_dynamic_triangle_usedata.py:47-49)
+ * Writes n_plans plan-table rows + budgets, plan ids first_id .. first_id + n_plans - 1.
+ *   draws : nullable injected draws of the reference's numpy stream.  dim 1: f64 [n_plans][3] = k_1, k_2, phase;
+ *           dim 2/3: i32 [n_plans][max_attempts][6] = x0,x1,x2,y0,y1,y2 of every attempt in draw order.
+ *           NULL -> Philox4x32-10, counter (plan id lo, plan id hi, attempt, "PLAN"), key = seed
+ *           (stream definition: oracle/plangen.py).
+ *   aux_out : nullable.  dim 1: f64 [n_plans][3] the parameters used (the reference's `one_hot`);
+ *           dim 2/3: i32 [n_plans] attempts used.
+ *   err   : device int32 (dim 2/3, required): DMP_ERR_PLANIDX is latched if a vertex is outside 0..19 or
+ *           max_attempts draws were all rejected.
+ * dmp_plans_from_state: plan row i := the structure env i has built so far, budget (nullable) := its brick count /
+ *   height sum -- hindsight relabelling, `env_hindsight.plan = env.environment_memory[...]`
+ *   (script/DRQN_hindsight/1d/DRQN_hindsight_1D_static.py:242-245).  plans_out has n_envs rows. */
+int dmp_plans_generate(int dim, int plan_choose, uint64_t seed, int64_t first_id, int n_plans, const void* draws,
+                       int max_attempts, void* plans_out, int32_t* plan_total_out, void* aux_out, int32_t* err,
+                       void* stream);
+int dmp_plans_from_state(const DmpState* st, void* plans_out, int32_t* plan_total_out, void* stream);
+
 /* ---- reset ---------------------------------------------------------------------------------------
  * replaces reset(): Env/1D/DMP_Env_1D_static.py:66-83, Env/1D/DMP_Env_1D_dynamic_usedata_plan.py:40-70,
  * Env/2D/DMP_Env_2D_static.py:54-76, Env/2D/DMP_Env_2D_dynamic_usedata_plan.py:34-66,

@@ -53,6 +53,8 @@ _SIGNATURES = {
     "dmp_layout": (C.c_int, [C.c_int, C.c_int64, C.POINTER(DmpLayout)]),
     "dmp_plan_static": (C.c_int, [C.c_int, C.c_int, _P, _P, _P]),
     "dmp_plans_pack": (C.c_int, [C.c_int, _P, C.c_int, _P, _P, _P]),
+    "dmp_plans_generate": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int, _P, C.c_int, _P, _P, _P, _P, _P]),
+    "dmp_plans_from_state": (C.c_int, [C.POINTER(DmpState), _P, _P, _P]),
     "dmp_reset": (C.c_int, [C.POINTER(DmpState), _P, _P, C.c_uint64, _P, C.c_int, _P]),
     "dmp_step": (C.c_int, [C.POINTER(DmpState), C.POINTER(DmpIO), _P]),
     "dmp_rollout": (C.c_int, [C.POINTER(DmpState), C.POINTER(DmpIO), C.c_int, _P]),

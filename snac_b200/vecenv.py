@@ -50,12 +50,64 @@ def load_plan_dataset(data_path: str, dim: int, key: Optional[str] = None) -> np
     return np.asarray(joblib.load(data_path), dtype=np.float64)
 
 
+def generate_plans(dim: int, n_plans: int, plan_choose: int = 0, *, seed: int = L.SEED_DEFAULT, first_id: int = 0,
+                   draws=None, max_attempts: int = 256, device="cuda"):
+    """On-device random plan generator (``dmp_plans_generate``): the reference's ``create_plan`` of the generator
+    classes -- 1D random sinusoid (Env/1D/DMP_Env_1D_dynamic_hindsight_replay.py:29-42), 2D/3D random dense / sparse
+    triangles (Env/2D/DMP_Env_2D_dynamic_hindsight_replay_usedata.py:37-59) -- for plan ids
+    ``first_id .. first_id + n_plans - 1``.
+
+    draws  None: counter-based Philox stream keyed by (seed, plan id); otherwise the reference's numpy draws:
+           1D float64 [n,3] = (k_1, k_2, phase); 2D/3D int32 [n,A,6] = (x0,x1,x2,y0,y1,y2) of each of A attempts.
+    Returns (table uint8 [n, row_bytes], totals int32 [n], aux) with aux = the 1D parameters used (float64 [n,3],
+    the reference's ``one_hot``) or the number of attempts per plan (int32 [n]).  Raises ValueError for a bad
+    plan_choose (like the reference) or if an injected vertex is outside the 20x20 grid / every attempt was rejected."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("snac_b200 has no CPU path; device must be a CUDA device")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    if dim != 1 and plan_choose not in (0, 1):
+        raise ValueError(' 0: Dense triangle, 1: Sparse triangle')
+    lay = L.DmpLayout()
+    L.check(L.lib.dmp_layout(dim, 1, C.byref(lay)), "dmp_layout")
+    n = int(n_plans)
+    with torch.cuda.device(dev):
+        table = torch.zeros((n, lay.plan_row_bytes), dtype=torch.uint8, device=dev)
+        totals = torch.zeros(n, dtype=torch.int32, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        d = None
+        if dim == 1:
+            aux = torch.zeros((n, 3), dtype=torch.float64, device=dev)
+            if draws is not None:
+                d = torch.as_tensor(np.ascontiguousarray(draws, dtype=np.float64), device=dev).reshape(n, 3).contiguous()
+        else:
+            aux = torch.zeros(n, dtype=torch.int32, device=dev)
+            if draws is not None:
+                d = torch.as_tensor(np.ascontiguousarray(draws, dtype=np.int32), device=dev)
+                if d.dim() == 2:
+                    d = d[:, None, :]
+                if d.dim() != 3 or d.shape[0] != n or d.shape[2] != 6:
+                    raise ValueError("draws must have shape [n_plans, attempts, 6]")
+                d = d.contiguous()
+                max_attempts = int(d.shape[1])
+        L.check(L.lib.dmp_plans_generate(dim, int(plan_choose), C.c_uint64(int(seed)), int(first_id), n, _ptr(d),
+                                         int(max_attempts), table.data_ptr(), totals.data_ptr(), aux.data_ptr(),
+                                         err.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "dmp_plans_generate")
+        if int(err.item()):
+            raise ValueError("plan generation failed: a vertex outside 0..19 or no accepted triangle in %d attempts" % max_attempts)
+    return table, totals, aux
+
+
 class BatchedDMPEnv:
     """N independent DMP environments on one GPU.
 
     dim               1, 2 or 3
     plan_choose       static plan selector (1D: 0 sine / 1 Gaussian / 2 step; 2D, 3D: 0 dense / 1 sparse)
-    plans             dynamic envs: float64 array of plans in the reference's format ([n,30] or [n,26,26])
+    plans             dynamic envs: float64 array of plans in the reference's format ([n,30] or [n,26,26]), or the
+                      string "generate": n_plans random plans from the on-device generators (generate_plans();
+                      plan_choose selects dense / sparse triangles), or a (table, totals) pair of device tensors
+    n_plans           size of the generated plan table (plans="generate" only; at most 65 535)
     random_choose_paln  (sic, reference spelling) True: random plan per reset; False: sequential with wrap
     auto_reset        fold finished episodes into the per-env statistics and reset them inside step()
     obs_dtype         torch.float32 (default), torch.float64 (the reference's dtype) or torch.int16
@@ -71,7 +123,8 @@ class BatchedDMPEnv:
                  random_choose_paln: bool = True, auto_reset: bool = False,
                  obs_dtype: torch.dtype = torch.float32, normalise: bool = False,
                  seed: int = L.SEED_DEFAULT, env_base: int = 0, action_dist: str = "uniform",
-                 total_step: Optional[int] = None, dynamic_rules: Optional[bool] = None):
+                 total_step: Optional[int] = None, dynamic_rules: Optional[bool] = None, n_plans: int = 4096,
+                 plan_id_base: int = 0):
         if dim not in (1, 2, 3):
             raise ValueError("dim must be 1, 2 or 3")
         if obs_dtype not in _TORCH_OBS:
@@ -112,7 +165,17 @@ class BatchedDMPEnv:
             self._stats = torch.zeros(4, dtype=torch.float64, device=dev)
             self._stats_scratch = torch.zeros(int(L.lib.dmp_stats_scratch_bytes(n)), **u8)
             # ---- plan table -----------------------------------------------------------------
-            if self.dynamic:
+            if self.dynamic and (isinstance(plans, str) or isinstance(plans, tuple)):
+                if isinstance(plans, str):
+                    if plans != "generate":
+                        raise ValueError('plans must be an array, a (table, totals) pair or "generate"')
+                    table, totals, self.plan_aux = generate_plans(dim, n_plans, plan_choose, seed=seed,
+                                                                  first_id=plan_id_base, device=dev)
+                else:
+                    table, totals = plans
+                self._plans_raw = None
+                self._install_plans(table, totals)
+            elif self.dynamic:
                 if plans is None:
                     raise ValueError("dynamic envs need plans= (see load_plan_dataset)")
                 raw = torch.as_tensor(np.ascontiguousarray(plans, dtype=np.float64), device=dev)
@@ -387,6 +450,43 @@ class BatchedDMPEnv:
         self.set_state(state)
         obs, rew, done = self.step(actions, step_sizes)
         return self.get_state(), obs.clone(), rew.clone(), done.clone()
+
+    # plan sources --------------------------------------------------------------------------------
+    def _install_plans(self, table: torch.Tensor, totals: torch.Tensor) -> None:
+        table = table.to(self.device).contiguous().view(torch.uint8).reshape(-1, self._lay.plan_row_bytes)
+        totals = totals.to(device=self.device, dtype=torch.int32).contiguous()
+        if table.shape[0] != totals.shape[0] or not 1 <= table.shape[0] <= 65535:
+            raise ValueError("plan table needs 1..65535 rows and one budget per row")
+        self.n_plans = int(table.shape[0])
+        self._plans, self._plan_total = table.reshape(-1), totals
+        if hasattr(self, "_st"):
+            self._st.n_plans = self.n_plans
+            self._st.plans, self._st.plan_total = self._plans.data_ptr(), self._plan_total.data_ptr()
+
+    def set_plan_table(self, table: torch.Tensor, totals: torch.Tensor) -> None:
+        """Swap the plan table (packed rows as produced by generate_plans() / hindsight_plans() / plan_table()).
+        Envs keep their plan index; call reset() (or pass plan_idx) afterwards."""
+        if not self.dynamic:
+            raise RuntimeError("static envs have a fixed plan; build the env with dynamic=True")
+        self._install_plans(table, totals)
+
+    def regenerate_plans(self, first_id: int, n_plans: Optional[int] = None, draws=None) -> None:
+        """Fresh random plans for ids first_id.. (removes the reference's 500-plan dataset limit)."""
+        table, totals, self.plan_aux = generate_plans(self.dim, n_plans or self.n_plans, self.plan_choose,
+                                                      seed=int(self._st.seed), first_id=first_id, draws=draws,
+                                                      device=self.device)
+        self.set_plan_table(table, totals)
+
+    def hindsight_plans(self):
+        """Hindsight relabelling: (table [N,row_bytes], totals [N]) where row i is what env i has built so far --
+        ``env_hindsight.plan = env.environment_memory[...]`` of script/DRQN_hindsight/1d/DRQN_hindsight_1D_static.py:242-245.
+        Feed it to a second env with set_plan_table() and reset(plan_idx=arange(N)) to replay the episode against it."""
+        table = torch.empty((self.num_envs, self._lay.plan_row_bytes), dtype=torch.uint8, device=self.device)
+        totals = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(L.lib.dmp_plans_from_state(C.byref(self._st), table.data_ptr(), totals.data_ptr(), self._stream()),
+                    "dmp_plans_from_state")
+        return table, totals
 
     # plan views ----------------------------------------------------------------------------------
     def plan_table(self) -> torch.Tensor:

@@ -82,6 +82,7 @@ def _check_chunk(args):
 
 
 _G = {}
+MAX_ATT = 96                     # attempts kept per reference create_plan call (P(area > 50) is about 0.2 per draw)
 
 
 def exhaustive(dense, procs):
@@ -169,8 +170,8 @@ def main():
             plan2, area2, att = G.create_plan_2d(draw, pc)
             assert np.array_equal(plan, plan2) and float(area) == area2, (pc, seed)
             plans.append(plan[3:23, 3:23].astype(np.uint8)); areas.append(area)
-            v = np.zeros((16, 6), np.int32)
-            assert att <= 16
+            v = np.zeros((MAX_ATT, 6), np.int32)
+            assert att <= MAX_ATT
             v[:att] = np.stack(log)
             verts.append(v); nverts.append(att)
         out2[dens] = (np.stack(plans), np.asarray(areas), np.stack(verts), np.asarray(nverts))
