@@ -333,6 +333,8 @@ def run_ours(args):
 
     # ---- e2e: the reference-facing call with HOST buffers (actions in, obs/reward/done out) -------
     from snac_b200.compat import HostStepper
+    if args.no_e2e:                                          # kernel A/B runs only; the default run always measures e2e
+        args.e2e_steps, args.no_e2e_i16 = 4, True
     hs = HostStepper(env)
     Ke = max(4, min(K_eff, args.e2e_steps))
     rng = np.random.RandomState(99 + rank)
@@ -398,7 +400,8 @@ def run_ours(args):
             "e2e": e2e, "e2e_i16": e2e_i16, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_note": "bytes per launch from the committed ncu capture (profiles/), not measured live; algorithmic bytes per launch = %d" % int(b_alg * n * KL),
-                         "peak_source": peak_src, "kernel": "k%dd%s_rollout<float> (K=%d)" % (dim, ("_cache" if KL > 1 else "_tile") if dim == 3 else "", KL),
+                         "peak_source": peak_src, "kernel": ("k3d_step_span<float> (K=1)" if (dim == 3 and KL == 1) else
+                                    "k%dd%s_rollout<float> (K=%d)" % (dim, "_cache" if dim == 3 else "", KL)),
                          "bytes_per_env_step": b_alg, "envs_per_launch": n},
             "episode_stats": {"sum_return": float(stats[0]), "sum_iou": float(stats[1]), "episodes": float(stats[2]),
                               "steps": float(stats[3])}}
@@ -434,6 +437,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-i16", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="kernel A/B runs: 4 e2e steps only, no int16 e2e")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -8,6 +8,7 @@
 // memory in the reference's padded form (a -1 halfword pair either side) so the 5-cell window is
 // three conflict-free word reads + funnel shifts; observations are staged per warp and streamed out
 // contiguously.
+#include <stdlib.h>
 #include "dmp_common.cuh"
 
 namespace {
@@ -67,7 +68,7 @@ __device__ __forceinline__ double iou1_words(const uint32_t (&hw)[15], const uin
     return __ddiv_rn((double)cross, (double)(a1 + a2 - cross));
 }
 
-template <typename ObsT, int B1>
+template <typename ObsT, int B1, bool PIPE>
 __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO io, const int K) {
     extern __shared__ uint4 smem_raw[];
     uint32_t* G = reinterpret_cast<uint32_t*>(smem_raw);                 // [S1_WORDS][B1]
@@ -86,6 +87,8 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
     const uint8_t* __restrict__ plans = reinterpret_cast<const uint8_t*>(st.plans);
     uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
     uint2 ax = make_uint2(D1_LO, 0);
+    pdl_launch_dependents();
+    pdl_wait();                                                          // the previous step's state is visible from here
     if (live) {
         v0 = cells[env]; v1 = cells[n + env]; v2 = cells[2 * n + env]; v3 = cells[3 * n + env];
         ax = aux[env];
@@ -109,11 +112,20 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
     const int tslot = (io.flags & DMP_F_TSLOT1) ? 1 : 0;
     const uint64_t t0 = st.t_dev ? st.t_dev[tslot] : st.t;
 
+    // software pipeline: the draw of step k+1 does not depend on the state, so it is computed one iteration ahead
+    // and its ~40 dependent integer ops overlap the shared-memory round trips of step k (at BASELINE's 65 536 envs a
+    // scheduler holds only 3-4 warps: instruction-level parallelism is what hides latency there)
+    Draw d_next = Draw{0, 0, 0, 0};
+    if (PIPE && need_draw) d_next = env_draw(st.seed, (uint64_t)(st.env_base + env), t0);
     for (int k = 0; k < K; ++k) {
         const uint64_t t = t0 + (uint64_t)k;
         const int64_t idx = (int64_t)k * n + env;
-        Draw d = Draw{0, 0, 0, 0};
-        if (need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
+        Draw d = d_next;
+        if constexpr (PIPE) {
+            if (need_draw && k + 1 < K) d_next = env_draw(st.seed, (uint64_t)(st.env_base + env), t + 1);
+        } else {
+            if (need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
+        }
         int a, s;
         if (io.actions) a = live ? io.actions[idx] : 0; else a = draw_action(d, D1_ACT, st.action_dist);
         if (io.step_sizes) s = live ? io.step_sizes[idx] : 1; else s = draw_step_size(d);
@@ -288,8 +300,9 @@ template <typename ObsT, int B1>
 int launch_rollout1_b(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
     const size_t smem = (size_t)S1_WORDS * B1 * 4 + (size_t)(B1 / 32) * 32 * D1_OBS * sizeof(ObsT);
     const unsigned blocks = (unsigned)((st.n_envs + B1 - 1) / B1);
-    k1d_rollout<ObsT, B1><<<blocks, B1, smem, s>>>(st, io, K);
-    return dmp_set_error(cudaGetLastError());
+    static const bool pipe = !(getenv("DMP_1D_PIPE") && getenv("DMP_1D_PIPE")[0] == '0');      // tuning switch
+    if (pipe && K > 1) return dmp_set_error(dmp_launch_pdl(k1d_rollout<ObsT, B1, true>, blocks, B1, smem, s, st, io, K));
+    return dmp_set_error(dmp_launch_pdl(k1d_rollout<ObsT, B1, false>, blocks, B1, smem, s, st, io, K));
 }
 
 template <typename ObsT>

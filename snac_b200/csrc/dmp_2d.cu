@@ -156,6 +156,8 @@ __global__ void __launch_bounds__(B2) k2d_rollout(const DmpState st, const DmpIO
     uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
     const uint64_t keep = l2_policy_keep();
     const bool hint = !(io.flags & DMP_F_NO_L2_HINT);
+    pdl_launch_dependents();
+    pdl_wait();                                                          // the previous step's state is visible from here
     if (live) {
         if (hint) {
             v0 = ldg_keep(cells + env, keep);
@@ -395,8 +397,7 @@ int launch_rollout2(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) 
         attr_done = true;
     }
     const unsigned blocks = (unsigned)((st.n_envs + B2 - 1) / B2);
-    k2d_rollout<ObsT><<<blocks, B2, smem, s>>>(st, io, K);
-    return dmp_set_error(cudaGetLastError());
+    return dmp_set_error(dmp_launch_pdl(k2d_rollout<ObsT>, blocks, (unsigned)B2, smem, s, st, io, K));
 }
 
 }  // namespace

@@ -332,14 +332,15 @@ static int dmp3d_wpe_rollout(const DmpState& st, const DmpIO& io, int K, cudaStr
 
 int dmp3d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
     // DMP_3D_KERNEL = w (warp per env) | t (u16 tile, whole maps by bulk async copies) | c (byte cache) |
-    // s (single step, window rows only; K == 1) forces one kernel.  Default: the byte-cache kernel for rollouts
-    // (K > 1), the window-rows kernel for single steps.
+    // r (single step, first generation: six cell loads + window rows; K == 1) forces one kernel.  Default: the
+    // byte-cache kernel for rollouts (K > 1), the row-span kernel (dmp_3d_step2.cu) for single steps.
     const char* v = getenv("DMP_3D_KERNEL");             // read per call: tests switch kernels in-process
     const int forced = v ? (int)v[0] : 0;
     if (forced == 'w') return dmp3d_wpe_rollout(st, io, K, s);
     if (forced == 't') return dmp3d_tile_rollout(st, io, K, s);
     if (forced == 'c') return dmp3d_cache_rollout(st, io, K, s);
-    return K > 1 ? dmp3d_cache_rollout(st, io, K, s) : dmp3d_step_rows(st, io, s);
+    if (forced == 'r' && K == 1) return dmp3d_step_rows(st, io, s);
+    return K > 1 ? dmp3d_cache_rollout(st, io, K, s) : dmp3d_step_span(st, io, s);
 }
 
 int dmp3d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs,

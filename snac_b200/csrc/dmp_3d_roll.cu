@@ -140,6 +140,8 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
 
     // ---- state in: coalesced 128-bit loads of the warp's contiguous maps, packed to bytes -------------
     if (lane == 0) *tallword = 0u;
+    pdl_launch_dependents();
+    pdl_wait();                                                       // the previous launch's state is visible from here
     __syncwarp();
     EnvR e{D2_LO, D2_LO, 0, 0, 0, 0.f, 0};
     double acc_iou = 0.0;                                             // this env's sum of episode IoUs (sequential, exact)
@@ -367,8 +369,7 @@ int launch_cache(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
     }
     const int64_t warps = (st.n_envs + 31) / 32;
     const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
-    k3d_cache_rollout<ObsT><<<blocks, wpb * 32, smem, s>>>(st, io, K);
-    return dmp_set_error(cudaGetLastError());
+    return dmp_set_error(dmp_launch_pdl(k3d_cache_rollout<ObsT>, blocks, (unsigned)(wpb * 32), smem, s, st, io, K));
 }
 
 }  // namespace

@@ -102,4 +102,32 @@ __device__ __forceinline__ void observe_tile(const uint16_t* g, const EnvT& e, O
     obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, total_step, row[49], row[50]);
 }
 
+// stage (c), first half: the 7x7 window of this lane's env as 7 x 4 words of biased halfwords (height + 1, 0 = frame;
+// the upper half of word 3 is unused).  emit_pair() turns them into observation values.
+__device__ __forceinline__ void window_regs(const uint16_t* g, const EnvT& e, uint32_t (&u)[7][4]) {
+    const int ic0 = e.pc - 6;                           // interior column of window column 0 (may be negative)
+    const int w0 = ic0 >> 1;                            // first word of the row to fetch (floor)
+    const int sh16 = (ic0 & 1) * 16;
+    const uint32_t colvalid = (COLVALID >> (e.pc - 3)) & 0x7Fu;
+    uint32_t m[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t lo = (colvalid >> (2 * q)) & 1u, hi = (q < 3) ? ((colvalid >> (2 * q + 1)) & 1u) : 0u;
+        m[q] = (lo ? 0x0000FFFFu : 0u) | (hi ? 0xFFFF0000u : 0u);
+    }
+    const uint32_t* gw = reinterpret_cast<const uint32_t*>(g);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const int ir = e.pr - 6 + k;                    // interior row of window row k
+        const uint32_t rm = ((unsigned)ir < 20u) ? 0xFFFFFFFFu : 0u;
+        const uint32_t* rw = gw + min(max(ir, 0), 19) * 10 + w0;       // over-reads stay inside the 16 B guards
+        const uint32_t x0 = rw[0], x1 = rw[1], x2 = rw[2], x3 = rw[3], x4 = rw[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t lo = q == 0 ? x0 : q == 1 ? x1 : q == 2 ? x2 : x3, hi = q == 0 ? x1 : q == 1 ? x2 : q == 2 ? x3 : x4;
+            u[k][q] = ((__funnelshift_r(lo, hi, sh16) & m[q]) + (m[q] & 0x00010001u)) & rm;
+        }
+    }
+}
+
 }  // namespace u16map

@@ -1,9 +1,15 @@
 // dmp_api.cu -- the C ABI of libdmp.so (include/dmp.h): argument checks, per-dimension dispatch,
 // plan generators / dataset packing (init path) and the episode-statistics reduction.
 #include <math.h>
+#include <stdlib.h>
 #include "dmp_common.cuh"
 
 static int g_last_cuda_error = 0;
+
+bool dmp_pdl_enabled() {
+    static const bool on = !(getenv("DMP_PDL") && getenv("DMP_PDL")[0] == '0');
+    return on;
+}
 
 int dmp_set_error(cudaError_t e) {
     if (e == cudaSuccess) return DMP_OK;

@@ -140,7 +140,36 @@ __device__ __forceinline__ void stg_keep(uint4* p, const uint4& v, uint64_t pol)
                  ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A vector step is one short launch (1D: 4 MB of traffic, ~1 us of work) replayed
+// back to back from a CUDA graph; with stream-serialised launches every step pays the full launch + block-scheduling
+// latency after the previous grid has drained.  The hot kernels therefore (1) signal `launch_dependents` as soon as
+// they start, so the next step's grid is scheduled while this one runs, and (2) touch no global memory before
+// `griddepcontrol.wait`, which returns once the previous grid has completed and its writes are visible.  Both
+// instructions are no-ops when a kernel is launched without the attribute (DMP_PDL=0).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // host-side helpers ---------------------------------------------------------------------------
+bool dmp_pdl_enabled();             // DMP_PDL environment switch (default on), dmp_api.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t dmp_launch_pdl(void (*kern)(KArgs...), unsigned blocks, unsigned threads, size_t smem, cudaStream_t s,
+                                  Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks, 1, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = dmp_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 int dmp_set_error(cudaError_t e);   // records e, returns DMP_OK / DMP_ECUDA
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -151,6 +180,7 @@ int dmp3d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);
 int dmp3d_tile_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);
 int dmp3d_cache_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);
 int dmp3d_step_rows(const DmpState& st, const DmpIO& io, cudaStream_t s);
+int dmp3d_step_span(const DmpState& st, const DmpIO& io, cudaStream_t s);
 int dmp1d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs, int obs_kind, cudaStream_t s);
 int dmp2d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs, int obs_kind, cudaStream_t s);
 int dmp3d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs, int obs_kind, cudaStream_t s);

@@ -311,7 +311,7 @@ def test_3d_kernels_agree(dynamic, K):
     plans = load_plans(3, "dense", "train") if dynamic else None
     n = 333                                                   # ragged last warp
     outs = {}
-    for kind in "wtcs":                                      # "s": the default dispatch (window-rows kernel for K = 1)
+    for kind in "wtcsr":                                     # "s": the default dispatch (row-span kernel for K = 1), "r": first-generation rows kernel
         env = make_gpu(3, dynamic, n, 0, plans, auto_reset=True, env_base=99, seed=SEED, normalise=dynamic,
                        obs_dtype=torch.float64 if dynamic else torch.float32)
         env.reset()
@@ -324,7 +324,7 @@ def test_3d_kernels_agree(dynamic, K):
         st = env.get_state()
         outs[kind] = (res, st["cells"].clone(), st["aux"].clone(), [x.clone() for x in env.episode_stats()])
         env.check_errors()
-    for kind in "tcs":
+    for kind in "tcsr":
         for a, b in zip(outs["w"][0], outs[kind][0]):
             for x, y in zip(a, b):
                 assert torch.equal(x, y), kind
@@ -333,7 +333,7 @@ def test_3d_kernels_agree(dynamic, K):
             assert torch.equal(x, y), kind
 
 
-@pytest.mark.parametrize("kind", ["c", "t", "s1"])
+@pytest.mark.parametrize("kind", ["c", "t", "s1", "r1"])
 @pytest.mark.parametrize("dynamic", [False, True])
 def test_3d_tall_columns_match_oracle(kind, dynamic):
     """Heights around and far beyond the byte range (252..256, 300, 40000) next to the agent: builds on top of
@@ -364,7 +364,7 @@ def test_3d_tall_columns_match_oracle(kind, dynamic):
 
     def run():
         ta, ts = torch.as_tensor(acts, device=env.device), torch.as_tensor(sizes, device=env.device)
-        if kind == "s1":                                      # step by step through the default single-step kernel
+        if kind in ("s1", "r1"):                              # step by step through a single-step kernel
             outs = [[x.clone() for x in env.step(ta[k], ts[k])] for k in range(K)]
             out = [torch.stack([o[i] for o in outs]) for i in range(3)]
         else:
