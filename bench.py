@@ -429,7 +429,9 @@ def main():
     ap.add_argument("--actions", default="philox", choices=["philox", "buffer"])
     ap.add_argument("--mode", default="rollout", choices=["rollout", "step"],
                     help="rollout: K steps per launch (dmp_rollout); step: one launch per vector step (dmp_step)")
-    ap.add_argument("--rollout-k", type=int, default=16)
+    ap.add_argument("--rollout-k", type=int, default=0,
+                    help="steps per dmp_rollout launch (default: 16; 64 for the 1D workloads, whose 65 536-env launches "
+                         "are otherwise dominated by launch latency)")
     ap.add_argument("--single-mode", action="store_true", help="skip the secondary measurement of the other mode")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="2d_static_dense", choices=sorted(WORKLOADS))
@@ -439,6 +441,8 @@ def main():
     ap.add_argument("--no-e2e-i16", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="kernel A/B runs: 4 e2e steps only, no int16 e2e")
     args = ap.parse_args()
+    if not args.rollout_k:
+        args.rollout_k = 64 if WORKLOADS[args.workload][0] == 1 else 16
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -9,17 +9,19 @@ on the CPU so parity tests can replay it through the oracle.
 
 Stream definition (the single source of truth for both sides):
     key     = (seed & 0xffffffff, seed >> 32)
-    counter = (env_id & 0xffffffff, env_id >> 32, t & 0xffffffff, t >> 32)
-              env_id = GLOBAL env index, t = global step index of the vector env
-    x0..x3  = philox4x32_10(counter, key)
-    step_size = 1 + mulhi32(x0, 3)                         in {1,2,3}
-    action    = mulhi32(x1, A)                             uniform over A actions
-              | ref3d: v = mulhi32(x1, 20); v < 16 ? v >> 2 : v - 12
-                (p = [.2,.2,.2,.2,.05,.05,.05,.05], Env/3D/DMP_simulator_3d_static_circle.py:361-362)
-    plan_idx  = mulhi32(x2, n_plans)                       consumed only if the env resets at step t
+    In-step draws -- one Philox block serves FOUR consecutive steps of an env:
+      counter = (env_id & 0xffffffff, env_id >> 32, (t >> 2) & 0xffffffff, (t >> 2) >> 32)
+                env_id = GLOBAL env index, t = global step index of the vector env
+      x0..x3  = philox4x32_10(counter, key);   w = x[t & 3]
+      step_size = 1 + (((w & 0xffff) * 3) >> 16)             in {1,2,3}
+      action    = ((w >> 16) * A) >> 16                      uniform over A actions (16-bit resolution)
+                | ref3d: v = ((w >> 16) * 20) >> 16; v < 16 ? v >> 2 : v - 12
+                  (p = [.2,.2,.2,.2,.05,.05,.05,.05], Env/3D/DMP_simulator_3d_static_circle.py:361-362)
+    Plan of an env that auto-resets in step t (consumed only then) -- a block of its own, keyed apart:
+      plan_idx  = mulhi32(philox4x32_10((env_id lo, env_id hi, t lo, t hi), key ^ PLAN_KEY).x2, n_plans)
 Explicit resets (dmp_reset with plan_idx == NULL, plan_mode Philox) draw
-    plan_idx  = mulhi32(x3, n_plans)   with t = 0xffffffffffffffff - (global step index at reset time)
-so they never share a word with the in-step auto-reset draw (x2).
+    plan_idx  = mulhi32(x3, n_plans)   with counter t = 0xffffffffffffffff - (global step index at reset time)
+under the plain key, far away from the in-step block counters t >> 2.
 """
 from __future__ import annotations
 
@@ -54,19 +56,27 @@ def mulhi32(x, n: int):
     return ((np.asarray(x, dtype=np.uint64) * np.uint64(n)) >> np.uint64(32)).astype(np.int64)
 
 
+PLAN_KEY = 0x504C414E5F4B4559      # "PLAN_KEY": xor-ed into the seed for the auto-reset plan draw
+
+
 def draws(seed: int, env_ids, t: int, n_actions: int, n_plans: int = 1, ref3d: bool = False):
     """(step_size, action, plan_idx) int64 arrays for global env ids at global step t."""
     env_ids = np.asarray(env_ids, dtype=np.uint64)
     t = int(t) & 0xFFFFFFFFFFFFFFFF
-    x0, x1, x2, _ = philox4x32_10(env_ids & MASK, env_ids >> np.uint64(32),
-                                  t & 0xFFFFFFFF, t >> 32,
-                                  seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    step_size = 1 + mulhi32(x0, 3)
+    tb = t >> 2
+    x = philox4x32_10(env_ids & MASK, env_ids >> np.uint64(32), tb & 0xFFFFFFFF, tb >> 32,
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    w = x[t & 3].astype(np.int64)
+    lo, hi = w & 0xFFFF, w >> 16
+    step_size = 1 + ((lo * 3) >> 16)
     if ref3d:
-        v = mulhi32(x1, 20)
+        v = (hi * 20) >> 16
         action = np.where(v < 16, v >> 2, v - 12)
     else:
-        action = mulhi32(x1, n_actions)
+        action = (hi * n_actions) >> 16
+    pk = (seed ^ PLAN_KEY) & 0xFFFFFFFFFFFFFFFF
+    _, _, x2, _ = philox4x32_10(env_ids & MASK, env_ids >> np.uint64(32), t & 0xFFFFFFFF, t >> 32,
+                                pk & 0xFFFFFFFF, (pk >> 32) & 0xFFFFFFFF)
     plan_idx = mulhi32(x2, max(int(n_plans), 1))
     return step_size, action, plan_idx
 

@@ -8,7 +8,6 @@
 // memory in the reference's padded form (a -1 halfword pair either side) so the 5-cell window is
 // three conflict-free word reads + funnel shifts; observations are staged per warp and streamed out
 // contiguously.
-#include <stdlib.h>
 #include "dmp_common.cuh"
 
 namespace {
@@ -68,7 +67,7 @@ __device__ __forceinline__ double iou1_words(const uint32_t (&hw)[15], const uin
     return __ddiv_rn((double)cross, (double)(a1 + a2 - cross));
 }
 
-template <typename ObsT, int B1, bool PIPE>
+template <typename ObsT, int B1>
 __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO io, const int K) {
     extern __shared__ uint4 smem_raw[];
     uint32_t* G = reinterpret_cast<uint32_t*>(smem_raw);                 // [S1_WORDS][B1]
@@ -87,8 +86,6 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
     const uint8_t* __restrict__ plans = reinterpret_cast<const uint8_t*>(st.plans);
     uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
     uint2 ax = make_uint2(D1_LO, 0);
-    pdl_launch_dependents();
-    pdl_wait();                                                          // the previous step's state is visible from here
     if (live) {
         v0 = cells[env]; v1 = cells[n + env]; v2 = cells[2 * n + env]; v3 = cells[3 * n + env];
         ax = aux[env];
@@ -112,23 +109,16 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
     const int tslot = (io.flags & DMP_F_TSLOT1) ? 1 : 0;
     const uint64_t t0 = st.t_dev ? st.t_dev[tslot] : st.t;
 
-    // software pipeline: the draw of step k+1 does not depend on the state, so it is computed one iteration ahead
-    // and its ~40 dependent integer ops overlap the shared-memory round trips of step k (at BASELINE's 65 536 envs a
-    // scheduler holds only 3-4 warps: instruction-level parallelism is what hides latency there)
-    Draw d_next = Draw{0, 0, 0, 0};
-    if (PIPE && need_draw) d_next = env_draw(st.seed, (uint64_t)(st.env_base + env), t0);
+    StepDraws draws;
+    const uint64_t gid = (uint64_t)(st.env_base + env);
     for (int k = 0; k < K; ++k) {
         const uint64_t t = t0 + (uint64_t)k;
         const int64_t idx = (int64_t)k * n + env;
-        Draw d = d_next;
-        if constexpr (PIPE) {
-            if (need_draw && k + 1 < K) d_next = env_draw(st.seed, (uint64_t)(st.env_base + env), t + 1);
-        } else {
-            if (need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
-        }
+        uint32_t dw = 0;
+        if (need_draw) dw = draws.word(st.seed, gid, t);
         int a, s;
-        if (io.actions) a = live ? io.actions[idx] : 0; else a = draw_action(d, D1_ACT, st.action_dist);
-        if (io.step_sizes) s = live ? io.step_sizes[idx] : 1; else s = draw_step_size(d);
+        if (io.actions) a = live ? io.actions[idx] : 0; else a = draw_action(dw, D1_ACT, st.action_dist);
+        if (io.step_sizes) s = live ? io.step_sizes[idx] : 1; else s = draw_step_size(dw);
         if ((unsigned)(s - 1) > 2u) errbits |= DMP_ERR_STEPSIZE;
 
         // ---- step(): Env/1D/DMP_Env_1D_static.py:85-136 ---------------------------------------
@@ -183,8 +173,7 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
                 const int p = io.next_plan[idx];
                 if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
             } else if (st.plan_mode == DMP_PLAN_PHILOX) {
-                if (!need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
-                e.plan_idx = draw_plan(d.x2, st.n_plans);
+                e.plan_idx = draw_plan(plan_word(st.seed, gid, t), st.n_plans);
             } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
                 e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
             }
@@ -300,9 +289,10 @@ template <typename ObsT, int B1>
 int launch_rollout1_b(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
     const size_t smem = (size_t)S1_WORDS * B1 * 4 + (size_t)(B1 / 32) * 32 * D1_OBS * sizeof(ObsT);
     const unsigned blocks = (unsigned)((st.n_envs + B1 - 1) / B1);
-    static const bool pipe = !(getenv("DMP_1D_PIPE") && getenv("DMP_1D_PIPE")[0] == '0');      // tuning switch
-    if (pipe && K > 1) return dmp_set_error(dmp_launch_pdl(k1d_rollout<ObsT, B1, true>, blocks, B1, smem, s, st, io, K));
-    return dmp_set_error(dmp_launch_pdl(k1d_rollout<ObsT, B1, false>, blocks, B1, smem, s, st, io, K));
+    // plain stream-ordered launch: with programmatic dependent launch the next grid's single-warp blocks become
+    // resident early and unbalance the SMs (measured: 47 vs 61 G env-steps/s at 65 536 envs, K = 16)
+    k1d_rollout<ObsT, B1><<<blocks, B1, smem, s>>>(st, io, K);
+    return dmp_set_error(cudaGetLastError());
 }
 
 template <typename ObsT>

@@ -187,14 +187,16 @@ __global__ void __launch_bounds__(B2) k2d_rollout(const DmpState st, const DmpIO
     const int tslot = (io.flags & DMP_F_TSLOT1) ? 1 : 0;
     const uint64_t t0 = st.t_dev ? st.t_dev[tslot] : st.t;
 
+    StepDraws draws;
+
     for (int k = 0; k < K; ++k) {
         const uint64_t t = t0 + (uint64_t)k;
         const int64_t idx = (int64_t)k * n + env;
-        Draw d = Draw{0, 0, 0, 0};
-        if (need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
+        uint32_t dw = 0;
+        if (need_draw) dw = draws.word(st.seed, (uint64_t)(st.env_base + env), t);
         int a, s;
-        if (io.actions) a = live ? io.actions[idx] : 0; else a = draw_action(d, D2_ACT, st.action_dist);
-        if (io.step_sizes) s = live ? io.step_sizes[idx] : 1; else s = draw_step_size(d);
+        if (io.actions) a = live ? io.actions[idx] : 0; else a = draw_action(dw, D2_ACT, st.action_dist);
+        if (io.step_sizes) s = live ? io.step_sizes[idx] : 1; else s = draw_step_size(dw);
         if ((unsigned)(s - 1) > 2u) errbits |= DMP_ERR_STEPSIZE;
 
         // ---- step(): Env/2D/DMP_Env_2D_static.py:95-154 ------------------------------------
@@ -249,8 +251,7 @@ __global__ void __launch_bounds__(B2) k2d_rollout(const DmpState st, const DmpIO
                 const int p = io.next_plan[idx];
                 if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
             } else if (st.plan_mode == DMP_PLAN_PHILOX) {
-                if (!need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
-                e.plan_idx = draw_plan(d.x2, st.n_plans);
+                e.plan_idx = draw_plan(plan_word(st.seed, (uint64_t)(st.env_base + env), t), st.n_plans);
             } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
                 e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
             }

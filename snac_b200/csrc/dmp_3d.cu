@@ -98,13 +98,15 @@ __global__ void __launch_bounds__(WPB3 * 32) k3d_rollout(const DmpState st, cons
     const int xdir = lane / 3, xdist = lane % 3 + 1;
     const int xdr = dir_dr(xdir) * xdist, xdc = dir_dc(xdir) * xdist;
 
+    StepDraws draws;
+
     for (int k = 0; k < K; ++k) {
         const uint64_t t = t0 + (uint64_t)k;
         const int64_t idx = (int64_t)k * n + env;
-        Draw d = Draw{0, 0, 0, 0};
-        if (need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
-        const int a = io.actions ? (int)io.actions[idx] : draw_action(d, D3_ACT, st.action_dist);
-        const int s = io.step_sizes ? (int)io.step_sizes[idx] : draw_step_size(d);
+        uint32_t dw = 0;
+        if (need_draw) dw = draws.word(st.seed, (uint64_t)(st.env_base + env), t);
+        const int a = io.actions ? (int)io.actions[idx] : draw_action(dw, D3_ACT, st.action_dist);
+        const int s = io.step_sizes ? (int)io.step_sizes[idx] : draw_step_size(dw);
         if ((unsigned)(s - 1) > 2u) errbits |= DMP_ERR_STEPSIZE;
         if (a > 7) errbits |= DMP_ERR_ACTION;          // reference: treated as an unbuilt brick (:187-208)
 
@@ -207,8 +209,7 @@ __global__ void __launch_bounds__(WPB3 * 32) k3d_rollout(const DmpState st, cons
                 const int p = io.next_plan[idx];
                 if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
             } else if (st.plan_mode == DMP_PLAN_PHILOX) {
-                if (!need_draw) d = env_draw(st.seed, (uint64_t)(st.env_base + env), t);
-                e.plan_idx = draw_plan(d.x2, st.n_plans);
+                e.plan_idx = draw_plan(plan_word(st.seed, (uint64_t)(st.env_base + env), t), st.n_plans);
             } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
                 e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
             }

@@ -63,11 +63,12 @@ __global__ void __launch_bounds__(WPB_STEP * 32) k3d_step_rows(const DmpState st
     const uint64_t gid = (uint64_t)(st.env_base + env0) + (uint64_t)lane;
     const int64_t idx = env0 + lane;
 
-    Draw d = Draw{0, 0, 0, 0};
-    if (need_draw) d = env_draw(st.seed, gid, t);
+    StepDraws draws;
+    uint32_t dw = 0;
+    if (need_draw) dw = draws.word(st.seed, gid, t);
     int a, s;
-    if (io.actions) a = live ? (int)io.actions[idx] : 0; else a = draw_action(d, D3_ACT, st.action_dist);
-    if (io.step_sizes) s = live ? (int)io.step_sizes[idx] : 1; else s = draw_step_size(d);
+    if (io.actions) a = live ? (int)io.actions[idx] : 0; else a = draw_action(dw, D3_ACT, st.action_dist);
+    if (io.step_sizes) s = live ? (int)io.step_sizes[idx] : 1; else s = draw_step_size(dw);
     if ((unsigned)(s - 1) > 2u) errbits |= DMP_ERR_STEPSIZE;
     if (a > 7) errbits |= DMP_ERR_ACTION;                  // reference: an unbuilt brick (:187-208)
 
@@ -179,8 +180,7 @@ __global__ void __launch_bounds__(WPB_STEP * 32) k3d_step_rows(const DmpState st
             const int p = io.next_plan[idx];
             if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
         } else if (st.plan_mode == DMP_PLAN_PHILOX) {
-            if (!need_draw) d = env_draw(st.seed, gid, t);
-            e.plan_idx = draw_plan(d.x2, st.n_plans);
+            e.plan_idx = draw_plan(plan_word(st.seed, gid, t), st.n_plans);
         } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
             e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
         }

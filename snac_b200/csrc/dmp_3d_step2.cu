@@ -8,8 +8,8 @@
 // is: the 7 rows under the old window, plus `step_size` more rows in the direction of a vertical move.  They come in
 // as ONE bulk async copy per env (cp.async.bulk -> UBLKCP, <= 416 B) right after the scalar state; the decision
 // cells, the new window and the brick patch are all served from that staged span.  The observation tile of the warp
-// is built in the same shared memory once every lane holds its window in registers, so a warp needs 14 KB instead
-// of 17 KB (+ f32 tile) and 15 single-warp blocks fit an SM.
+// is built in the same shared memory once every lane holds its window in registers, so a warp needs 14.5 KB instead
+// of 17 KB (+ f32 tile) and 14 single-warp blocks fit an SM.
 // Semantics: Env/3D/DMP_simulator_3d_static_circle.py:67-276 and
 // Env/3D/DMP_simulator_3d_dynamic_triangle_usedata.py:45-277 (see dmp_3d.cu for the line-by-line citations).
 #include "dmp_3d_u16.cuh"
@@ -18,7 +18,9 @@ namespace {
 
 using namespace u16map;
 
-constexpr int SLOT2_B = 448;                 // per-lane staging: 16 B guard | <= 416 B of rows | 16 B guard
+constexpr int SLOT2_B = 464;                 // per-lane staging: 16 B guard | <= 416 B of rows | 16 B guard, padded to an
+                                             // ODD number of 16 B granules (29): same-offset words of the 32 lanes then fall
+                                             // into 8 distinct 4-bank groups (4-way conflicts; 448 B = 28 granules gave 16-way)
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
 template <typename ObsT>
@@ -57,11 +59,12 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
     const int64_t idx = env0 + lane;
     int errbits = 0;
 
-    Draw d = Draw{0, 0, 0, 0};
-    if (need_draw) d = env_draw(st.seed, gid, t);
+    StepDraws draws;
+    uint32_t dw = 0;
+    if (need_draw) dw = draws.word(st.seed, gid, t);
     int a, s;
-    if (io.actions) a = live ? (int)io.actions[idx] : 0; else a = draw_action(d, D3_ACT, st.action_dist);
-    if (io.step_sizes) s = live ? (int)io.step_sizes[idx] : 1; else s = draw_step_size(d);
+    if (io.actions) a = live ? (int)io.actions[idx] : 0; else a = draw_action(dw, D3_ACT, st.action_dist);
+    if (io.step_sizes) s = live ? (int)io.step_sizes[idx] : 1; else s = draw_step_size(dw);
     if ((unsigned)(s - 1) > 2u) errbits |= DMP_ERR_STEPSIZE;
     if (a > 7) errbits |= DMP_ERR_ACTION;                  // reference: an unbuilt brick (:187-208)
     const int dir = a & 3, dr = dir_dr(dir), dc = dir_dc(dir);
@@ -195,8 +198,7 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
             const int p = io.next_plan[idx];
             if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
         } else if (st.plan_mode == DMP_PLAN_PHILOX) {
-            if (!need_draw) d = env_draw(st.seed, gid, t);
-            e.plan_idx = draw_plan(d.x2, st.n_plans);
+            e.plan_idx = draw_plan(plan_word(st.seed, gid, t), st.n_plans);
         } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
             e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
         }

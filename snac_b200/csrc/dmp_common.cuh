@@ -45,13 +45,38 @@ __device__ __forceinline__ Draw env_draw(uint64_t seed, uint64_t env_id, uint64_
                          (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
-__device__ __forceinline__ int draw_step_size(const Draw& d) { return 1 + (int)__umulhi(d.x0, 3u); }
-__device__ __forceinline__ int draw_action(const Draw& d, int n_actions, int dist) {
+// In-step draws (stream definition: oracle/philox.py).  One Philox block serves FOUR consecutive steps:
+//   block = philox4x32_10(counter = (env lo, env hi, (t >> 2) lo, (t >> 2) hi), key = seed),  w = block.x[t & 3]
+//   step_size = 1 + (((w & 0xffff) * 3) >> 16)          action = ((w >> 16) * A) >> 16
+// so a rollout pays the ten Philox rounds once per four steps (they were a quarter of the 1D kernel's instructions).
+struct StepDraws {
+    Draw blk;
+    uint64_t tb;                                        // block index held in blk (~0 = none)
+    __device__ __forceinline__ StepDraws() : blk{0u, 0u, 0u, 0u}, tb(~0ull) {}
+    __device__ __forceinline__ uint32_t word(uint64_t seed, uint64_t env_id, uint64_t t) {
+        const uint64_t b = t >> 2;
+        if (b != tb) {                                  // warp-uniform: t is the same for every env of a launch
+            blk = env_draw(seed, env_id, b);
+            tb = b;
+        }
+        const uint32_t j = (uint32_t)t & 3u;
+        return j == 0u ? blk.x0 : (j == 1u ? blk.x1 : (j == 2u ? blk.x2 : blk.x3));
+    }
+};
+
+__device__ __forceinline__ int draw_step_size(uint32_t w) { return 1 + (int)(((w & 0xFFFFu) * 3u) >> 16); }
+__device__ __forceinline__ int draw_action(uint32_t w, int n_actions, int dist) {
+    const uint32_t h = w >> 16;
     if (dist == DMP_ACT_REF3D) {
-        const int v = (int)__umulhi(d.x1, 20u);
+        const int v = (int)((h * 20u) >> 16);
         return v < 16 ? (v >> 2) : (v - 12);
     }
-    return (int)__umulhi(d.x1, (uint32_t)n_actions);
+    return (int)((h * (uint32_t)n_actions) >> 16);
+}
+// plan index of an env that auto-resets in step t: its own block, keyed apart from the step draws
+constexpr uint64_t DMP_PLAN_KEY = 0x504C414E5F4B4559ull;     // "PLAN_KEY"
+__device__ __forceinline__ uint32_t plan_word(uint64_t seed, uint64_t env_id, uint64_t t) {
+    return env_draw(seed ^ DMP_PLAN_KEY, env_id, t).x2;
 }
 __device__ __forceinline__ int draw_plan(uint32_t x, int n_plans) { return (int)__umulhi(x, (uint32_t)n_plans); }
 

@@ -90,10 +90,11 @@ __device__ int plan_cell(const DmpState& st, int plan_idx, int r, int c) {
 
 __device__ __forceinline__ void step_inputs(const DmpState& st, const DmpIO& io, int64_t env, int& a, int& s) {
     const int A = st.dim == 1 ? D1_ACT : (st.dim == 2 ? D2_ACT : D3_ACT);
-    Draw d = Draw{0, 0, 0, 0};
-    if (!io.actions || !io.step_sizes) d = env_draw(st.seed, (uint64_t)(st.env_base + env), st.t);
-    a = io.actions ? (int)io.actions[env] : draw_action(d, A, st.action_dist);
-    s = io.step_sizes ? (int)io.step_sizes[env] : draw_step_size(d);
+    StepDraws draws;
+    uint32_t dw = 0;
+    if (!io.actions || !io.step_sizes) dw = draws.word(st.seed, (uint64_t)(st.env_base + env), st.t);
+    a = io.actions ? (int)io.actions[env] : draw_action(dw, A, st.action_dist);
+    s = io.step_sizes ? (int)io.step_sizes[env] : draw_step_size(dw);
 }
 
 __device__ __forceinline__ int dr_of(int d) { return d == 2 ? 1 : (d == 3 ? -1 : 0); }
@@ -292,7 +293,7 @@ __global__ void k_stage_done_reset(const DmpState st, const DmpIO io) {
     st.ep_ret[env] += (double)e.ret;
     st.ep_iou[env] += iou_generic(st, env, e);
     if (io.next_plan) e.plan_idx = io.next_plan[env];
-    else if (st.plan_mode == DMP_PLAN_PHILOX) e.plan_idx = draw_plan(env_draw(st.seed, (uint64_t)(st.env_base + env), st.t).x2, st.n_plans);
+    else if (st.plan_mode == DMP_PLAN_PHILOX) e.plan_idx = draw_plan(plan_word(st.seed, (uint64_t)(st.env_base + env), st.t), st.n_plans);
     else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
     if (st.dim == 3) {
         uint4* g4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(st.cells) + env * CELLS3D);

@@ -1,15 +1,15 @@
 #!/bin/bash
 # One gpurun call: GPU tests, A/B benches of the round's kernel changes, ncu captures.  Outputs -> gpurun_out/
 set -u
-O=gpurun_out/ra; mkdir -p $O
+O=gpurun_out/${1:-ra}; mkdir -p $O
 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest exit $?" >> $O/pytest.log; tail -3 $O/pytest.log
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -2 $O/smoke.log
 B="python bench.py --steps 8192 --warmup 1024"
 $B > $O/b_2d.json 2> $O/b_2d.err
 DMP_PDL=0 $B --no-cpu-baseline --no-e2e > $O/b_2d_nopdl.json 2>&1
 $B --workload 1d_dynamic --no-cpu-baseline --no-e2e > $O/b_1d.json 2>&1
-DMP_PDL=0 $B --workload 1d_dynamic --no-cpu-baseline --no-e2e > $O/b_1d_nopdl.json 2>&1
-DMP_1D_PIPE=0 $B --workload 1d_dynamic --no-cpu-baseline --no-e2e > $O/b_1d_nopipe.json 2>&1
+$B --workload 1d_dynamic --rollout-k 16 --no-cpu-baseline --no-e2e > $O/b_1d_k16.json 2>&1
+$B --workload 1d_static_step --no-cpu-baseline --no-e2e > $O/b_1d_static.json 2>&1
 $B --workload 1d_dynamic --envs 4194304 --no-cpu-baseline --no-e2e > $O/b_1d_4m.json 2>&1
 $B --workload 3d_static_dense --no-cpu-baseline --no-e2e > $O/b_3d.json 2>&1
 DMP_PDL=0 $B --workload 3d_static_dense --no-cpu-baseline --no-e2e > $O/b_3d_nopdl.json 2>&1
