@@ -2,12 +2,14 @@
 """Per-source-line totals (instructions executed, stall samples, shared-memory wavefronts) from an
 `ncu --set full --import-source on` report of a kernel compiled with -lineinfo.
 
-    python tools/ncu_lines.py gpurun_out/prof.ncu-rep [top_n]
+    python tools/ncu_lines.py gpurun_out/prof.ncu-rep [top_n] [--by-samples]
 """
 import csv, io, subprocess, sys, collections
 
-rep = sys.argv[1]
-top = int(sys.argv[2]) if len(sys.argv) > 2 else 45
+by_samples = "--by-samples" in sys.argv
+argv = [a for a in sys.argv if a != "--by-samples"]
+rep = argv[1]
+top = int(argv[2]) if len(argv) > 2 else 45
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
                      capture_output=True, text=True, check=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
@@ -34,5 +36,5 @@ for r in rows:
     a[4] = r[1]
 tot = sum(a[0] for a in agg.values()); tots = sum(a[1] for a in agg.values())
 print("total inst %d, samples %d" % (tot, tots))
-for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1 if by_samples else 0])[:top]:
     print("%-22s inst %5.1f%%  samples %5.1f%%  smem_wf %9d excess %9d  %s" % ("%s:%d" % k, 100.0 * a[0] / max(tot, 1), 100.0 * a[1] / max(tots, 1), a[2], a[3], a[4].strip()[:100]))
