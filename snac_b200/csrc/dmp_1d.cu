@@ -8,7 +8,6 @@
 // memory in the reference's padded form (a -1 halfword pair either side) so the 5-cell window is
 // three conflict-free word reads + funnel shifts; observations are staged per warp and streamed out
 // contiguously.
-#include <stdlib.h>
 #include "dmp_common.cuh"
 
 namespace {
@@ -198,196 +197,6 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
     if (st.t_dev && blockIdx.x == 0 && tid == 0) st.t_dev[tslot ^ 1] = t0 + (uint64_t)K;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Rollouts (K >= 8): the same step, split over two warp roles per 32 envs.
-//
-// At BASELINE's 65 536 envs a scheduler holds 3-4 warps of the one-role kernel above, each a single dependent
-// chain of ~220 instructions per step (draw -> move/deposit -> window -> convert -> tile -> store): the kernel is
-// bound by instruction latency (53 % issue utilisation, profiles/README.md), not by HBM.  Only the first half of
-// that chain carries state from step to step.  So a block is a PRODUCER warp that advances the 32 envs (draws,
-// move, deposit, reward, done, auto-reset, statistics; heights stay in its shared-memory columns) and hands each
-// step's raw results -- the window's five halfwords, the counters, reward, done: 5 words per env -- through a
-// 4-deep shared-memory ring to a CONSUMER warp that formats the observation row, transposes it through the warp
-// tile and streams obs / reward / done to HBM.  The two chains overlap (the producer runs up to four steps ahead),
-// which doubles the warps per scheduler without adding envs.  Hand-off is two named barriers per ring slot
-// (bar.arrive by the side that is done with the slot, bar.sync by the side that needs it).
-// ---------------------------------------------------------------------------------------------------------
-constexpr int WS_RING = 4;            // ring depth (slots)
-constexpr int WS_WORDS = 5;           // words per env per slot
-
-__device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
-
-template <typename ObsT>
-__global__ void __launch_bounds__(64) k1d_rollout_ws(const DmpState st, const DmpIO io, const int K) {
-    extern __shared__ uint4 smem_raw[];
-    uint32_t* G = reinterpret_cast<uint32_t*>(smem_raw);                 // [S1_WORDS][32]  producer: height columns
-    uint32_t* ring = G + S1_WORDS * 32;                                  // [WS_RING][WS_WORDS][32]
-    ObsT* tile = reinterpret_cast<ObsT*>(ring + WS_RING * WS_WORDS * 32); // [32*7]          consumer: warp tile
-    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-    const int64_t n = st.n_envs;
-    const int64_t env0 = (int64_t)blockIdx.x * 32;
-    const int64_t env = env0 + lane;
-    const int nvalid = (int)min((int64_t)32, n - env0);
-    const bool live = env < n;
-    const bool normalise = io.flags & DMP_F_NORMALISE;
-
-    if (role == 1) {
-        // ================================ consumer: format + store ================================
-        ObsT* obs_dst = io.obs ? reinterpret_cast<ObsT*>(io.obs) + env0 * D1_OBS : nullptr;
-        float* rew_dst = io.reward ? io.reward + env : nullptr;
-        uint8_t* done_dst = io.done ? io.done + env : nullptr;
-        const int64_t obs_stride = n * D1_OBS;
-        const uint32_t* slot_base = ring + lane;
-        for (int k = 0; k < K; ++k) {
-            const int sl = k & (WS_RING - 1);
-            named_bar_sync(1 + sl);                                       // slot filled by the producer
-            const uint32_t* r = slot_base + sl * (WS_WORDS * 32);
-            const uint32_t w0 = r[0], w1 = r[32], w2 = r[64], w3 = r[96], w4 = r[128];
-            if (k + WS_RING < K) named_bar_arrive(1 + WS_RING + sl);      // slot free again (nobody waits for the last ones)
-            if (obs_dst) {
-                ObsT* row = tile + lane * D1_OBS;
-                row[0] = obs_from_int<ObsT>((int)(int16_t)(w0 & 0xFFFF));
-                row[1] = obs_from_int<ObsT>((int)(int16_t)(w0 >> 16));
-                row[2] = obs_from_int<ObsT>((int)(int16_t)(w1 & 0xFFFF));
-                row[3] = obs_from_int<ObsT>((int)(int16_t)(w1 >> 16));
-                row[4] = obs_from_int<ObsT>((int)(int16_t)(w2 & 0xFFFF));
-                obs_counters<ObsT>(normalise, (int)(w3 & 0xFFFF), (int)(w3 >> 16), (int)(w4 >> 8), st.total_step, row[5], row[6]);
-                __syncwarp();
-                if (nvalid == 32) warp_tile_store_full<ObsT, 32 * D1_OBS>(obs_dst, tile, lane);
-                else warp_tile_store<ObsT>(obs_dst, tile, nvalid * D1_OBS, lane);
-                __syncwarp();
-                obs_dst += obs_stride;
-            }
-            if (live) {
-                if (rew_dst) *rew_dst = (float)(int)(int16_t)(w2 >> 16);
-                if (done_dst) *done_dst = (uint8_t)(w4 & 1u);
-            }
-            if (rew_dst) rew_dst += n;
-            if (done_dst) done_dst += n;
-        }
-        return;
-    }
-
-    // ==================================== producer: advance the envs ====================================
-    uint32_t* g = G + lane;
-    uint4* cells = reinterpret_cast<uint4*>(st.cells);
-    uint2* aux = reinterpret_cast<uint2*>(st.aux);
-    const uint8_t* __restrict__ plans = reinterpret_cast<const uint8_t*>(st.plans);
-    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
-    uint2 ax = make_uint2(D1_LO, 0);
-    if (live) {
-        v0 = cells[env]; v1 = cells[n + env]; v2 = cells[2 * n + env]; v3 = cells[3 * n + env];
-        ax = aux[env];
-    }
-    g[0] = 0xFFFFFFFFu;
-    g[1 * 32] = v0.x;  g[2 * 32] = v0.y;  g[3 * 32] = v0.z;  g[4 * 32] = v0.w;
-    g[5 * 32] = v1.x;  g[6 * 32] = v1.y;  g[7 * 32] = v1.z;  g[8 * 32] = v1.w;
-    g[9 * 32] = v2.x;  g[10 * 32] = v2.y; g[11 * 32] = v2.z; g[12 * 32] = v2.w;
-    g[13 * 32] = v3.x; g[14 * 32] = v3.y; g[15 * 32] = v3.z;
-    g[16 * 32] = 0xFFFFFFFFu;
-    Env1 e;
-    e.pos = ax.x & 0xFFFF; e.plan_idx = ax.x >> 16; e.ret = __uint_as_float(ax.y);
-    e.cb = v3.w & 0xFFFF; e.cs = v3.w >> 16;
-    int total_brick = __ldg(st.plan_total + e.plan_idx);
-    unsigned dirty = 0;
-    int errbits = 0;
-    const bool autoreset = io.flags & DMP_F_AUTORESET;
-    const bool need_draw = (io.actions == nullptr) || (io.step_sizes == nullptr);
-    const int tslot = (io.flags & DMP_F_TSLOT1) ? 1 : 0;
-    const uint64_t t0 = st.t_dev ? st.t_dev[tslot] : st.t;
-    const uint64_t gid = (uint64_t)(st.env_base + env);
-    const uint8_t* act_src = io.actions ? io.actions + env : nullptr;
-    const uint8_t* size_src = io.step_sizes ? io.step_sizes + env : nullptr;
-    uint32_t* slot_base = ring + lane;
-
-    StepDraws draws;
-    for (int k = 0; k < K; ++k) {
-        const uint64_t t = t0 + (uint64_t)k;
-        uint32_t dw = 0;
-        if (need_draw) dw = draws.word(st.seed, gid, t);
-        int a, s;
-        if (act_src) { a = live ? *act_src : 0; act_src += n; } else a = draw_action(dw, D1_ACT, st.action_dist);
-        if (size_src) { s = live ? *size_src : 1; size_src += n; } else s = draw_step_size(dw);
-        if ((unsigned)(s - 1) > 2u) errbits |= DMP_ERR_STEPSIZE;
-
-        // ---- step(): Env/1D/DMP_Env_1D_static.py:85-136 ---------------------------------------
-        e.cs += 1;
-        int reward = 0;                                     // -1 / 0 / 1 / 10: exact as int16
-        bool done;
-        if (a < 2) {                                        // (a) move left / right
-            stage_move1(e, a, s);
-            done = e.cs >= st.total_step;
-        } else if (a == 2) {                                // (b) drop + (d) reward
-            e.cb += 1;
-            const int h = stage_deposit1<32>(g, e);
-            dirty |= 1u << ((e.pos - D1_HW) >> 3);
-            if (e.cb >= total_brick) {                      // :107-114
-                done = true;
-            } else {                                        // :116-123
-                done = e.cs >= st.total_step;
-                const int p = plans[e.plan_idx * PLAN1D_BYTES + (e.pos - D1_HW)];
-                reward = (h > p) ? -1 : (h == p ? 10 : 1);
-            }
-        } else {
-            errbits |= DMP_ERR_ACTION;
-            done = e.cs >= st.total_step;
-        }
-        e.ret += (float)reward;
-
-        // ---- hand the step's raw results to the consumer ------------------------------------------
-        const int sl = k & (WS_RING - 1);
-        if (k >= WS_RING) named_bar_sync(1 + WS_RING + sl);                // the consumer has drained this slot
-        {
-            const int p0 = e.pos - D1_HW;
-            const int w = p0 >> 1, sh = (p0 & 1) * 16;
-            const uint32_t x0 = g[w * 32], x1 = g[(w + 1) * 32], x2 = g[(w + 2) * 32];
-            uint32_t* r = slot_base + sl * (WS_WORDS * 32);
-            r[0] = __funnelshift_r(x0, x1, sh);
-            r[32] = __funnelshift_r(x1, x2, sh);
-            r[64] = ((x2 >> sh) & 0xFFFFu) | ((uint32_t)reward << 16);
-            r[96] = (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16);
-            r[128] = (done ? 1u : 0u) | ((uint32_t)total_brick << 8);
-        }
-        named_bar_arrive(1 + sl);
-
-        if (done && autoreset && live) {
-            uint32_t hw[15];
-#pragma unroll
-            for (int j = 0; j < 15; ++j) hw[j] = g[(j + 1) * 32];
-            const double iou = iou1_words(hw, plans + e.plan_idx * PLAN1D_BYTES);
-            atomicAdd(st.ep_cnt + env, 1u);
-            atomicAdd(st.ep_len + env, (uint32_t)e.cs);
-            atomicAdd(st.ep_ret + env, (double)e.ret);
-            atomicAdd(st.ep_iou + env, iou);
-            if (io.next_plan) {
-                const int p = io.next_plan[(int64_t)k * n + env];
-                if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
-            } else if (st.plan_mode == DMP_PLAN_PHILOX) {
-                e.plan_idx = draw_plan(plan_word(st.seed, gid, t), st.n_plans);
-            } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
-                e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
-            }
-            total_brick = __ldg(st.plan_total + e.plan_idx);
-#pragma unroll
-            for (int j = 1; j <= 15; ++j) g[j * 32] = 0;
-            e.pos = D1_LO; e.cb = e.cs = 0; e.ret = 0.f;
-            dirty = 0xFu;
-        }
-    }
-
-    if (live) {
-        if (dirty & 1u) cells[env] = make_uint4(g[1 * 32], g[2 * 32], g[3 * 32], g[4 * 32]);
-        if (dirty & 2u) cells[n + env] = make_uint4(g[5 * 32], g[6 * 32], g[7 * 32], g[8 * 32]);
-        if (dirty & 4u) cells[2 * n + env] = make_uint4(g[9 * 32], g[10 * 32], g[11 * 32], g[12 * 32]);
-        cells[3 * n + env] = make_uint4(g[13 * 32], g[14 * 32], g[15 * 32],
-                                        (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16));
-        aux[env] = make_uint2((uint32_t)e.pos | ((uint32_t)e.plan_idx << 16), __float_as_uint(e.ret));
-        if (errbits) atomicOr(st.err, errbits);
-    }
-    if (st.t_dev && blockIdx.x == 0 && lane == 0) st.t_dev[tslot ^ 1] = t0 + (uint64_t)K;
-}
-
 template <typename ObsT>
 __global__ void k1d_reset(const DmpState st, const uint8_t* __restrict__ mask, const int32_t* __restrict__ plan_idx,
                           const uint64_t t_draw, ObsT* __restrict__ obs) {
@@ -487,20 +296,7 @@ int launch_rollout1_b(const DmpState& st, const DmpIO& io, int K, cudaStream_t s
 }
 
 template <typename ObsT>
-int launch_rollout1_ws(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
-    const size_t smem = (size_t)(S1_WORDS + WS_RING * WS_WORDS) * 32 * 4 + (size_t)32 * D1_OBS * sizeof(ObsT);
-    const unsigned blocks = (unsigned)((st.n_envs + 31) / 32);
-    k1d_rollout_ws<ObsT><<<blocks, 64, smem, s>>>(st, io, K);
-    return dmp_set_error(cudaGetLastError());
-}
-
-template <typename ObsT>
 int launch_rollout1(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
-    // DMP_1D_KERNEL = o (one warp role) | w (producer / consumer warps) forces a kernel; default: two roles for
-    // rollouts that are long enough to fill the ring, one role for single steps and short rollouts
-    const char* v = getenv("DMP_1D_KERNEL");
-    const int forced = v ? (int)v[0] : 0;
-    if (forced == 'w' || (forced != 'o' && K >= 8)) return launch_rollout1_ws<ObsT>(st, io, K, s);
     // fewer than ~4 blocks of 128 per SM: single-warp blocks spread the warps evenly over the 148 SMs
     if (st.n_envs < (int64_t)128 * 148 * 4) return launch_rollout1_b<ObsT, 32>(st, io, K, s);
     return launch_rollout1_b<ObsT, 128>(st, io, K, s);

@@ -85,6 +85,7 @@ class DeviceRollout:
         self.T = int(horizon) + (int(horizon) & 1)
         n, D, dev = env.num_envs, env.obs_dim, env.device
         self.obs = torch.zeros((self.T + 1, n, D), dtype=env.obs_dtype, device=dev)      # obs[t] is the input of step t
+        self._cur = torch.zeros((n, D), dtype=env.obs_dtype, device=dev)                 # observation carried between collects
         self.actions = torch.zeros((self.T, n), dtype=torch.uint8, device=dev)
         self.reward = torch.zeros((self.T, n), dtype=torch.float32, device=dev)
         self.done = torch.zeros((self.T, n), dtype=torch.uint8, device=dev)
@@ -95,11 +96,12 @@ class DeviceRollout:
 
     def set_initial_obs(self, obs: torch.Tensor) -> None:
         """Observation the first step's policy call sees (normally what env.reset() returned)."""
-        self.obs[0].copy_(obs)
+        self._cur.copy_(obs)
         self._primed = True
 
     def _body(self) -> None:
         env = self.env
+        self.obs[0].copy_(self._cur)
         for t in range(self.T):
             a = None
             if self.policy is not None:
@@ -107,7 +109,7 @@ class DeviceRollout:
                 a = self.actions[t:t + 1]
             env.rollout(1, actions=a, out=(self.obs[t + 1:t + 2], self.reward[t:t + 1], self.done[t:t + 1]),
                         use_device_t=True, t_slot=t & 1)
-        self.obs[0].copy_(self.obs[self.T])                  # next collect() continues from the last observation
+        self._cur.copy_(self.obs[self.T])                    # next collect() continues from the last observation
 
     def collect(self) -> dict:
         env = self.env
@@ -120,11 +122,11 @@ class DeviceRollout:
                 if self._use_graph:
                     # warm-up pass outside capture (lazy initialisation, cuBLAS workspaces); it must not count as
                     # experience, so the env is put back exactly where it was before capturing
-                    first, snapshot = self.obs[0].clone(), env.get_state()
+                    first, snapshot = self._cur.clone(), env.get_state()
                     env._t_dev.fill_(env.t)
                     self._body()
                     env.set_state(snapshot)
-                    self.obs[0].copy_(first)
+                    self._cur.copy_(first)
                     self._stream.synchronize()
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=self._stream):

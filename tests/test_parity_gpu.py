@@ -381,38 +381,3 @@ def test_3d_tall_columns_match_oracle(kind, dynamic):
     assert np.array_equal(st["scalars"].cpu().numpy()[:, :4], sc_ref[:, :4])
     assert g_ref.max() > 40000 or g_ref.max() >= 254
     assert np.array_equal(env.iou().cpu().numpy(), ob.iou(), equal_nan=True)
-
-
-# ------------------------------------------------------------------------------------------------
-# 8. the two 1D rollout kernels (one warp role / producer + consumer warps) are interchangeable
-# ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("dynamic", [False, True])
-@pytest.mark.parametrize("K", [8, 13, 96])
-def test_1d_kernels_agree(dynamic, K):
-    plans = load_plans(1) if dynamic else None
-    n = 1000                                                  # ragged last warp
-    outs = {}
-    for kind in "ow":
-        env = make_gpu(1, dynamic, n, 2, plans, auto_reset=True, env_base=7, seed=SEED, normalise=dynamic,
-                       obs_dtype=torch.float64 if dynamic else torch.float32, total_step=40)
-        env.reset()
-        old = os.environ.get("DMP_1D_KERNEL")
-        os.environ["DMP_1D_KERNEL"] = kind
-        try:
-            res = [[x.clone() for x in env.rollout(K)] for _ in range(3)]
-            torch.cuda.synchronize()
-        finally:
-            if old is None:
-                del os.environ["DMP_1D_KERNEL"]
-            else:
-                os.environ["DMP_1D_KERNEL"] = old
-        st = env.get_state()
-        outs[kind] = (res, st["cells"].clone(), st["aux"].clone(), [x.clone() for x in env.episode_stats()])
-        env.check_errors()
-    for a, b in zip(outs["o"][0], outs["w"][0]):
-        for x, y in zip(a, b):
-            assert torch.equal(x, y)
-    assert torch.equal(outs["o"][1], outs["w"][1]) and torch.equal(outs["o"][2], outs["w"][2])
-    for x, y in zip(outs["o"][3], outs["w"][3]):
-        assert torch.equal(x, y)
-    assert outs["w"][3][0].sum().item() > 0                   # episodes did finish (total_step = 40)

@@ -69,7 +69,8 @@ def test_epsilon_greedy_qsa_graph_equals_eager():
                                          torch.nn.Linear(128, 128), torch.nn.ReLU(), torch.nn.Linear(128, 1))
 
         def forward(self, s, a):
-            return self.f(torch.cat((s, a), dim=1))
+            # a state-dependent phase on top of the MLP, so that the greedy action of a random-init net varies
+            return self.f(torch.cat((s, a), dim=1)) + torch.sin(0.37 * s.sum(dim=1, keepdim=True) + 1.3 * a)
 
     torch.manual_seed(0)
     q = QSAAdapter(QNet().cuda(), 5)

@@ -9,8 +9,6 @@ $B > $O/b_2d.json 2> $O/b_2d.err
 DMP_PDL=0 $B --no-cpu-baseline --no-e2e > $O/b_2d_nopdl.json 2>&1
 $B --workload 1d_dynamic --no-cpu-baseline --no-e2e > $O/b_1d.json 2>&1
 $B --workload 1d_dynamic --rollout-k 16 --no-cpu-baseline --no-e2e > $O/b_1d_k16.json 2>&1
-DMP_1D_KERNEL=o $B --workload 1d_dynamic --single-mode --no-cpu-baseline --no-e2e > $O/b_1d_onerole.json 2>&1
-$B --workload 1d_dynamic --rollout-k 256 --single-mode --no-cpu-baseline --no-e2e > $O/b_1d_k256.json 2>&1
 $B --workload 1d_static_step --no-cpu-baseline --no-e2e > $O/b_1d_static.json 2>&1
 $B --workload 1d_dynamic --envs 4194304 --no-cpu-baseline --no-e2e > $O/b_1d_4m.json 2>&1
 $B --workload 3d_static_dense --no-cpu-baseline --no-e2e > $O/b_3d.json 2>&1
