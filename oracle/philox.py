@@ -59,8 +59,9 @@ def mulhi32(x, n: int):
 PLAN_KEY = 0x504C414E5F4B4559      # "PLAN_KEY": xor-ed into the seed for the auto-reset plan draw
 
 
-def draws(seed: int, env_ids, t: int, n_actions: int, n_plans: int = 1, ref3d: bool = False):
-    """(step_size, action, plan_idx) int64 arrays for global env ids at global step t."""
+def draws(seed: int, env_ids, t: int, n_actions: int, n_plans: int = 1, ref3d: bool = False, with_plan: bool = True):
+    """(step_size, action, plan_idx) int64 arrays for global env ids at global step t
+    (with_plan=False skips the plan block and returns plan_idx = None: static envs never consume it)."""
     env_ids = np.asarray(env_ids, dtype=np.uint64)
     t = int(t) & 0xFFFFFFFFFFFFFFFF
     tb = t >> 2
@@ -74,6 +75,8 @@ def draws(seed: int, env_ids, t: int, n_actions: int, n_plans: int = 1, ref3d: b
         action = np.where(v < 16, v >> 2, v - 12)
     else:
         action = (hi * n_actions) >> 16
+    if not with_plan:
+        return step_size, action, None
     pk = (seed ^ PLAN_KEY) & 0xFFFFFFFFFFFFFFFF
     _, _, x2, _ = philox4x32_10(env_ids & MASK, env_ids >> np.uint64(32), t & 0xFFFFFFFF, t >> 32,
                                 pk & 0xFFFFFFFF, (pk >> 32) & 0xFFFFFFFF)
