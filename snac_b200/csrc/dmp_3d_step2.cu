@@ -47,8 +47,10 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
     if (lane == 0) mbar_init(bar, 32);
     pdl_launch_dependents();
     pdl_wait();                                                       // the previous step's state is visible from here
-    // ---- round trip 1: scalar state (the draws do not depend on it and overlap its latency) ------------------
-    const uint4 ax = aux[env];
+    // ---- round trip 1: scalar state (the draws do not depend on it and overlap its latency).  16 B per env: the whole
+    // array (4 MB at 262 144 envs) is kept in L2 (evict_last), so this round trip is an L2 hit, not a DRAM access
+    const uint64_t keep = l2_policy_keep();
+    const uint4 ax = ldg_keep(aux + env, keep);
     const bool dynamic = st.dynamic != 0;
     const bool autoreset = io.flags & DMP_F_AUTORESET;
     const bool normalise = io.flags & DMP_F_NORMALISE;
@@ -215,8 +217,8 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
         }
     }
     if (live) {
-        aux[env] = make_uint4((uint32_t)e.pr | ((uint32_t)e.pc << 8) | ((uint32_t)e.plan_idx << 16),
-                              (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16), __float_as_uint(e.ret), (uint32_t)e.cross);
+        stg_keep(aux + env, make_uint4((uint32_t)e.pr | ((uint32_t)e.pc << 8) | ((uint32_t)e.plan_idx << 16),
+                                       (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16), __float_as_uint(e.ret), (uint32_t)e.cross), keep);
         if (errbits) atomicOr(st.err, errbits);
         if (st.t_dev && env == 0) st.t_dev[tslot ^ 1] = t + 1;
     }

@@ -236,7 +236,8 @@ class BatchedDMPEnv:
     def _flags(self, K: int = 1) -> int:
         # L2 evict_last hints for the state pay off when the state can actually stay resident: measured on
         # B200 (profiles/README.md) they help K>1 rollouts and shards <= ~40 MB, and cost ~4 % on a 67 MB
-        # state stepped one launch at a time (the two L2 partitions hold less than 126 MB of distinct lines).
+        # state stepped one launch at a time (the two L2 partitions hold less than 126 MB of distinct lines;
+        # fractional evict_last / evict_first policies that keep a half or a quarter of the lines were slower still).
         hint = self.l2_hints and (K > 1 or self._cells.numel() <= 40 * 1024 * 1024)
         return ((L.F_AUTORESET if self.auto_reset else 0) | (L.F_NORMALISE if self.normalise else 0)
                 | (0 if hint else L.F_NO_L2_HINT))
