@@ -11,7 +11,6 @@
 // shared memory and streamed out as one contiguous, 16 B aligned span with 128-bit stores.
 // K > 1 keeps the state on chip between steps (rollout mode).
 #include <stdlib.h>
-#include <type_traits>
 #include "dmp_common.cuh"
 
 namespace {
@@ -127,74 +126,6 @@ __device__ __forceinline__ void stage_observe2(const uint32_t* g, const Env2& e,
     obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, total_step, row[49], row[50]);
 }
 
-// Compact tile (single-step launches with f32 observations, raw counters): the warp tile holds BIASED HALFWORDS
-// (value + 1: 0 frame, 1 empty, 2 occupied; counters + 1) instead of floats and the conversion to f32 happens in the
-// copy-out.  Halving the tile takes a block from 34 KB to 22 KB of shared memory, i.e. from 6 to 8 resident blocks per
-// SM -- a single step is bound by the latency of its state loads, so residency is what it needs (profiles/README.md).
-// Counters up to 65 534 are exact (the state packing already limits them to 16 bits).
-__device__ __forceinline__ void stage_observe2_codes(const uint32_t* g, const Env2& e, uint16_t* row) {
-    const int B0 = 64 + (e.pr - 2 * D2_HW) * D2_W - D2_HW;
-    const int w0 = B0 >> 5, off = B0 & 31;
-    const uint32_t x0 = g[(w0 + 0) * B2], x1 = g[(w0 + 1) * B2], x2 = g[(w0 + 2) * B2];
-    const uint32_t x3 = g[(w0 + 3) * B2], x4 = g[(w0 + 4) * B2], x5 = g[(w0 + 5) * B2];
-    const uint32_t q0 = __funnelshift_r(x0, x1, off), q1 = __funnelshift_r(x1, x2, off);
-    const uint32_t q2 = __funnelshift_r(x2, x3, off), q3 = __funnelshift_r(x3, x4, off);
-    const uint32_t q4 = __funnelshift_r(x4, x5, off);
-    uint32_t R[7];
-    R[0] = q0;
-    R[1] = __funnelshift_r(q0, q1, 20);
-    R[2] = q1 >> 8;
-    R[3] = __funnelshift_r(q1, q2, 28);
-    R[4] = __funnelshift_r(q2, q3, 16);
-    R[5] = q3 >> 4;
-    R[6] = __funnelshift_r(q3, q4, 24);
-    const int sh = e.pc - D2_HW;
-    const uint32_t colvalid = (COLVALID >> sh) & 0x7Fu;
-    const uint64_t vcode = spread7(colvalid);
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-        const int p = e.pr - D2_HW + k;
-        const bool rowvalid = (unsigned)(p - D2_HW) < (unsigned)D2_W;
-        const uint32_t occ = (R[k] >> sh) & colvalid;
-        const uint64_t code = rowvalid ? spread7(occ) + vcode : 0ull;
-        const uint32_t lo = (uint32_t)code, hi = (uint32_t)(code >> 32);
-        uint16_t* o = row + k * 7;
-        o[0] = (uint16_t)(lo & 0xFFu);
-        o[1] = (uint16_t)((lo >> 8) & 0xFFu);
-        o[2] = (uint16_t)((lo >> 16) & 0xFFu);
-        o[3] = (uint16_t)(lo >> 24);
-        o[4] = (uint16_t)(hi & 0xFFu);
-        o[5] = (uint16_t)((hi >> 8) & 0xFFu);
-        o[6] = (uint16_t)((hi >> 16) & 0xFFu);
-    }
-    row[49] = (uint16_t)(e.cb + 1);
-    row[50] = (uint16_t)(e.cs + 1);
-}
-
-// two biased halfwords -> two floats: the halfword goes into the mantissa of 2^23 (PRMT), minus 2^23 + 1 (FADD)
-__device__ __forceinline__ float cvt_biased_lo(uint32_t u) { return __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7610u)) - 8388609.0f; }
-__device__ __forceinline__ float cvt_biased_hi(uint32_t u) { return __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7632u)) - 8388609.0f; }
-
-// copy-out of a compact tile: 4 halfwords in (LDS.64), 4 floats out (STG.128, streaming)
-__device__ __forceinline__ void warp_tile_store_cvt(float* __restrict__ dst, const uint16_t* tile, int n_elems, int lane) {
-    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && n_elems == 32 * D2_OBS) {
-        constexpr int NG = 32 * D2_OBS / 4;                              // 408 groups
-        const uint2* s2 = reinterpret_cast<const uint2*>(tile);
-        float4* d4 = reinterpret_cast<float4*>(dst);
-        uint2 u[(NG + 31) / 32];
-#pragma unroll
-        for (int i = 0; i < (NG + 31) / 32; ++i)
-            if (i * 32 + 31 < NG || i * 32 + lane < NG) u[i] = s2[i * 32 + lane];
-#pragma unroll
-        for (int i = 0; i < (NG + 31) / 32; ++i)
-            if (i * 32 + 31 < NG || i * 32 + lane < NG)
-                __stcs(d4 + i * 32 + lane, make_float4(cvt_biased_lo(u[i].x), cvt_biased_hi(u[i].x),
-                                                       cvt_biased_lo(u[i].y), cvt_biased_hi(u[i].y)));
-    } else {
-        for (int i = lane; i < n_elems; i += 32) dst[i] = (float)((int)tile[i] - 1);
-    }
-}
-
 // stage (d) helper: IoU = |G & P| / |G | P| over the interior (render :169-175) with warp-free popc.
 __device__ __forceinline__ double iou2(const uint32_t* g, const uint32_t* __restrict__ plan) {
     int inter = 0, uni = 0;
@@ -207,20 +138,20 @@ __device__ __forceinline__ double iou2(const uint32_t* g, const uint32_t* __rest
     return __ddiv_rn((double)inter, (double)uni);
 }
 
-template <typename ObsT, bool COMPACT>
-__global__ void __launch_bounds__(B2, COMPACT ? 8 : 7) k2d_rollout(const DmpState st, const DmpIO io, const int K) {
-    static_assert(!COMPACT || sizeof(ObsT) == 4, "the compact tile is the f32 path");
-    using TileT = typename std::conditional<COMPACT, uint16_t, ObsT>::type;
+// TMA = true: the warp tile leaves through one bulk async copy (dmp_common.cuh: warp_tile_bulk_store) instead of 13 x
+// (LDS.128 + STG.128) per lane -- used for single steps, where the L1 data pipe was the busiest unit (ncu: 69 %).
+template <typename ObsT, bool TMA>
+__global__ void __launch_bounds__(B2, TMA ? 6 : 7) k2d_rollout(const DmpState st, const DmpIO io, const int K) {
     extern __shared__ uint4 smem_raw[];
     uint32_t* G = reinterpret_cast<uint32_t*>(smem_raw);                 // [S2_WORDS][B2]
-    TileT* tiles = reinterpret_cast<TileT*>(G + S2_WORDS * B2);          // [B2/32][32*51]
+    ObsT* tiles = reinterpret_cast<ObsT*>(G + S2_WORDS * B2);            // [B2/32][32*51]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t n = st.n_envs;
     const int64_t env = (int64_t)blockIdx.x * B2 + tid;
     const int64_t env0 = env - lane;                                     // first env of this warp
     const int nvalid = (int)min((int64_t)32, n - env0);                  // <= 0: idle warp
     const bool live = env < n;
-    TileT* tile = tiles + warp * (32 * D2_OBS);
+    ObsT* tile = tiles + warp * (32 * D2_OBS);
     uint32_t* g = G + tid;
 
     uint4* cells = reinterpret_cast<uint4*>(st.cells);
@@ -299,10 +230,15 @@ __global__ void __launch_bounds__(B2, COMPACT ? 8 : 7) k2d_rollout(const DmpStat
         // ---- (c) observation ------------------------------------------------------------------
         if (io.obs) {
             ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * D2_OBS;
-            if constexpr (COMPACT) {
-                stage_observe2_codes(g, e, tile + lane * D2_OBS);
-                __syncwarp();
-                if (nvalid > 0) warp_tile_store_cvt(dst, tile, nvalid * D2_OBS, lane);
+            if constexpr (TMA) {
+                if (k > 0) warp_tile_bulk_wait(lane);               // the previous step's copy has drained the tile
+                stage_observe2<ObsT>(g, e, tile + lane * D2_OBS, normalise, total_brick, st.total_step);
+                if (nvalid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                    warp_tile_bulk_store(dst, tile, 32 * D2_OBS * sizeof(ObsT), lane);
+                } else {
+                    __syncwarp();
+                    if (nvalid > 0) warp_tile_store<ObsT>(dst, tile, nvalid * D2_OBS, lane);
+                }
             } else {
                 stage_observe2<ObsT>(g, e, tile + lane * D2_OBS, normalise, total_brick, st.total_step);
                 __syncwarp();
@@ -357,6 +293,7 @@ __global__ void __launch_bounds__(B2, COMPACT ? 8 : 7) k2d_rollout(const DmpStat
         if (errbits) atomicOr(st.err, errbits);
     }
     if (st.t_dev && blockIdx.x == 0 && tid == 0) st.t_dev[tslot ^ 1] = t0 + (uint64_t)K;
+    if constexpr (TMA) warp_tile_bulk_wait(lane);                        // the tile must outlive the copy that reads it
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -464,30 +401,25 @@ __global__ void k2d_import(const DmpState st, const int32_t* __restrict__ grid, 
     if (ret) wref(15) = __float_as_uint(ret[env]);
 }
 
-template <typename ObsT, bool COMPACT>
+template <typename ObsT, bool TMA>
 int launch_rollout2_t(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
-    const size_t smem = (size_t)S2_WORDS * B2 * 4 + (size_t)(B2 / 32) * 32 * D2_OBS * (COMPACT ? 2 : sizeof(ObsT));
+    const size_t smem = (size_t)S2_WORDS * B2 * 4 + (size_t)(B2 / 32) * 32 * D2_OBS * sizeof(ObsT);
     static bool attr_done = false;           // per instantiation
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k2d_rollout<ObsT, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k2d_rollout<ObsT, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return dmp_set_error(e);
-        if (COMPACT) {
-            e = cudaFuncSetAttribute(k2d_rollout<ObsT, COMPACT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            if (e != cudaSuccess) return dmp_set_error(e);
-        }
         attr_done = true;
     }
     const unsigned blocks = (unsigned)((st.n_envs + B2 - 1) / B2);
-    return dmp_set_error(dmp_launch_pdl(k2d_rollout<ObsT, COMPACT>, blocks, (unsigned)B2, smem, s, st, io, K));
+    return dmp_set_error(dmp_launch_pdl(k2d_rollout<ObsT, TMA>, blocks, (unsigned)B2, smem, s, st, io, K));
 }
 
 template <typename ObsT>
 int launch_rollout2(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
-    if constexpr (sizeof(ObsT) == 4) {
-        // single steps with raw counters: compact (halfword) tile, 8 resident blocks per SM.  DMP_2D_TILE=f keeps floats.
-        const char* v = getenv("DMP_2D_TILE");
-        if (K == 1 && !(io.flags & DMP_F_NORMALISE) && !(v && v[0] == 'f')) return launch_rollout2_t<ObsT, true>(st, io, K, s);
-    }
+    // DMP_2D_TILE (tuning switch): f = load/store copy-out, t = bulk (TMA) copy-out.  Default: bulk for single steps.
+    const char* v = getenv("DMP_2D_TILE");
+    const int mode = v ? (int)v[0] : (K == 1 ? 't' : 'f');
+    if (mode == 't') return launch_rollout2_t<ObsT, true>(st, io, K, s);
     return launch_rollout2_t<ObsT, false>(st, io, K, s);
 }
 

@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
     }
 
     // ---- (c) observation: window -> registers, then the warp's [32][51] tile over the drained slots ----------
+    bool bulk_pending = false;
     if (io.obs) {
         uint32_t u[7][4];
         window_regs(g, e, u);
@@ -168,10 +169,14 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
             emit_pair<ObsT>(u[k][3], row[k * 7 + 6], dummy);
         }
         obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, st.total_step, row[49], row[50]);
-        __syncwarp();
         ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + env0 * D3_OBS;
-        if (nvalid == 32) warp_tile_store_full<ObsT, 32 * D3_OBS>(dst, tile, lane);
-        else warp_tile_store<ObsT>(dst, tile, nvalid * D3_OBS, lane);
+        if (nvalid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            warp_tile_bulk_store(dst, tile, 32 * D3_OBS * sizeof(ObsT), lane);          // one bulk async copy per warp
+            bulk_pending = true;
+        } else {
+            __syncwarp();
+            warp_tile_store<ObsT>(dst, tile, nvalid * D3_OBS, lane);
+        }
     }
 
     // ---- (d) reward (reward_check :232-239) -----------------------------------------------------
@@ -222,6 +227,7 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
         if (errbits) atomicOr(st.err, errbits);
         if (st.t_dev && env == 0) st.t_dev[tslot ^ 1] = t + 1;
     }
+    if (bulk_pending) warp_tile_bulk_wait(lane);                        // the tile must outlive the copy that reads it
 }
 
 template <typename ObsT>

@@ -144,6 +144,30 @@ __device__ __forceinline__ void warp_tile_store_full(T* __restrict__ dst, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Bulk (TMA) copy-out of a warp tile: ONE cp.async.bulk shared -> global instead of N16/32 x (LDS.128 + STG.128) per
+// lane.  The copy engine reads the tile itself, so the 2 x 4 wavefronts per 512 B that the load/store path spends in
+// the L1 data pipe disappear -- that pipe, not HBM, was the busiest unit of the single-step kernels (ncu: 69 %).
+// Protocol: every lane orders its own tile writes before the async proxy (fence.proxy.async), the warp converges, one
+// lane issues the copy and commits it; `warp_tile_bulk_wait` must be called before the tile is written again or the
+// block exits.  `dst` and `tile` must be 16 B aligned and `bytes` a multiple of 16.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_tile_bulk_store(void* dst, const void* tile, uint32_t bytes, int lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        uint64_t pol;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));      // write-once stream
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                     ::"l"(dst), "r"((uint32_t)__cvta_generic_to_shared(tile)), "r"(bytes), "l"(pol) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+}
+__device__ __forceinline__ void warp_tile_bulk_wait(int lane) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
 // L2 residency hints.  Env state is re-read every step while observations are written once and never
 // read back by these kernels: state accesses carry an evict_last policy, observation stores are
 // streaming (__stcs), so that on B200's 126 MB L2 the state of ~10^6 2D envs (67 MB) stays on chip and

@@ -384,16 +384,16 @@ def test_3d_tall_columns_match_oracle(kind, dynamic):
 
 
 # ------------------------------------------------------------------------------------------------
-# 8. 2D single steps with f32 observations go through the compact (halfword) tile: equal to the oracle, to the float
-#    tile (DMP_2D_TILE=f) and independent of the alignment of the caller's observation buffer
+# 8. 2D single steps leave through a bulk (TMA) copy of the warp tile: equal to the oracle, to the load/store copy-out
+#    (DMP_2D_TILE=f) and independent of the alignment of the caller's observation buffer
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dynamic", [False, True])
-def test_2d_compact_tile_step_mode(dynamic):
+def test_2d_bulk_copy_out_step_mode(dynamic):
     plans = load_plans(2, "sparse", "train") if dynamic else None
     n, K = 1000 + 13, 90                                      # ragged last warp
     ob = OracleBatch(2, dynamic, n, 0, plans)
     envs = {}
-    for kind in ("compact", "float", "unaligned"):
+    for kind in ("float", "unaligned", "tma"):
         envs[kind] = make_gpu(2, dynamic, n, 0, plans, auto_reset=True, env_base=3, seed=SEED, obs_dtype=torch.float32,
                               total_step=35)
     for e in ob.envs:
@@ -406,18 +406,20 @@ def test_2d_compact_tile_step_mode(dynamic):
     raw = torch.zeros(n * 51 + 1, dtype=torch.float32, device="cuda")
     odd = raw[1:].view(1, n, 51)                              # 4 B aligned only
     for k in range(K):
-        o1, r1, d1 = envs["compact"].step(None)
-        old = os.environ.get("DMP_2D_TILE")
-        os.environ["DMP_2D_TILE"] = "f"
-        try:
-            o2, r2, d2 = envs["float"].step(None)
-        finally:
-            if old is None:
-                del os.environ["DMP_2D_TILE"]
-            else:
-                os.environ["DMP_2D_TILE"] = old
+        def with_tile(mode, fn):
+            old = os.environ.get("DMP_2D_TILE")
+            os.environ["DMP_2D_TILE"] = mode
+            try:
+                return fn()
+            finally:
+                if old is None:
+                    del os.environ["DMP_2D_TILE"]
+                else:
+                    os.environ["DMP_2D_TILE"] = old
+        o1, r1, d1 = with_tile("t", lambda: envs["tma"].step(None))
+        o2, r2, d2 = with_tile("f", lambda: envs["float"].step(None))
         e3 = envs["unaligned"]
-        o3, r3, d3 = e3.rollout(1, out=(odd, e3._reward[None], e3._done[None]))
+        o3, r3, d3 = e3.rollout(1, out=(odd, e3._reward[None], e3._done[None]))           # default mode, 4 B aligned buffer
         assert np.array_equal(o1.cpu().numpy().astype(np.float64), r_obs[k]), k
         assert torch.equal(o1, o2) and torch.equal(o1, o3[0]), k
         assert np.array_equal(r1.cpu().numpy(), r_rew[k]) and np.array_equal(d1.cpu().numpy(), r_done[k])
