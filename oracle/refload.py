@@ -88,6 +88,10 @@ _MODULES = {
     # classes that carry the random plan generators
     ("1D", "hindsight_dynamic"): ("1D", "DMP_Env_1D_dynamic_hindsight_replay", "deep_mobile_printing_1d1r_hindsight"),
     ("2D", "hindsight_dynamic"): ("2D", "DMP_Env_2D_dynamic_hindsight_replay_usedata", "deep_mobile_printing_2d1r_hindsight"),
+    ("3D", "hindsight_dynamic"): ("3D", "DMP_simulator_3d_dynamic_triangle_hindsight_replay", "deep_mobile_printing_3d1r_hindsight"),
+    ("1D", "hindsight_static"): ("1D", "DMP_Env_1D_static_hindsight_replay", "deep_mobile_printing_1d1r_hindsight"),
+    ("2D", "hindsight_static"): ("2D", "DMP_Env_2D_static_hindsight_replay", "deep_mobile_printing_2d1r_hindsight"),
+    ("3D", "hindsight_static"): ("3D", "DMP_simulator_3d_static_circle_hindsight_replay", "deep_mobile_printing_3d1r_hindsight"),
 }
 
 

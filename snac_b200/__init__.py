@@ -9,11 +9,17 @@ from .compat import (HostStepper, VectorizedEnvWrapper, deep_mobile_printing_1d1
                      deep_mobile_printing_1d1r_dynamic, deep_mobile_printing_2d1r,
                      deep_mobile_printing_2d1r_dynamic, deep_mobile_printing_3d1r,
                      deep_mobile_printing_3d1r_dynamic, deep_mobile_printing_1d1r_Lnet,
-                     deep_mobile_printing_2d1r_Lnet, deep_mobile_printing_3d1r_Lnet)
+                     deep_mobile_printing_2d1r_Lnet, deep_mobile_printing_3d1r_Lnet,
+                     deep_mobile_printing_1d1r_hindsight, deep_mobile_printing_2d1r_hindsight,
+                     deep_mobile_printing_3d1r_hindsight, deep_mobile_printing_1d1r_hindsight_static,
+                     deep_mobile_printing_2d1r_hindsight_static, deep_mobile_printing_3d1r_hindsight_static)
 
 __all__ = ["BatchedDMPEnv", "load_plan_dataset", "generate_plans", "DeviceRollout", "EpsilonGreedy", "QSAAdapter",
            "RandomPolicy", "HostStepper", "VectorizedEnvWrapper",
            "deep_mobile_printing_1d1r", "deep_mobile_printing_1d1r_dynamic",
            "deep_mobile_printing_2d1r", "deep_mobile_printing_2d1r_dynamic",
            "deep_mobile_printing_3d1r", "deep_mobile_printing_3d1r_dynamic",
-           "deep_mobile_printing_1d1r_Lnet", "deep_mobile_printing_2d1r_Lnet", "deep_mobile_printing_3d1r_Lnet"]
+           "deep_mobile_printing_1d1r_Lnet", "deep_mobile_printing_2d1r_Lnet", "deep_mobile_printing_3d1r_Lnet",
+           "deep_mobile_printing_1d1r_hindsight", "deep_mobile_printing_2d1r_hindsight",
+           "deep_mobile_printing_3d1r_hindsight", "deep_mobile_printing_1d1r_hindsight_static",
+           "deep_mobile_printing_2d1r_hindsight_static", "deep_mobile_printing_3d1r_hindsight_static"]

@@ -24,7 +24,10 @@ from typing import Optional
 import numpy as np
 import torch
 
-from .vecenv import BatchedDMPEnv, load_plan_dataset
+import ctypes as C
+
+from . import _lib as L
+from .vecenv import BatchedDMPEnv, generate_plans, load_plan_dataset
 
 
 class HostStepper:
@@ -89,6 +92,8 @@ class _ScalarDMP:
         self._device = device
         self._plans_arg = None if not self._dynamic else np.asarray(self.plan_dataset)
         self._env: Optional[BatchedDMPEnv] = None
+        self._plan_cache = None            # content of self.plan as the device last saw it (hindsight overwrites)
+        self._plan_row = 0
         self.step_size = 1
         self.count_step = 0
         self.total_brick = 0
@@ -100,6 +105,7 @@ class _ScalarDMP:
         self.observation = None
         self.brick_memory = None
         self._set_count_brick(None)
+        self._dataset_idx = None
         # constants (reference __init__ blocks)
         probe = {1: (30, 20, 2, 3, 7, 750, 750), 2: (20, 20, 3, 5, 51, 600, 600), 3: (20, 20, 3, 8, 51, 1300, 1000)}[self._dim]
         self.plan_width, self.plan_height, self.HALF_WINDOW_SIZE, self.action_dim, self.state_dim = probe[:5]
@@ -126,6 +132,46 @@ class _ScalarDMP:
                                       obs_dtype=torch.float64, random_choose_paln=self.random_choose_paln,
                                       dynamic_rules=True if (self._lnet and self._dim == 3) else None)
             self._dense_plans = self._env.plans_dense()
+            # one spare plan row: a plan written by the caller (hindsight relabelling) is packed there
+            tab, tot = self._env.plan_table().clone(), self._env.plan_totals().clone()
+            self._env._install_plans(torch.cat([tab, torch.zeros_like(tab[:1])]), torch.cat([tot, tot[:1]]))
+            self._scratch_row = self._env.n_plans - 1
+
+    # ---- hindsight relabelling: the reference's learners overwrite ``env.plan`` between reset() and step(), by
+    # assignment (script/DRQN_hindsight/1d/DRQN_hindsight_1D_dynamic.py:255) or in place
+    # (script/DRQN_hindsight/2d/DRQN_hindsight_2D_dynamic.py:274-276).  Both are noticed at the next step().
+    def _pack_plan_row(self, plan, row, budget=None):
+        env = self._env
+        shape = (1, 30) if self._dim == 1 else (1, 26, 26)
+        raw = torch.as_tensor(np.ascontiguousarray(np.asarray(plan, dtype=np.float64).reshape(shape)), device=env.device)
+        rb = env._lay.plan_row_bytes
+        tot = torch.zeros(1, dtype=torch.int32, device=env.device)
+        with torch.cuda.device(env.device):
+            L.check(L.lib.dmp_plans_pack(self._dim, raw.data_ptr(), 1, env._plans.data_ptr() + row * rb, tot.data_ptr(),
+                                         env._stream()), "dmp_plans_pack")
+        env._plan_total[row] = tot[0] if budget is None else int(np.ceil(budget))
+
+    def _point_env_at_row(self, row):
+        sc = self._env.export_state()["scalars"]
+        sc[0, 4] = row
+        self._env.import_state(scalars=sc)
+        self._plan_row = row
+
+    def _sync_plan(self):
+        if self.plan is None or self._plan_cache is None:
+            return
+        cur = np.asarray(self.plan, dtype=np.float64)
+        if cur.shape == self._plan_cache.shape and np.array_equal(cur, self._plan_cache):
+            return
+        if cur.shape != self._plan_cache.shape:
+            raise ValueError("plan must keep its shape %s" % (self._plan_cache.shape,))
+        # the episode goes on against the new plan with the budget reset() fixed (the reference does not recompute it)
+        self._pack_plan_row(cur, self._scratch_row, budget=self.total_brick)
+        self._point_env_at_row(self._scratch_row)
+        if self._dynamic and self._dataset_idx is not None and np.shares_memory(self.plan, self._dense_plans[self._dataset_idx]):
+            # in-place edit of a dataset entry: it persists in the reference's plan_dataset, so it persists here
+            self._pack_plan_row(cur, self._dataset_idx)
+        self._plan_cache = cur.copy()
 
     def _sync_attrs(self):
         st = self._env.export_state()
@@ -138,8 +184,8 @@ class _ScalarDMP:
         pos = int(sc[0]) if self._dim == 1 else [int(sc[0]), int(sc[1])]
         return pos
 
-    def reset(self):
-        self._ensure()
+    def _choose_plan(self) -> int:
+        """Plan-table row for the next episode, consuming the global numpy RNG exactly like the reference's reset()."""
         idx = 0
         if self._dynamic:
             if self.random_choose_paln:                      # e.g. Env/2D/DMP_Env_2D_dynamic_usedata_plan.py:35-38
@@ -150,8 +196,16 @@ class _ScalarDMP:
                 self.index_for_non_random += 1
                 if self.index_for_non_random == self.plan_dataset_len:
                     self.index_for_non_random = 0
+        return idx
+
+    def reset(self):
+        self._ensure()
+        idx = self._choose_plan()
+        self._dataset_idx = idx if self._dynamic else None
+        self._plan_row = idx
         obs = self._env.reset(plan_idx=[idx]).cpu().numpy().reshape(1, -1)
-        self.plan = self._dense_plans[idx]
+        # dataset classes alias the dataset entry (as the reference does); static ones get a fresh array per reset()
+        self.plan = self._dense_plans[idx] if self._dynamic else self._dense_plans[idx].copy()
         tb = float(self._env.plan_totals()[idx].item())
         self.total_brick = tb
         if self._dim != 1:
@@ -159,6 +213,7 @@ class _ScalarDMP:
             self.input_plan = self.plan[h:h + self.plan_height, h:h + self.plan_width]
         if self._dim == 1 and not self._dynamic:
             self.one_hot = None
+        self._plan_cache = np.asarray(self.plan, dtype=np.float64).copy()
         pos = self._sync_attrs()
         self.position_memory = [pos]
         self.brick_memory = [[-1, -1]] if self._dim == 1 else None
@@ -170,6 +225,7 @@ class _ScalarDMP:
         if self._env is None or self.position_memory is None:
             raise AttributeError("call reset() before step()")
         a = int(action)
+        self._sync_plan()
         self.step_size = int(np.random.randint(1, 4)) if step_size is None else int(step_size)
         if self._dim != 3 and not (0 <= a < self.action_dim):
             # the reference increments count_step, draws, then fails on the unbound 'position'
@@ -288,6 +344,102 @@ class deep_mobile_printing_3d1r_Lnet(deep_mobile_printing_3d1r):
     """Env/3D/DMP_simulator_3d_static_circle_Lnet.py: static plan, the dynamic class's termination rules
     (-100 when boxed in), normalised counters, returns [obs, position]."""
     _lnet = True
+
+
+# --------------------------------------------------------------------------------------------------
+# *_hindsight_replay classes (explicit step_size; SURVEY.md 8(f) row 3).  The reference gives all six the same class
+# name per dimension and tells them apart by module; here the dataset / generator ones keep the reference name and the
+# static ones get a ``_static`` suffix.
+# --------------------------------------------------------------------------------------------------
+class deep_mobile_printing_1d1r_hindsight(_ScalarDMP):
+    """Env/1D/DMP_Env_1D_dynamic_hindsight_replay.py: a fresh random sinusoid from ``create_plan()`` at every reset()
+    (generated on the device from the reference's three numpy draws); observations are ``[raw (1,7), plan (30,)]``."""
+    _dim, _dynamic = 1, True
+
+    def __init__(self, device="cuda"):
+        self._setup(device=device, plans=np.full((1, 30), 20.0), random_choose_paln=False)
+
+    def create_plan(self):
+        k_1 = np.random.uniform(3, 12)                       # :32-34, same draws in the same order
+        k_2 = np.random.randint(1, 4)
+        phase = np.random.uniform(-1, 1) * np.pi
+        self.one_hot = [k_1, k_2, phase]
+        table, _, _ = generate_plans(1, 1, draws=np.array([[k_1, k_2, phase]]), device=self._device)
+        y = table[0, :30].cpu().numpy().astype(np.float64)
+        return y, sum(y)
+
+    def _choose_plan(self) -> int:
+        self.one_hot = None
+        y, _ = self.create_plan()
+        self._dense_plans[0] = y
+        self._pack_plan_row(y, 0)
+        return 0
+
+    def _format_obs(self, obs, pos, reset):
+        return [obs, self.plan]                              # :69-70, :96-109
+
+
+class deep_mobile_printing_2d1r_hindsight(_ScalarDMP):
+    """Env/2D/DMP_Env_2D_dynamic_hindsight_replay_usedata.py: dataset plans like the ``usedata_plan`` class, but reset()
+    first runs ``create_plan()`` (a random triangle that is then discarded -- it still consumes the numpy RNG) and
+    observations carry the raw counters: ``[raw (1,51), input_plan, position]``."""
+    _dim, _dynamic = 2, True
+
+    def __init__(self, data_path=None, random_choose_paln=True, device="cuda", plans=None, plan_choose=None):
+        self._setup(data_path=data_path, random_choose_paln=random_choose_paln, device=device, plans=plans)
+        if plan_choose is not None:                          # the reference infers it from the file name (:31-32)
+            self.plan_choose = plan_choose
+        elif data_path is not None and "sparse" in data_path:
+            self.plan_choose = 1
+
+    def create_plan(self):
+        if self.plan_choose not in (0, 1):
+            raise ValueError(' 0: Dense triangle, 1: Sparse triangle')
+        while True:                                          # :41-57: redraw until the area exceeds 50 / 20
+            x = np.random.randint(0, self.plan_width, size=3)
+            y = np.random.randint(0, self.plan_height, size=3)
+            try:
+                table, _, _ = generate_plans(2, 1, self.plan_choose, draws=np.concatenate([x, y])[None, None, :],
+                                             device=self._device)
+            except ValueError:
+                continue
+            bits = np.unpackbits(table[0, :52].cpu().numpy(), bitorder="little")[:400].reshape(20, 20)
+            plan = np.zeros((26, 26))
+            plan[3:23, 3:23] = bits
+            return plan, sum(sum(plan))
+
+    def _choose_plan(self) -> int:
+        self.create_plan()
+        return _ScalarDMP._choose_plan(self)
+
+    def _format_obs(self, obs, pos, reset):
+        return [obs, self.input_plan, pos]
+
+
+class deep_mobile_printing_3d1r_hindsight(_ScalarDMP):
+    """Env/3D/DMP_simulator_3d_dynamic_triangle_hindsight_replay.py: the dataset class with an explicit step size;
+    reset() returns ``[obs, input_plan]`` (no position, :70-72)."""
+    _dim, _dynamic = 3, True
+
+    def __init__(self, data_path=None, random_choose_paln=True, device="cuda", plans=None):
+        self._setup(data_path=data_path, random_choose_paln=random_choose_paln, device=device, plans=plans)
+
+    def _format_obs(self, obs, pos, reset):
+        if reset:
+            return [obs, self.input_plan]
+        return [self._normalised(obs), self.input_plan, pos]
+
+
+class deep_mobile_printing_1d1r_hindsight_static(deep_mobile_printing_1d1r):
+    """Env/1D/DMP_Env_1D_static_hindsight_replay.py: the static class with ``step(action, step_size)``."""
+
+
+class deep_mobile_printing_2d1r_hindsight_static(deep_mobile_printing_2d1r):
+    """Env/2D/DMP_Env_2D_static_hindsight_replay.py."""
+
+
+class deep_mobile_printing_3d1r_hindsight_static(deep_mobile_printing_3d1r):
+    """Env/3D/DMP_simulator_3d_static_circle_hindsight_replay.py."""
 
 
 # --------------------------------------------------------------------------------------------------
