@@ -5,7 +5,7 @@ include/dmp.h) and fails loudly if it is missing: there is no CPU fallback."""
 from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is absent)
 from .vecenv import BatchedDMPEnv, generate_plans, load_plan_dataset  # noqa: F401
 from .policy_loop import DeviceRollout, EpsilonGreedy, QSAAdapter, RandomPolicy  # noqa: F401
-from .compat import (HostStepper, VectorizedEnvWrapper, deep_mobile_printing_1d1r,  # noqa: F401
+from .compat import (FlatObsEnv, HostStepper, VectorizedEnvWrapper, deep_mobile_printing_1d1r,  # noqa: F401
                      deep_mobile_printing_1d1r_dynamic, deep_mobile_printing_2d1r,
                      deep_mobile_printing_2d1r_dynamic, deep_mobile_printing_3d1r,
                      deep_mobile_printing_3d1r_dynamic, deep_mobile_printing_1d1r_Lnet,
@@ -14,7 +14,7 @@ from .compat import (HostStepper, VectorizedEnvWrapper, deep_mobile_printing_1d1
                      deep_mobile_printing_3d1r_hindsight, deep_mobile_printing_1d1r_hindsight_static,
                      deep_mobile_printing_2d1r_hindsight_static, deep_mobile_printing_3d1r_hindsight_static)
 
-__all__ = ["BatchedDMPEnv", "load_plan_dataset", "generate_plans", "DeviceRollout", "EpsilonGreedy", "QSAAdapter",
+__all__ = ["FlatObsEnv", "BatchedDMPEnv", "load_plan_dataset", "generate_plans", "DeviceRollout", "EpsilonGreedy", "QSAAdapter",
            "RandomPolicy", "HostStepper", "VectorizedEnvWrapper",
            "deep_mobile_printing_1d1r", "deep_mobile_printing_1d1r_dynamic",
            "deep_mobile_printing_2d1r", "deep_mobile_printing_2d1r_dynamic",

@@ -443,6 +443,56 @@ class deep_mobile_printing_3d1r_hindsight_static(deep_mobile_printing_3d1r):
 
 
 # --------------------------------------------------------------------------------------------------
+# learner-side copies of the envs (script/SAC/environments/*.py, script/PPO/*/DMP_*.py): the same simulators with a
+# flat (D,) observation, and -- for the stable-baselines PPO scripts -- gym spaces and a 4-tuple step()
+# --------------------------------------------------------------------------------------------------
+class _Space:
+    """Minimal stand-in for gym.spaces.{Discrete,Box} (gym is not a dependency of this package)."""
+
+    def __init__(self, n=None, low=None, high=None, dtype=np.int64):
+        self.n, self.low, self.high, self.dtype = n, low, high, dtype
+        self.shape = () if low is None else np.asarray(low).shape
+
+    def sample(self):
+        if self.n is not None:
+            return int(np.random.randint(self.n))
+        return np.random.uniform(self.low, self.high).astype(self.dtype)
+
+    def contains(self, x):
+        if self.n is not None:
+            return 0 <= int(x) < self.n
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+
+class FlatObsEnv:
+    """``FlatObsEnv(env)``: reset() -> (D,) ; step(a) -> ((D,), reward, done) like script/SAC/environments/DMP_Env_1D_static.py:72-118;
+    ``FlatObsEnv(env, gym_api=True)``: step(a) -> ((D,), reward, done, {}) plus ``action_space`` / ``observation_space``
+    like script/PPO/2d_static/DMP_Env_2D_static.py:32-34, :144-161.  Everything else is forwarded to the wrapped env."""
+
+    def __init__(self, env: _ScalarDMP, gym_api: bool = False):
+        self.env, self.gym_api = env, bool(gym_api)
+        win = env.state_dim - 2
+        self.action_space = _Space(n=env.action_dim)
+        self.observation_space = _Space(low=np.array([-1] * win + [0, 0]),
+                                        high=np.array([99] * win + [env.total_step, env.total_step]))
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    @staticmethod
+    def _flat(o):
+        return np.asarray(o[0] if isinstance(o, list) else o).reshape(-1)
+
+    def reset(self):
+        return self._flat(self.env.reset())
+
+    def step(self, action, step_size=None):
+        o, r, d = self.env.step(action, step_size)
+        return (self._flat(o), r, d, {}) if self.gym_api else (self._flat(o), r, d)
+
+
+# --------------------------------------------------------------------------------------------------
 # multiprocess.py replacement
 # --------------------------------------------------------------------------------------------------
 class VectorizedEnvWrapper:

@@ -153,3 +153,24 @@ def test_lnet_observation_variants_replay_reference(name):
             ri += 1
             assert np.array_equal(flat(env.reset()), z["reset_obs"][ri])
     assert np.array_equal(env.environment_memory.astype(np.int16).reshape(z["final_grid"].shape), z["final_grid"])
+
+
+def test_flat_observation_wrappers_like_the_sac_and_ppo_env_copies():
+    """script/SAC/environments/*.py return (D,) observations; script/PPO/*/DMP_*.py add gym spaces and a 4-tuple."""
+    import snac_b200 as S
+    for cls, D, A in ((S.deep_mobile_printing_1d1r, 7, 3), (S.deep_mobile_printing_2d1r, 51, 5), (S.deep_mobile_printing_3d1r, 51, 8)):
+        np.random.seed(5)
+        base = cls(plan_choose=0)
+        want = [base.reset()] + [base.step(a % A)[0] for a in range(12)]
+        np.random.seed(5)
+        sac, ppo = S.FlatObsEnv(cls(plan_choose=0)), S.FlatObsEnv(cls(plan_choose=0), gym_api=True)
+        o = sac.reset()
+        assert o.shape == (D,) and np.array_equal(o, want[0][0])
+        for a in range(12):
+            o, r, d = sac.step(a % A)
+            assert o.shape == (D,) and np.array_equal(o, want[a + 1][0])
+        assert ppo.reset().shape == (D,)
+        o, r, d, info = ppo.step(0)
+        assert o.shape == (D,) and info == {} and isinstance(d, bool)
+        assert ppo.action_space.n == A and ppo.observation_space.shape == (D,) and ppo.observation_space.contains(o)
+        assert ppo.total_step == base.total_step and ppo.HALF_WINDOW_SIZE == base.HALF_WINDOW_SIZE
