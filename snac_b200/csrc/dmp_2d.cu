@@ -139,7 +139,7 @@ __device__ __forceinline__ double iou2(const uint32_t* g, const uint32_t* __rest
 }
 
 // TMA = true: the warp tile leaves through one bulk async copy (dmp_common.cuh: warp_tile_bulk_store) instead of 13 x
-// (LDS.128 + STG.128) per lane -- used for single steps, where the L1 data pipe was the busiest unit (ncu: 69 %).
+// (LDS.128 + STG.128) per lane: the L1 data pipe was the busiest unit of this kernel (ncu: 69 %).
 template <typename ObsT, bool TMA>
 __global__ void __launch_bounds__(B2, TMA ? 6 : 7) k2d_rollout(const DmpState st, const DmpIO io, const int K) {
     extern __shared__ uint4 smem_raw[];
@@ -416,11 +416,10 @@ int launch_rollout2_t(const DmpState& st, const DmpIO& io, int K, cudaStream_t s
 
 template <typename ObsT>
 int launch_rollout2(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
-    // DMP_2D_TILE (tuning switch): f = load/store copy-out, t = bulk (TMA) copy-out.  Default: bulk for single steps.
-    const char* v = getenv("DMP_2D_TILE");
-    const int mode = v ? (int)v[0] : (K == 1 ? 't' : 'f');
-    if (mode == 't') return launch_rollout2_t<ObsT, true>(st, io, K, s);
-    return launch_rollout2_t<ObsT, false>(st, io, K, s);
+    // DMP_TILE_COPY (tuning switch): l = load/store copy-out of the observation tile, b = bulk async copy (default)
+    const char* v = getenv("DMP_TILE_COPY");
+    if (v && v[0] == 'l') return launch_rollout2_t<ObsT, false>(st, io, K, s);
+    return launch_rollout2_t<ObsT, true>(st, io, K, s);
 }
 
 }  // namespace

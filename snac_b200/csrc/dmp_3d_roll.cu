@@ -114,7 +114,8 @@ __device__ __forceinline__ void observe_cache(const uint8_t* gb, int pr, int pc,
 template <typename ObsT>
 __host__ __device__ constexpr size_t warp_smem_bytes() { return (size_t)WARP_MAP_B + 32 * D3_OBS * sizeof(ObsT) + 4; }
 
-template <typename ObsT>
+// TMA = true: each step's warp tile leaves through one bulk async copy (dmp_common.cuh: warp_tile_bulk_store).
+template <typename ObsT, bool TMA>
 __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, const DmpIO io, const int K) {
     extern __shared__ uint4 smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
     int64_t idx = env0 + lane;                                        // flat [k][env] index of this step's outputs
 
     StepDraws draws;
+    bool bulk_pending = false;
     for (int k = 0; k < K; ++k, idx += n) {
         const uint64_t t = t0 + (uint64_t)k;
         uint32_t dw = 0;
@@ -273,15 +275,21 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
 
         // ---- (c) observation --------------------------------------------------------------------
         if (io.obs) {
+            if (TMA && bulk_pending) { warp_tile_bulk_wait(lane); bulk_pending = false; }   // previous copy has drained the tile
             ObsT* row = tile + lane * D3_OBS;
             if (!tall) observe_cache<ObsT>(gb, e.pr, e.pc, row);
             else observe_tall<ObsT>(ge, e.pr, e.pc, row);
             obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, st.total_step, row[49], row[50]);
-            __syncwarp();
             ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * D3_OBS;
-            if (nvalid == 32) warp_tile_store_full<ObsT, 32 * D3_OBS>(dst, tile, lane);
-            else warp_tile_store<ObsT>(dst, tile, nvalid * D3_OBS, lane);
-            __syncwarp();
+            if (TMA && nvalid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                warp_tile_bulk_store(dst, tile, 32 * D3_OBS * sizeof(ObsT), lane);
+                bulk_pending = true;
+            } else {
+                __syncwarp();
+                if (nvalid == 32) warp_tile_store_full<ObsT, 32 * D3_OBS>(dst, tile, lane);
+                else warp_tile_store<ObsT>(dst, tile, nvalid * D3_OBS, lane);
+                __syncwarp();
+            }
         }
 
         // ---- (d) reward (reward_check :232-239); the plan byte requested above has arrived by now -------
@@ -344,13 +352,14 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
         if (errbits) atomicOr(st.err, errbits);
         if (st.t_dev && env == 0) st.t_dev[tslot ^ 1] = t0 + (uint64_t)K;
     }
+    if (TMA && bulk_pending) warp_tile_bulk_wait(lane);                 // the tile must outlive the copy that reads it
 }
 
 // Launch shape.  Every warp is an independent tile of 32 envs, so blocks are single warps unless DMP_3D_WPB
 // says otherwise: the block scheduler then refills an SM warp by warp instead of waiting for the slowest
 // warp of a big block.  Shared memory alone limits residency (11 warps per SM for f32 observations).
-template <typename ObsT>
-int launch_cache(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+template <typename ObsT, bool TMA>
+int launch_cache_t(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
     const char* wv = getenv("DMP_3D_WPB");
     const int wpb_env = wv ? atoi(wv) : 0;
     const size_t per_warp = warp_smem_bytes<ObsT>();
@@ -361,15 +370,23 @@ int launch_cache(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
     const size_t smem = (size_t)wpb * per_warp + 16;
     static size_t attr_smem = 0;                             // per instantiation
     if (smem > attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(k3d_cache_rollout<ObsT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k3d_cache_rollout<ObsT, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return dmp_set_error(e);
-        e = cudaFuncSetAttribute(k3d_cache_rollout<ObsT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        e = cudaFuncSetAttribute(k3d_cache_rollout<ObsT, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return dmp_set_error(e);
         attr_smem = smem;
     }
     const int64_t warps = (st.n_envs + 31) / 32;
     const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
-    return dmp_set_error(dmp_launch_pdl(k3d_cache_rollout<ObsT>, blocks, (unsigned)(wpb * 32), smem, s, st, io, K));
+    return dmp_set_error(dmp_launch_pdl(k3d_cache_rollout<ObsT, TMA>, blocks, (unsigned)(wpb * 32), smem, s, st, io, K));
+}
+
+// DMP_TILE_COPY (tuning switch): l = load/store copy-out of the observation tile, b = bulk async copy (default)
+template <typename ObsT>
+int launch_cache(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    const char* v = getenv("DMP_TILE_COPY");
+    if (v && v[0] == 'l') return launch_cache_t<ObsT, false>(st, io, K, s);
+    return launch_cache_t<ObsT, true>(st, io, K, s);
 }
 
 }  // namespace

@@ -385,7 +385,7 @@ def test_3d_tall_columns_match_oracle(kind, dynamic):
 
 # ------------------------------------------------------------------------------------------------
 # 8. 2D single steps leave through a bulk (TMA) copy of the warp tile: equal to the oracle, to the load/store copy-out
-#    (DMP_2D_TILE=f) and independent of the alignment of the caller's observation buffer
+#    (DMP_TILE_COPY=l) and independent of the alignment of the caller's observation buffer
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dynamic", [False, True])
 def test_2d_bulk_copy_out_step_mode(dynamic):
@@ -407,17 +407,17 @@ def test_2d_bulk_copy_out_step_mode(dynamic):
     odd = raw[1:].view(1, n, 51)                              # 4 B aligned only
     for k in range(K):
         def with_tile(mode, fn):
-            old = os.environ.get("DMP_2D_TILE")
-            os.environ["DMP_2D_TILE"] = mode
+            old = os.environ.get("DMP_TILE_COPY")
+            os.environ["DMP_TILE_COPY"] = mode
             try:
                 return fn()
             finally:
                 if old is None:
-                    del os.environ["DMP_2D_TILE"]
+                    del os.environ["DMP_TILE_COPY"]
                 else:
-                    os.environ["DMP_2D_TILE"] = old
-        o1, r1, d1 = with_tile("t", lambda: envs["tma"].step(None))
-        o2, r2, d2 = with_tile("f", lambda: envs["float"].step(None))
+                    os.environ["DMP_TILE_COPY"] = old
+        o1, r1, d1 = with_tile("b", lambda: envs["tma"].step(None))
+        o2, r2, d2 = with_tile("l", lambda: envs["float"].step(None))
         e3 = envs["unaligned"]
         o3, r3, d3 = e3.rollout(1, out=(odd, e3._reward[None], e3._done[None]))           # default mode, 4 B aligned buffer
         assert np.array_equal(o1.cpu().numpy().astype(np.float64), r_obs[k]), k
