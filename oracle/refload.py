@@ -40,6 +40,12 @@ def _install_stubs():
 
         gym.Env, gym.Wrapper = Env, Wrapper
         gym.spaces = types.ModuleType("gym.spaces")
+
+        class Discrete:                  # gym.spaces.Discrete(n): the *_MCTS classes only store it
+            def __init__(self, n):
+                self.n = n
+
+        gym.spaces.Discrete = Discrete
         sys.modules["gym"] = gym
         sys.modules["gym.spaces"] = gym.spaces
     if "matplotlib" not in sys.modules:
@@ -92,6 +98,13 @@ _MODULES = {
     ("1D", "hindsight_static"): ("1D", "DMP_Env_1D_static_hindsight_replay", "deep_mobile_printing_1d1r_hindsight"),
     ("2D", "hindsight_static"): ("2D", "DMP_Env_2D_static_hindsight_replay", "deep_mobile_printing_2d1r_hindsight"),
     ("3D", "hindsight_static"): ("3D", "DMP_simulator_3d_static_circle_hindsight_replay", "deep_mobile_printing_3d1r_hindsight"),
+    # tree-search variants: state tuples + functional transition(state, action)
+    ("1D", "mcts_static"): ("1D", "DMP_Env_1D_static_MCTS", "deep_mobile_printing_1d1r_MCTS"),
+    ("1D", "mcts_dynamic"): ("1D", "DMP_Env_1D_dynamic_MCTS", "deep_mobile_printing_1d1r_MCTS_obs"),
+    ("2D", "mcts_static"): ("2D", "DMP_ENV_2D_static_MCTS", "deep_mobile_printing_2d1r_MCTS"),
+    ("2D", "mcts_dynamic"): ("2D", "DMP_ENV_2D_dynamic_MCTS", "deep_mobile_printing_2d1r"),
+    ("3D", "mcts_static"): ("3D", "DMP_simulator_3d_static_circle_MCTS", "deep_mobile_printing_3d1r"),
+    ("3D", "mcts_dynamic"): ("3D", "DMP_simulator_3d_dynamic_triangle_MCTS", "deep_mobile_printing_3d1r"),
 }
 
 

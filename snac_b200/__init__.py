@@ -12,7 +12,10 @@ from .compat import (FlatObsEnv, HostStepper, VectorizedEnvWrapper, deep_mobile_
                      deep_mobile_printing_2d1r_Lnet, deep_mobile_printing_3d1r_Lnet,
                      deep_mobile_printing_1d1r_hindsight, deep_mobile_printing_2d1r_hindsight,
                      deep_mobile_printing_3d1r_hindsight, deep_mobile_printing_1d1r_hindsight_static,
-                     deep_mobile_printing_2d1r_hindsight_static, deep_mobile_printing_3d1r_hindsight_static)
+                     deep_mobile_printing_2d1r_hindsight_static, deep_mobile_printing_3d1r_hindsight_static,
+                     deep_mobile_printing_1d1r_MCTS, deep_mobile_printing_1d1r_MCTS_obs,
+                     deep_mobile_printing_2d1r_MCTS, deep_mobile_printing_2d1r_MCTS_dynamic,
+                     deep_mobile_printing_3d1r_MCTS, deep_mobile_printing_3d1r_MCTS_dynamic)
 
 __all__ = ["FlatObsEnv", "BatchedDMPEnv", "load_plan_dataset", "generate_plans", "DeviceRollout", "EpsilonGreedy", "QSAAdapter",
            "RandomPolicy", "HostStepper", "VectorizedEnvWrapper",
@@ -22,4 +25,7 @@ __all__ = ["FlatObsEnv", "BatchedDMPEnv", "load_plan_dataset", "generate_plans",
            "deep_mobile_printing_1d1r_Lnet", "deep_mobile_printing_2d1r_Lnet", "deep_mobile_printing_3d1r_Lnet",
            "deep_mobile_printing_1d1r_hindsight", "deep_mobile_printing_2d1r_hindsight",
            "deep_mobile_printing_3d1r_hindsight", "deep_mobile_printing_1d1r_hindsight_static",
-           "deep_mobile_printing_2d1r_hindsight_static", "deep_mobile_printing_3d1r_hindsight_static"]
+           "deep_mobile_printing_2d1r_hindsight_static", "deep_mobile_printing_3d1r_hindsight_static",
+           "deep_mobile_printing_1d1r_MCTS", "deep_mobile_printing_1d1r_MCTS_obs", "deep_mobile_printing_2d1r_MCTS",
+           "deep_mobile_printing_2d1r_MCTS_dynamic", "deep_mobile_printing_3d1r_MCTS",
+           "deep_mobile_printing_3d1r_MCTS_dynamic"]

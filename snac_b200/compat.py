@@ -443,6 +443,145 @@ class deep_mobile_printing_3d1r_hindsight_static(deep_mobile_printing_3d1r):
 
 
 # --------------------------------------------------------------------------------------------------
+# tree-search variants (Env/*/...MCTS*.py): reset() -> (state, obs), step(a) -> (state, obs, reward,
+# done), and the functional transition(state, a) that script/MCTS/utils/uct.py expands tree nodes with.
+# state = (position, environment_memory, count_brick, count_step); observations are always the raw (1, D) row.
+# --------------------------------------------------------------------------------------------------
+class _MCTSMixin:
+    _transition_copies = False      # only the 1D dataset class copies the caller's array (Env/1D/DMP_Env_1D_dynamic_MCTS.py:86)
+
+    def _format_obs(self, obs, pos, reset):
+        return obs
+
+    def _snapshot(self):
+        pos = self.position_memory[-1]
+        pos = pos if self._dim == 1 else list(pos)
+        self.state = (pos, self.environment_memory.copy(), self.count_brick, self.count_step)
+        return self.state
+
+    def reset(self):
+        self.state = None
+        if not hasattr(self, "action_space"):
+            self.action_space = _Space(n=self.action_dim)
+        obs = super().reset()
+        return self._snapshot(), obs
+
+    def step(self, action, step_size=None):
+        obs, r, d = super().step(action, step_size)
+        return self._snapshot(), obs, r, d
+
+    def equality_operator(self, o1, o2):
+        return bool(np.array_equal(o1, o2))
+
+    def iou_MCTS(self, environment_memory):
+        """IoU of a tree node's grid against the current plan (Env/1D/DMP_Env_1D_static_MCTS.py:250-264)."""
+        tw = self._twin(1)
+        sc = torch.zeros((1, 8), dtype=torch.int32, device=tw.device)
+        sc[0, 0], sc[0, 1], sc[0, 4] = self.HALF_WINDOW_SIZE, (self.HALF_WINDOW_SIZE if self._dim != 1 else 0), self._plan_row
+        tw.import_state(grid=self._grid_to_device(environment_memory, tw), scalars=sc)
+        return float(tw.iou().item())
+
+    # ---- expansion ------------------------------------------------------------------------------
+    def _twin(self, n):
+        """A second device env of n slots that shares this env's plan table: tree nodes are stepped there, so
+        expanding never disturbs the episode the env itself is in."""
+        if self._env is None:
+            raise AttributeError("call reset() before transition()")
+        tw = getattr(self, "_twins", {}).get(n)
+        if tw is None:
+            if not hasattr(self, "_twins"):
+                self._twins = {}
+            src = self._env
+            tw = BatchedDMPEnv(self._dim, dynamic=self._dynamic, plan_choose=self.plan_choose,
+                               plans=(src.plan_table(), src.plan_totals()) if self._dynamic else None, num_envs=n,
+                               device=self._device, obs_dtype=torch.float64, dynamic_rules=src.dynamic_rules)
+            if not self._dynamic:
+                tw._install_plans(src.plan_table(), src.plan_totals())       # incl. the hindsight scratch row
+            self._twins[n] = tw
+        return tw
+
+    def _grid_to_device(self, grids, tw):
+        g = np.asarray(grids, dtype=np.float64)
+        if self._lnet and self._dim == 2:
+            g = np.where(g == 2, -1, g)
+        return torch.as_tensor(np.ascontiguousarray(g).astype(np.int32), device=tw.device)
+
+    def transition_batch(self, states, actions, step_sizes=None):
+        """``transition`` for many (state, action) pairs in ONE kernel launch (leaf-parallel expansion).  Step sizes
+        default to one ``np.random.randint(1, 4)`` draw per pair, in order -- the stream a loop over transition()
+        would consume.  Returns a list of (state', observation, reward, done)."""
+        n = len(states)
+        acts = [int(a) for a in actions]
+        if len(acts) != n:
+            raise ValueError("one action per state")
+        if step_sizes is None:
+            step_sizes = [int(np.random.randint(1, 4)) for _ in range(n)]
+        self._sync_plan()
+        tw = self._twin(n)
+        pos = np.asarray([[s[0], 0] if self._dim == 1 else list(s[0]) for s in states], dtype=np.int32)
+        grids = np.stack([np.asarray(s[1], dtype=np.float64).reshape(tw._lay.grid_rows, tw._lay.grid_cols) for s in states])
+        a_dev = [min(a, 255) if a >= 0 else 255 for a in acts]
+        if self._dim == 3 and any(a < 0 for a in acts):
+            raise ValueError("negative actions are not supported by the device path")
+        npos, ngrid, ncb, ncs, obs, rew, done = tw.transition_dense(
+            pos[:, 0] if self._dim == 1 else pos, self._grid_to_device(grids, tw),
+            [int(s[2]) for s in states], [int(s[3]) for s in states], a_dev, step_sizes,
+            plan_idx=[self._plan_row] * n)
+        tw._err.zero_()                                      # out-of-range actions are no-op steps here, not errors
+        npos, ncb, ncs = npos.cpu().numpy(), ncb.cpu().numpy(), ncs.cpu().numpy()
+        ngrid = ngrid.cpu().numpy().astype(np.float64)
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        out = []
+        for i, st in enumerate(states):
+            g_in = st[1]
+            g_new = ngrid[i].reshape(np.shape(g_in))
+            if self._transition_copies or not isinstance(g_in, np.ndarray):
+                g_out = g_new
+            else:                                            # the reference mutates the caller's array in place
+                g_in[...] = g_new
+                g_out = g_in
+            p = int(npos[i]) if self._dim == 1 else [int(npos[i, 0]), int(npos[i, 1])]
+            cb, r, d = int(ncb[i]), float(rew[i]), bool(done[i])
+            if self._dim == 2:                               # 2D: int 0 on moves and on drops above the plan, like step()
+                a = acts[i]
+                if a != 4 or (r == 0.0 and not cb >= self.total_brick):
+                    r = 0
+            out.append(((p, g_out, cb, int(ncs[i])), obs[i].reshape(1, -1).copy(), r, d))
+        return out
+
+    def transition(self, state, action, is_model_dynamic=True):
+        """(state, action) -> (state', observation, reward, done), e.g. Env/2D/DMP_ENV_2D_static_MCTS.py:110-169,
+        Env/3D/DMP_simulator_3d_static_circle_MCTS.py:215-289.  Draws its step size from the global numpy stream."""
+        step_size = int(np.random.randint(1, 4))
+        return self.transition_batch([state], [action], [step_size])[0]
+
+
+class deep_mobile_printing_1d1r_MCTS(_MCTSMixin, deep_mobile_printing_1d1r):
+    """Env/1D/DMP_Env_1D_static_MCTS.py."""
+
+
+class deep_mobile_printing_1d1r_MCTS_obs(_MCTSMixin, deep_mobile_printing_1d1r_dynamic):
+    """Env/1D/DMP_Env_1D_dynamic_MCTS.py (dataset plans; transition() leaves the caller's grid untouched)."""
+    _transition_copies = True
+
+
+class deep_mobile_printing_2d1r_MCTS(_MCTSMixin, deep_mobile_printing_2d1r):
+    """Env/2D/DMP_ENV_2D_static_MCTS.py."""
+
+
+class deep_mobile_printing_2d1r_MCTS_dynamic(_MCTSMixin, deep_mobile_printing_2d1r_dynamic):
+    """Env/2D/DMP_ENV_2D_dynamic_MCTS.py (class ``deep_mobile_printing_2d1r`` of that module)."""
+
+
+class deep_mobile_printing_3d1r_MCTS(_MCTSMixin, deep_mobile_printing_3d1r):
+    """Env/3D/DMP_simulator_3d_static_circle_MCTS.py (class ``deep_mobile_printing_3d1r`` of that module)."""
+
+
+class deep_mobile_printing_3d1r_MCTS_dynamic(_MCTSMixin, deep_mobile_printing_3d1r_dynamic):
+    """Env/3D/DMP_simulator_3d_dynamic_triangle_MCTS.py (class ``deep_mobile_printing_3d1r`` of that module)."""
+
+
+# --------------------------------------------------------------------------------------------------
 # learner-side copies of the envs (script/SAC/environments/*.py, script/PPO/*/DMP_*.py): the same simulators with a
 # flat (D,) observation, and -- for the stable-baselines PPO scripts -- gym spaces and a 4-tuple step()
 # --------------------------------------------------------------------------------------------------

@@ -452,6 +452,36 @@ class BatchedDMPEnv:
         obs, rew, done = self.step(actions, step_sizes)
         return self.get_state(), obs.clone(), rew.clone(), done.clone()
 
+    def transition_dense(self, position, grid, count_brick, count_step, actions, step_sizes=None, plan_idx=None):
+        """The MCTS variants' ``transition(state, action)`` for N tree nodes in ONE launch, with the state in the
+        reference's own tuple format (Env/2D/DMP_ENV_2D_static_MCTS.py:110-169,
+        Env/3D/DMP_simulator_3d_static_circle_MCTS.py:215-289): ``position`` [N] (1D) or [N,2], ``grid`` =
+        environment_memory incl. its -1 frame ([N,1,34] / [N,26,26]), ``count_brick`` / ``count_step`` [N].
+        ``plan_idx`` [N] selects each node's plan row (default: the rows the envs already point at).
+        Returns (position', grid', count_brick', count_step', obs, reward, done) as device tensors; this env's
+        state is replaced by the successor states (episode statistics are not touched: use auto_reset=False)."""
+        n = self.num_envs
+        if self.auto_reset:
+            raise RuntimeError("transition_dense() needs an env built with auto_reset=False")
+        pos = torch.as_tensor(position, device=self.device).to(torch.int32).reshape(n, -1)
+        sc = torch.zeros((n, 8), dtype=torch.int32, device=self.device)
+        sc[:, 0] = pos[:, 0]
+        if self.dim != 1:
+            sc[:, 1] = pos[:, 1]
+        sc[:, 2] = torch.as_tensor(count_brick, device=self.device).to(torch.int32).reshape(n)
+        sc[:, 3] = torch.as_tensor(count_step, device=self.device).to(torch.int32).reshape(n)
+        if plan_idx is None:
+            sc[:, 4] = self.export_state()["scalars"][:, 4] if not self._needs_initial_reset else 0
+        else:
+            sc[:, 4] = torch.as_tensor(plan_idx, device=self.device).to(torch.int32).reshape(n)
+        g = torch.as_tensor(grid, device=self.device).to(torch.int32)
+        self.import_state(grid=g, scalars=sc, ret=torch.zeros(n, dtype=torch.float32, device=self.device))
+        obs, rew, done = self.step(actions, step_sizes)
+        st = self.export_state()
+        s2 = st["scalars"]
+        npos = s2[:, 0].clone() if self.dim == 1 else s2[:, 0:2].clone()
+        return npos, st["grid"], s2[:, 2].clone(), s2[:, 3].clone(), obs.clone(), rew.clone(), done.clone()
+
     # plan sources --------------------------------------------------------------------------------
     def _install_plans(self, table: torch.Tensor, totals: torch.Tensor) -> None:
         table = table.to(self.device).contiguous().view(torch.uint8).reshape(-1, self._lay.plan_row_bytes)
