@@ -15,6 +15,9 @@ namespace {
 // B1 = threads (= envs) per block is a template parameter: 128 for large batches, 32 when the batch is too small
 // to give every SM several blocks (BASELINE config 2: 65 536 envs = 2 048 warps for 592 schedulers)
 constexpr int S1_WORDS = 17;          // padded 34 halfwords: word 0 and 16 are the -1 walls
+#ifndef DMP_1D_TMA_DEFAULT
+#define DMP_1D_TMA_DEFAULT 0          // load/store copy-out unless DMP_TILE_COPY=b (see profiles/README.md)
+#endif
 
 struct Env1 {
     int pos, plan_idx, cb, cs;
@@ -67,18 +70,23 @@ __device__ __forceinline__ double iou1_words(const uint32_t (&hw)[15], const uin
     return __ddiv_rn((double)cross, (double)(a1 + a2 - cross));
 }
 
-template <typename ObsT, int B1>
+// TMA = true: the warp's observation tile leaves through one bulk async copy per step (dmp_common.cuh:
+// warp_tile_bulk_store) out of a ring of NT1 tiles, so a step never waits for the previous step's copy; TMA = false:
+// 2 x (LDS.128 + STG.128) per lane out of a single tile.
+constexpr int NT1 = 4;
+
+template <typename ObsT, int B1, bool TMA>
 __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO io, const int K) {
     extern __shared__ uint4 smem_raw[];
     uint32_t* G = reinterpret_cast<uint32_t*>(smem_raw);                 // [S1_WORDS][B1]
-    ObsT* tiles = reinterpret_cast<ObsT*>(G + S1_WORDS * B1);            // [B1/32][32*7]
+    ObsT* tiles = reinterpret_cast<ObsT*>(G + S1_WORDS * B1);            // [B1/32][TMA ? NT1 : 1][32*7]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t n = st.n_envs;
     const int64_t env = (int64_t)blockIdx.x * B1 + tid;
     const int64_t env0 = env - lane;
     const int nvalid = (int)min((int64_t)32, n - env0);
     const bool live = env < n;
-    ObsT* tile = tiles + warp * (32 * D1_OBS);
+    ObsT* tile = tiles + warp * ((TMA ? NT1 : 1) * 32 * D1_OBS);
     uint32_t* g = G + tid;
 
     uint4* cells = reinterpret_cast<uint4*>(st.cells);
@@ -146,14 +154,28 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
         e.ret += reward;
 
         if (io.obs) {
-            stage_observe1<ObsT, B1>(g, e, tile + lane * D1_OBS, normalise, total_brick, st.total_step);
-            __syncwarp();
-            {
-                ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * D1_OBS;
+            ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * D1_OBS;
+            if constexpr (TMA) {
+                ObsT* tk = tile + (k & (NT1 - 1)) * (32 * D1_OBS);
+                if (k >= NT1) {                             // the copy that read this ring slot NT1 steps ago has drained it
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NT1 - 1) : "memory");
+                    __syncwarp();
+                }
+                stage_observe1<ObsT, B1>(g, e, tk + lane * D1_OBS, normalise, total_brick, st.total_step);
+                if (nvalid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                    warp_tile_bulk_store(dst, tk, 32 * D1_OBS * sizeof(ObsT), lane);
+                } else {
+                    __syncwarp();
+                    if (nvalid > 0) warp_tile_store<ObsT>(dst, tk, nvalid * D1_OBS, lane);
+                    __syncwarp();
+                }
+            } else {
+                stage_observe1<ObsT, B1>(g, e, tile + lane * D1_OBS, normalise, total_brick, st.total_step);
+                __syncwarp();
                 if (nvalid == 32) warp_tile_store_full<ObsT, 32 * D1_OBS>(dst, tile, lane);
                 else if (nvalid > 0) warp_tile_store<ObsT>(dst, tile, nvalid * D1_OBS, lane);
+                __syncwarp();
             }
-            __syncwarp();
         }
         if (live) {
             if (io.reward) io.reward[idx] = reward;
@@ -195,6 +217,7 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
         if (errbits) atomicOr(st.err, errbits);
     }
     if (st.t_dev && blockIdx.x == 0 && tid == 0) st.t_dev[tslot ^ 1] = t0 + (uint64_t)K;
+    if constexpr (TMA) warp_tile_bulk_wait(lane);                        // the tiles must outlive the copies that read them
 }
 
 template <typename ObsT>
@@ -285,21 +308,31 @@ __global__ void k1d_import(const DmpState st, const int32_t* __restrict__ grid, 
     aux[env] = ax;
 }
 
-template <typename ObsT, int B1>
+template <typename ObsT, int B1, bool TMA>
 int launch_rollout1_b(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
-    const size_t smem = (size_t)S1_WORDS * B1 * 4 + (size_t)(B1 / 32) * 32 * D1_OBS * sizeof(ObsT);
+    const size_t smem = (size_t)S1_WORDS * B1 * 4 + (size_t)(B1 / 32) * (TMA ? NT1 : 1) * 32 * D1_OBS * sizeof(ObsT);
     const unsigned blocks = (unsigned)((st.n_envs + B1 - 1) / B1);
+    static bool attr_done = false;           // per instantiation
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k1d_rollout<ObsT, B1, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return dmp_set_error(e);
+        attr_done = true;
+    }
     // plain stream-ordered launch: with programmatic dependent launch the next grid's single-warp blocks become
     // resident early and unbalance the SMs (measured: 47 vs 61 G env-steps/s at 65 536 envs, K = 16)
-    k1d_rollout<ObsT, B1><<<blocks, B1, smem, s>>>(st, io, K);
+    k1d_rollout<ObsT, B1, TMA><<<blocks, B1, smem, s>>>(st, io, K);
     return dmp_set_error(cudaGetLastError());
 }
 
 template <typename ObsT>
 int launch_rollout1(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    // DMP_TILE_COPY (tuning switch): b = bulk async copy-out of the observation tile, l = load/store copy-out
+    const char* v = getenv("DMP_TILE_COPY");
+    const bool tma = DMP_1D_TMA_DEFAULT ? !(v && v[0] == 'l') : (v && v[0] == 'b');
     // fewer than ~4 blocks of 128 per SM: single-warp blocks spread the warps evenly over the 148 SMs
-    if (st.n_envs < (int64_t)128 * 148 * 4) return launch_rollout1_b<ObsT, 32>(st, io, K, s);
-    return launch_rollout1_b<ObsT, 128>(st, io, K, s);
+    const bool small = st.n_envs < (int64_t)128 * 148 * 4;
+    if (tma) return small ? launch_rollout1_b<ObsT, 32, true>(st, io, K, s) : launch_rollout1_b<ObsT, 128, true>(st, io, K, s);
+    return small ? launch_rollout1_b<ObsT, 32, false>(st, io, K, s) : launch_rollout1_b<ObsT, 128, false>(st, io, K, s);
 }
 
 }  // namespace

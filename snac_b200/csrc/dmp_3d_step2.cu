@@ -23,8 +23,11 @@ constexpr int SLOT2_B = 464;                 // per-lane staging: 16 B guard | <
                                              // into 8 distinct 4-bank groups (4-way conflicts; 448 B = 28 granules gave 16-way)
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
+// `tune` (DMP_3D_STEP_TUNE, default 0): bit 0 = at the end of the step ask L2 for the rows under the NEW window, so that
+// the next step's round trip 2 is an L2 hit; bits 1-2 = L2 policy of the row copy (1: evict_last for half of the lines,
+// 2: for all of them) -- the rows an agent looks at change by at most three per step.
 template <typename ObsT>
-__global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const DmpIO io) {
+__global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const DmpIO io, const int tune) {
     extern __shared__ uint4 smem_raw[];
     const int lane = threadIdx.x;
     const int64_t n = st.n_envs;
@@ -85,7 +88,14 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
     __syncwarp();                                                                       // mbarrier init visible
     if (live) {
         mbar_arrive_expect_tx(bar, (uint32_t)(b_hi - b_lo));
-        bulk_g2s(slot + 16, reinterpret_cast<const uint8_t*>(ge) + b_lo, (uint32_t)(b_hi - b_lo), bar);
+        if (tune & 6) {
+            uint64_t pol;
+            if (tune & 4) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+            else asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 0.5;" : "=l"(pol));
+            bulk_g2s_hint(slot + 16, reinterpret_cast<const uint8_t*>(ge) + b_lo, (uint32_t)(b_hi - b_lo), bar, pol);
+        } else {
+            bulk_g2s(slot + 16, reinterpret_cast<const uint8_t*>(ge) + b_lo, (uint32_t)(b_hi - b_lo), bar);
+        }
     } else {
         mbar_arrive(bar);
     }
@@ -221,6 +231,10 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
             gg[0] = z; gg[1] = z;
         }
     }
+    if ((tune & 1) && live) {                               // rows under the window the next step starts from
+        const int p_lo = (max(e.pr - 6, 0) * 40) & ~15, p_hi = ((min(e.pr, 19) + 1) * 40 + 15) & ~15;
+        bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(ge) + p_lo, (uint32_t)(p_hi - p_lo));
+    }
     if (live) {
         stg_keep(aux + env, make_uint4((uint32_t)e.pr | ((uint32_t)e.pc << 8) | ((uint32_t)e.plan_idx << 16),
                                        (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16), __float_as_uint(e.ret), (uint32_t)e.cross), keep);
@@ -243,7 +257,9 @@ int launch_span(const DmpState& st, const DmpIO& io, cudaStream_t s) {
         attr_done = true;
     }
     const unsigned blocks = (unsigned)((st.n_envs + 31) / 32);
-    return dmp_set_error(dmp_launch_pdl(k3d_step_span<ObsT>, blocks, 32u, smem, s, st, io));
+    const char* tv = getenv("DMP_3D_STEP_TUNE");
+    const int tune = tv ? atoi(tv) : 0;
+    return dmp_set_error(dmp_launch_pdl(k3d_step_span<ObsT>, blocks, 32u, smem, s, st, io, tune));
 }
 
 }  // namespace

@@ -427,3 +427,47 @@ def test_2d_bulk_copy_out_step_mode(dynamic):
     assert ob.ep_cnt.sum() > 0
     for env in envs.values():
         env.check_errors()
+
+
+# ------------------------------------------------------------------------------------------------
+# 9. 1D rollouts with the bulk (TMA) copy-out of the observation tile (a ring of tiles per warp, DMP_TILE_COPY=b):
+#    equal to the oracle and to the load/store copy-out for every observation dtype, ragged last warp, K beyond the ring
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dynamic,n", [(False, 32 * 37 + 20), (True, 128 * 148 * 4 + 64)])
+def test_1d_bulk_copy_out_rollout(dynamic, n):
+    plans = load_plans(1, "dense", "train") if dynamic else None
+    K = 23 if n > 10000 else 70
+    def with_tile(mode, fn):
+        old = os.environ.get("DMP_TILE_COPY")
+        os.environ["DMP_TILE_COPY"] = mode
+        try:
+            return fn()
+        finally:
+            if old is None:
+                del os.environ["DMP_TILE_COPY"]
+            else:
+                os.environ["DMP_TILE_COPY"] = old
+    ref = None
+    if n < 10000:
+        ob = OracleBatch(1, dynamic, n, 2, plans)
+        for e in ob.envs:
+            e.total_step = 30
+        ob.reset(philox.reset_draw(SEED, np.arange(5, 5 + n), 0, ob.n_plans) if dynamic else None)
+        ref = philox_rollout(ob, K, SEED, 5, 0, 3)
+    outs = {}
+    for dt in (torch.float32, torch.int16, torch.float64):
+        for mode in ("b", "l"):
+            env = make_gpu(1, dynamic, n, 2, plans, auto_reset=True, env_base=5, seed=SEED, obs_dtype=dt, total_step=30)
+            env.reset()
+            o, r, d = with_tile(mode, lambda: env.rollout(K))
+            o2, r2, d2 = with_tile(mode, lambda: env.rollout(3))          # K below the ring depth
+            torch.cuda.synchronize()
+            env.check_errors()
+            outs[(dt, mode)] = (o, r, d, o2, r2, d2, env.export_state())
+        a, b = outs[(dt, "b")], outs[(dt, "l")]
+        for x, y in zip(a[:6], b[:6]):
+            assert torch.equal(x, y), dt
+        assert torch.equal(a[6]["grid"], b[6]["grid"]) and torch.equal(a[6]["scalars"], b[6]["scalars"])
+        if ref is not None:
+            assert np.array_equal(a[0].cpu().numpy().astype(np.float64), ref[0]), dt
+            assert np.array_equal(a[1].cpu().numpy(), ref[1]) and np.array_equal(a[2].cpu().numpy(), ref[2])
