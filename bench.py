@@ -218,7 +218,7 @@ def run_ours(args):
 
     wl = args.workload
     dim, dynamic, plan_choose, density, default_envs, b_alg_step = WORKLOADS[wl]
-    state_bytes = {1: 72, 2: 64, 3: 816}[dim]
+    state_bytes = {1: 72, 2: 64, 3: 1216}[dim]
     total_envs = args.envs or default_envs
     from snac_b200.sharding import shard_bounds
     env_base, n = shard_bounds(total_envs, rank, world)  # strong scaling: the batch is sharded
@@ -259,10 +259,15 @@ def run_ours(args):
             acts = [act_pool[(torch.arange(KL) + 7 * j) % RA].contiguous() for j in range(8)]
         G = max(16 if KL > 1 else 32, R + (R & 1))            # launches per graph (even: t_dev slots alternate)
 
-        def launch(i):
-            env.rollout(KL, actions=None if acts is None else acts[i % 8],
-                        out=(obs_ring[i % R], rew_ring[i % R], done_ring[i % R]), use_device_t=True, t_slot=i & 1)
+        def launch(i, kl=KL):
+            a = None if acts is None else acts[i % 8][:kl]
+            env.rollout(kl, actions=a, out=(obs_ring[i % R][:kl], rew_ring[i % R][:kl], done_ring[i % R][:kl]),
+                        use_device_t=True, t_slot=i & 1)
 
+        # EXACTLY K steps are timed: n_replay replays of a graph of G full launches, then one replay of a tail graph
+        # holding the remaining full launches and (when KL does not divide K) one shorter launch
+        full, rem = divmod(K, KL)
+        n_replay, n_tail = divmod(full, G)
         with torch.cuda.stream(stream):
             for i in range(4):
                 launch(i)                                    # sets func attributes before capture
@@ -271,9 +276,16 @@ def run_ours(args):
             with torch.cuda.graph(graph, stream=stream):
                 for i in range(G):
                     launch(i)
+            tail = None
+            if n_tail or rem:
+                tail = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(tail, stream=stream):
+                    for i in range(n_tail):
+                        launch(i)
+                    if rem:
+                        launch(n_tail, rem)
             per_replay = G * KL
             n_replay_w = max(1, -(-W // per_replay))
-            n_replay = max(1, -(-K // per_replay))
             for _ in range(n_replay_w):
                 graph.replay()
             stream.synchronize()
@@ -285,18 +297,24 @@ def run_ours(args):
                 e0.record(stream)
                 for _ in range(n_replay):
                     graph.replay()
+                if tail is not None:
+                    tail.replay()
                 e1.record(stream)
                 stream.synchronize()
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             ms = e0.elapsed_time(e1)
+            n_launch = n_replay * G + n_tail + (1 if rem else 0)
+            if (n_tail + (1 if rem else 0)) & 1:             # keep the two device step-counter slots alternating
+                launch(1)
+                stream.synchronize()
         tm = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ring = "obs ring of %d x %.1f MB (> 2 x L2) + state %.1f MB" % (R, obs_bytes / 1e6, n * state_bytes / 1e6)
-        del graph, obs_ring, rew_ring, done_ring
-        return float(tm.item()), n_replay * per_replay, n_replay_w * per_replay, n_replay * G, ring, clk.summary()
+        del graph, tail, obs_ring, rew_ring, done_ring
+        return float(tm.item()), K, n_replay_w * per_replay, n_launch, ring, clk.summary()
 
     def b_alg_of(KL, mean_len=None):
         """algorithmic bytes per env-step with fp32 observations.
@@ -400,7 +418,7 @@ def run_ours(args):
             "e2e": e2e, "e2e_i16": e2e_i16, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_note": "bytes per launch from the committed ncu capture (profiles/), not measured live; algorithmic bytes per launch = %d" % int(b_alg * n * KL),
-                         "peak_source": peak_src, "kernel": ("k3d_step_span<float> (K=1)" if (dim == 3 and KL == 1) else
+                         "peak_source": peak_src, "kernel": ("k3d_step_bytes<float> (K=1)" if (dim == 3 and KL == 1) else
                                     "k%dd%s_rollout<float> (K=%d)" % (dim, "_cache" if dim == 3 else "", KL)),
                          "bytes_per_env_step": b_alg, "envs_per_launch": n},
             "episode_stats": {"sum_return": float(stats[0]), "sum_iou": float(stats[1]), "episodes": float(stats[2]),

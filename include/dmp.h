@@ -21,7 +21,10 @@
  *                              20x20 interior), word 13 = pos_row | pos_col << 8 | plan_idx << 16,
  *                              word 14 = count_brick | count_step << 16, word 15 = episode return (f32)
  *       aux   : unused (NULL)
- *   3D  cells : u16 [n][400]   per-env contiguous 20x20 height map (row-major), 800 B, 16 B aligned
+ *   3D  cells : u16 [n][400]   per-env contiguous 20x20 height map (row-major), 800 B, 16 B aligned (canonical),
+ *               followed at byte offset 800 n by its byte shadow u8 [n][400], byte = min(height, 255): single steps
+ *               and rollouts stage these 400 B maps (half the traffic and shared memory); a saturated or large
+ *               byte sends the env to an exact path over the u16 map.  Every kernel keeps both in step.
  *       aux   : uint4 [n]      .x = pos_row | pos_col << 8 | plan_idx << 16 ; .y = count_brick | count_step << 16 ;
  *                              .z = episode return (f32 bits) ; .w = running sum(min(height, plan)), the IoU
  *                              numerator, +1 for every brick laid at or below the plan height
@@ -44,7 +47,7 @@
 extern "C" {
 #endif
 
-#define DMP_ABI_VERSION 1
+#define DMP_ABI_VERSION 2
 
 /* return codes */
 #define DMP_OK       0

@@ -8,7 +8,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libdmp.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, EINVAL, ECUDA = 0, 1, 2
 OBS_F32, OBS_F64, OBS_I16 = 0, 1, 2
 F_AUTORESET, F_NORMALISE, F_TSLOT1, F_NO_L2_HINT = 1, 2, 4, 8

@@ -249,6 +249,7 @@ __global__ void k3d_reset(const DmpState st, const uint8_t* __restrict__ mask, c
     const uint4 z = make_uint4(0, 0, 0, 0);
     g4[lane] = z;
     if (lane < 18) g4[lane + 32] = z;
+    if (lane < 25) reinterpret_cast<uint4*>(bmap3(st) + env * CELLS3D)[lane] = z;       // byte shadow
     if (lane == 0) aux[env] = pack3(Env3{D2_LO, D2_LO, p, 0, 0, 0.f, 0});
     if (obs) {
         ObsT* o = obs + env * D3_OBS;
@@ -315,6 +316,23 @@ __global__ void k3d_import(const DmpState st, const int32_t* __restrict__ grid, 
     if (lane == 0) aux[env] = pack3(e);
 }
 
+// byte shadow := min(height, 255) for every env (one 16 B vector of bytes per thread)
+__global__ void k3d_sync_bytes(const DmpState st) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;                 // vector index: 25 per env
+    if (i >= st.n_envs * (CELLS3D / 16)) return;
+    const uint4* src = reinterpret_cast<const uint4*>(st.cells) + 2 * i;
+    const uint4 a = src[0], b = src[1];
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t h0 = min(w[2 * q] & 0xFFFFu, 255u), h1 = min(w[2 * q] >> 16, 255u);
+        const uint32_t h2 = min(w[2 * q + 1] & 0xFFFFu, 255u), h3 = min(w[2 * q + 1] >> 16, 255u);
+        o[q] = h0 | (h1 << 8) | (h2 << 16) | (h3 << 24);
+    }
+    reinterpret_cast<uint4*>(bmap3(st))[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 inline unsigned blocks3(int64_t n) { return (unsigned)((n + WPB3 - 1) / WPB3); }
 
 }  // namespace
@@ -331,17 +349,27 @@ static int dmp3d_wpe_rollout(const DmpState& st, const DmpIO& io, int K, cudaStr
     return dmp_set_error(cudaGetLastError());
 }
 
+int dmp3d_sync_bytes(const DmpState& st, cudaStream_t s) {
+    const int64_t nvec = st.n_envs * (CELLS3D / 16);
+    k3d_sync_bytes<<<(unsigned)((nvec + 255) / 256), 256, 0, s>>>(st);
+    return dmp_set_error(cudaGetLastError());
+}
+
 int dmp3d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
     // DMP_3D_KERNEL = w (warp per env) | t (u16 tile, whole maps by bulk async copies) | c (byte cache) |
-    // r (single step, first generation: six cell loads + window rows; K == 1) forces one kernel.  Default: the
-    // byte-cache kernel for rollouts (K > 1), the row-span kernel (dmp_3d_step2.cu) for single steps.
+    // r / s (single step, first / second generation over the u16 maps; K == 1) forces one kernel.  Default: the
+    // byte-cache kernel for rollouts (K > 1), the byte-row kernel (dmp_3d_step3.cu) for single steps.  The forced
+    // cross-check kernels only know the u16 maps; the byte shadow is rebuilt after them.
     const char* v = getenv("DMP_3D_KERNEL");             // read per call: tests switch kernels in-process
     const int forced = v ? (int)v[0] : 0;
-    if (forced == 'w') return dmp3d_wpe_rollout(st, io, K, s);
-    if (forced == 't') return dmp3d_tile_rollout(st, io, K, s);
+    int rc = -1;
+    if (forced == 'w') rc = dmp3d_wpe_rollout(st, io, K, s);
+    else if (forced == 't') rc = dmp3d_tile_rollout(st, io, K, s);
+    else if (forced == 'r' && K == 1) rc = dmp3d_step_rows(st, io, s);
+    else if (forced == 's' && K == 1) rc = dmp3d_step_span(st, io, s);
+    if (rc >= 0) return rc != DMP_OK ? rc : dmp3d_sync_bytes(st, s);
     if (forced == 'c') return dmp3d_cache_rollout(st, io, K, s);
-    if (forced == 'r' && K == 1) return dmp3d_step_rows(st, io, s);
-    return K > 1 ? dmp3d_cache_rollout(st, io, K, s) : dmp3d_step_span(st, io, s);
+    return K > 1 ? dmp3d_cache_rollout(st, io, K, s) : dmp3d_step_bytes(st, io, s);
 }
 
 int dmp3d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs,
@@ -366,5 +394,6 @@ int dmp3d_export(const DmpState& st, int32_t* grid, int32_t* scalars, float* ret
 }
 int dmp3d_import(const DmpState& st, const int32_t* grid, const int32_t* scalars, const float* ret, cudaStream_t s) {
     k3d_import<<<blocks3(st.n_envs), WPB3 * 32, 0, s>>>(st, grid, scalars, ret);
-    return dmp_set_error(cudaGetLastError());
+    const int rc = dmp_set_error(cudaGetLastError());
+    return (rc != DMP_OK || !grid) ? rc : dmp3d_sync_bytes(st, s);
 }

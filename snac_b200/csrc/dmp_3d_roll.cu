@@ -7,9 +7,10 @@
 // lifts the number of resident warps per SM from 7 to 11 (f32 observations; 14 with i16), which is what this
 // latency-bound kernel needs, and an odd word stride (101) makes same-offset accesses of the 32 lanes
 // bank-conflict free.  HBM keeps the canonical u16 maps; every brick is written through.
-//   * state in : the warp's 32 maps are one contiguous 25 600 B span: coalesced 128-bit loads, low bytes packed
-//                with PRMT, two 32-bit shared stores per 16 B.  An env that holds a height >= 254 anywhere is
-//                flagged "tall" and runs entirely from HBM (exact, slow, practically never).
+//   * state in : the warp's 32 byte maps are one contiguous 12 800 B span of the byte shadow (include/dmp.h): 25
+//                coalesced 128-bit loads per lane in one round trip, four 32-bit shared stores per 16 B.  An env that
+//                holds a byte >= 128 anywhere is flagged "tall" and runs entirely from the u16 map in HBM (exact,
+//                slow, practically never).
 //   * step     : neighbours / walk cells / 7x7 window are shared-memory byte reads;
 //   * obs out  : window rows are cut out of the byte map with funnel shifts, biased by +1 (0 = frame), each byte
 //                is dropped into the mantissa of 2^23 (PRMT) and turned into -1/0/h by one FADD; the warp's
@@ -135,6 +136,8 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
     uint16_t* cells = reinterpret_cast<uint16_t*>(st.cells);
     uint16_t* gwarp = cells + env0 * CELLS3D;                         // the warp's 32 maps in HBM (contiguous)
     uint16_t* ge = cells + env * CELLS3D;                             // this lane's map in HBM
+    uint8_t* bwarp = bmap3(st) + env0 * CELLS3D;                      // the warp's 32 byte maps (the byte shadow, contiguous)
+    uint8_t* be = bmap3(st) + env * CELLS3D;
     uint4* aux = reinterpret_cast<uint4*>(st.aux);
     const uint8_t* __restrict__ plans = reinterpret_cast<const uint8_t*>(st.plans);
     const bool autoreset = io.flags & DMP_F_AUTORESET;
@@ -147,38 +150,35 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
     EnvR e{D2_LO, D2_LO, 0, 0, 0, 0.f, 0};
     double acc_iou = 0.0;                                             // this env's sum of episode IoUs (sequential, exact)
     {
-        const uint4* src = reinterpret_cast<const uint4*>(gwarp);
-        const int nvec = nvalid * (CELLS3D / 8);                      // 50 vectors of 8 cells per env
+        // the warp's 32 byte maps are one contiguous 12 800 B span of the byte shadow: 25 coalesced 128-bit loads per
+        // lane, all in flight at once (ONE DRAM round trip per launch), four 32-bit shared stores per vector
+        const uint4* src = reinterpret_cast<const uint4*>(bwarp);
+        const int nvec = nvalid * (CELLS3D / 16);                     // 25 vectors of 16 cells per env
         uint32_t tallbits = 0;
-        constexpr int U = 25;                                         // 25 x 16 B in flight per lane: two DRAM round trips per launch
-#pragma unroll 1
-        for (int i0 = 0; i0 < CELLS3D / 8; i0 += U) {
-            uint4 v[U];
+        constexpr int U = CELLS3D / 16;
+        uint4 v[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int idx = (i0 + u) * 32 + lane;
-                v[u] = (idx < nvec) ? src[idx] : make_uint4(0, 0, 0, 0);
-            }
-            if (i0 == 0 && live) {                                    // scalar state rides along with the first batch
-                const uint4 a = aux[env];
-                e.pr = a.x & 0xFF; e.pc = (a.x >> 8) & 0xFF; e.plan_idx = a.x >> 16;
-                e.cb = a.y & 0xFFFF; e.cs = a.y >> 16;
-                e.ret = __uint_as_float(a.z);
-                e.cross = (int)a.w;
-                if (autoreset) acc_iou = st.ep_iou[env];
-            }
+        for (int u = 0; u < U; ++u) {
+            const int idx = u * 32 + lane;
+            v[u] = (idx < nvec) ? src[idx] : make_uint4(0, 0, 0, 0);
+        }
+        if (live) {                                                   // scalar state rides along
+            const uint4 a = aux[env];
+            e.pr = a.x & 0xFF; e.pc = (a.x >> 8) & 0xFF; e.plan_idx = a.x >> 16;
+            e.cb = a.y & 0xFFFF; e.cs = a.y >> 16;
+            e.ret = __uint_as_float(a.z);
+            e.cross = (int)a.w;
+            if (autoreset) acc_iou = st.ep_iou[env];
+        }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int idx = (i0 + u) * 32 + lane;
-                const int el = idx / (CELLS3D / 8), j = idx - el * (CELLS3D / 8);
-                const uint32_t lo = __byte_perm(v[u].x, v[u].y, 0x6420u), hi = __byte_perm(v[u].z, v[u].w, 0x6420u);
-                const uint32_t any = v[u].x | v[u].y | v[u].z | v[u].w;
-                // conservative: true whenever one of the 8 heights is >= 254 (false positives only cost speed)
-                const bool t8 = (any & 0xFF00FF00u) || ((any & 0xFEu) == 0xFEu) || ((any & 0xFE0000u) == 0xFE0000u);
-                tallbits |= t8 ? (1u << el) : 0u;
-                uint32_t* dst = reinterpret_cast<uint32_t*>(wmap + el * MAP_B + j * 8);
-                dst[0] = lo; dst[1] = hi;                             // lanes beyond nvec write zeros into their own slots
-            }
+        for (int u = 0; u < U; ++u) {
+            const int idx = u * 32 + lane;
+            const int el = idx / U, j = idx - el * U;
+            // conservative: an env holding any byte >= 128 runs from the u16 map (false positives only cost speed)
+            const uint32_t any = v[u].x | v[u].y | v[u].z | v[u].w;
+            tallbits |= (any & 0x80808080u) ? (1u << el) : 0u;
+            uint32_t* dst = reinterpret_cast<uint32_t*>(wmap + el * MAP_B + j * 16);
+            dst[0] = v[u].x; dst[1] = v[u].y; dst[2] = v[u].z; dst[3] = v[u].w;   // lanes beyond nvec write zeros into their own slots
         }
         if (tallbits) atomicOr(tallword, tallbits);
     }
@@ -255,7 +255,8 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
                 pplan = ldg_u8(plans + e.plan_idx * CELLS3D + ti);             // consumed after the observation
                 if (!tall) gb[ti] = (uint8_t)newh;
                 if (live) {
-                    ge[ti] = (uint16_t)newh;                                   // write-through
+                    ge[ti] = (uint16_t)newh;                                   // write-through: canonical map ...
+                    be[ti] = sat_u8(newh);                                     // ... and its byte shadow
                     if (newh >= TALL) tall = true;                             // the byte cache stops being exact
                 }
                 // neighbours after placement: only neighbour `dir` changed, and it is now > 0
@@ -336,6 +337,7 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
                 uint4* gg = reinterpret_cast<uint4*>(gwarp + src * CELLS3D) + 2 * lane;
                 const uint4 z = make_uint4(0, 0, 0, 0);
                 gg[0] = z; gg[1] = z;
+                reinterpret_cast<uint4*>(bwarp + src * CELLS3D)[lane] = z;
             }
         }
         __syncwarp();

@@ -1,15 +1,20 @@
-// dmp_3d_step2.cu -- 3D envs, single-step kernel (K = 1, dmp_step), second generation: TWO dependent HBM round
-// trips per step instead of three, and 40 % less shared memory per env in flight.
+// dmp_3d_step3.cu -- 3D envs, single-step kernel (K = 1, dmp_step), third generation: the rows a step looks at are
+// staged from the BYTE shadow of the height maps (include/dmp.h: u8[n][400] behind the u16 maps, byte = min(h, 255)).
 //
-// dmp_3d_step.cu fetched (1) the scalar state, (2) the six cells the move/build decision reads, (3) the map rows
-// under the window at the NEW position -- three dependent DRAM latencies with ~11 warps per SM to hide them
-// (profiles/README.md: 0.34 of the HBM roofline, long-scoreboard bound).  Here the action and the step size are
-// known before anything is loaded (inputs or Philox), so the rows that can matter are known as soon as the position
-// is: the 7 rows under the old window, plus `step_size` more rows in the direction of a vertical move.  They come in
-// as ONE bulk async copy per env (cp.async.bulk -> UBLKCP, <= 416 B) right after the scalar state; the decision
-// cells, the new window and the brick patch are all served from that staged span.  The observation tile of the warp
-// is built in the same shared memory once every lane holds its window in registers, so a warp needs 14.5 KB instead
-// of 17 KB (+ f32 tile) and 14 single-warp blocks fit an SM.
+// dmp_3d_step2.cu (k3d_step_span) staged u16 rows: <= 416 B per env in a 464 B slot, 14.5 KB of shared memory per
+// warp, 14 resident warps per SM -- too few to hide the two dependent round trips of a step (scalar state, rows);
+// it reached 0.55 of the HBM roofline with 463 B of DRAM traffic per env-step.  Byte rows halve both: <= 224 B per
+// env in a 272 B slot (17 granules of 16 B: an odd count spreads same-offset words of the 32 lanes over 8 bank groups),
+// 8.7 KB per warp, 23 resident warps per SM, and the window is cut out with 3 word reads + 2 funnel shifts per row
+// instead of 5 + 4.  Everything else follows the span kernel: the action and the step size are known before anything is
+// loaded, so ONE bulk async copy per env (cp.async.bulk -> UBLKCP, completion on the warp's mbarrier) right after the
+// scalar state fetches the 7 rows under the old window plus `step_size` more rows in the direction of a vertical move;
+// the six decision cells, the window at the new position and the brick patch are served from that span; every lane
+// pulls its window into registers, then the warp's [32][51] observation tile is built over the drained slots and
+// leaves through one bulk async copy.
+// Exactness: bytes below 255 ARE the heights.  A build on a saturated cell reads the true height from the u16 map, and a
+// lane whose window holds a byte >= 128 builds its observation row from the u16 map (both out of line, practically
+// never: plan height is 6).  Bricks are written through to both maps.
 // Semantics: Env/3D/DMP_simulator_3d_static_circle.py:67-276 and
 // Env/3D/DMP_simulator_3d_dynamic_triangle_usedata.py:45-277 (see dmp_3d.cu for the line-by-line citations).
 #include "dmp_3d_u16.cuh"
@@ -18,13 +23,35 @@ namespace {
 
 using namespace u16map;
 
-constexpr int SLOT2_B = 464;                 // per-lane staging: 16 B guard | <= 416 B of rows | 16 B guard, padded to an
-                                             // ODD number of 16 B granules (29): same-offset words of the 32 lanes then fall
-                                             // into 8 distinct 4-bank groups (4-way conflicts; 448 B = 28 granules gave 16-way)
+constexpr int SLOT3_B = 272;                 // per-lane staging: 16 B guard | <= 224 B of byte rows | 16 B guard + pad
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
+__device__ __forceinline__ uint64_t spread7(uint32_t x) {       // bit j -> byte j (see dmp_2d.cu)
+    return ((uint64_t)x * 0x0002040810204081ull) & 0x0101010101010101ull;
+}
+
+// biased byte (height + 1, 0 = frame) -> observation value
+template <typename ObsT, int BYTE>
+__device__ __forceinline__ ObsT obs_from_biased(uint32_t packed) {
+    if constexpr (sizeof(ObsT) == 4) {
+        return __uint_as_float(__byte_perm(packed, 0x4B000000u, 0x7650u + BYTE)) - 8388609.0f;
+    } else {
+        return obs_from_int<ObsT>((int)((packed >> (8 * BYTE)) & 0xFFu) - 1);
+    }
+}
+
+// exact path of a lane whose window holds large bytes: its observation row straight from the u16 map
 template <typename ObsT>
-__global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const DmpIO io) {
+__device__ __noinline__ void observe_u16(const uint16_t* ge, int pr, int pc, ObsT* row) {
+    for (int k = 0; k < 7; ++k)
+        for (int j = 0; j < 7; ++j) {
+            const unsigned ir = (unsigned)(pr - 6 + k), ic = (unsigned)(pc - 6 + j);
+            row[k * 7 + j] = obs_from_int<ObsT>((ir < 20u && ic < 20u) ? (int)__ldcg(ge + ir * 20u + ic) : -1);
+        }
+}
+
+template <typename ObsT>
+__global__ void __launch_bounds__(32) k3d_step_bytes(const DmpState st, const DmpIO io) {
     extern __shared__ uint4 smem_raw[];
     const int lane = threadIdx.x;
     const int64_t n = st.n_envs;
@@ -34,13 +61,16 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
     const int64_t env = env0 + (live ? lane : 0);                     // idle lanes shadow env0 but never store
 
     uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw);
-    uint8_t* slot = base + (size_t)lane * SLOT2_B;
+    uint8_t* slot = base + (size_t)lane * SLOT3_B;
     ObsT* tile = reinterpret_cast<ObsT*>(base);                       // aliases the slots (used after they are drained)
-    uint64_t* bar = reinterpret_cast<uint64_t*>(base + (size_t)32 * SLOT2_B);
+    constexpr size_t TILE_B = (size_t)32 * D3_OBS * sizeof(ObsT), SLOTS_B = (size_t)32 * SLOT3_B;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(base + (TILE_B > SLOTS_B ? TILE_B : SLOTS_B));     // behind slots AND tile
 
     uint16_t* cells = reinterpret_cast<uint16_t*>(st.cells);
     uint16_t* gwarp = cells + env0 * CELLS3D;
-    uint16_t* ge = cells + env * CELLS3D;                             // this lane's map in HBM
+    uint16_t* ge = cells + env * CELLS3D;                             // this lane's u16 map in HBM (canonical)
+    uint8_t* bwarp = bmap3(st) + env0 * CELLS3D;
+    uint8_t* be = bmap3(st) + env * CELLS3D;                          // ... and its byte shadow
     uint4* aux = reinterpret_cast<uint4*>(st.aux);
     const uint8_t* __restrict__ plans = reinterpret_cast<const uint8_t*>(st.plans);
 
@@ -77,15 +107,15 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
     e.ret = __uint_as_float(ax.z);
     e.cross = (int)ax.w;
 
-    // ---- round trip 2: every map row this step can look at, one bulk copy per env ---------------------------
+    // ---- round trip 2: every map row this step can look at, one bulk copy of byte rows per env ----------------
     const int ext = min(max(s, 1), 3);                     // a move covers at most min(s, 3) cells (move_step :104-134)
     const int row_lo = max(e.pr - 6 - (a == 3 ? ext : 0), 0);
     const int row_hi = min(e.pr + (a == 2 ? ext : 0), 19);
-    const int b_lo = (row_lo * 40) & ~15, b_hi = ((row_hi + 1) * 40 + 15) & ~15;      // 16 B granules, <= 416 B
+    const int b_lo = (row_lo * 20) & ~15, b_hi = ((row_hi + 1) * 20 + 15) & ~15;      // 16 B granules, <= 224 B
     __syncwarp();                                                                       // mbarrier init visible
     if (live) {
         mbar_arrive_expect_tx(bar, (uint32_t)(b_hi - b_lo));
-        bulk_g2s(slot + 16, reinterpret_cast<const uint8_t*>(ge) + b_lo, (uint32_t)(b_hi - b_lo), bar);
+        bulk_g2s(slot + 16, be + b_lo, (uint32_t)(b_hi - b_lo), bar);
     } else {
         mbar_arrive(bar);
     }
@@ -94,13 +124,13 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
     const int ti = min(max(o + dr * 20 + dc, 0), CELLS3D - 1);        // build target (valid whenever a brick is laid)
     int pplan = 0;
     if (a >= 4) pplan = __ldg(plans + e.plan_idx * CELLS3D + ti);     // consumed after the observation
-    // virtual map base: cell (r, c) of the staged rows lives at g[r * 20 + c]
-    uint16_t* g = reinterpret_cast<uint16_t*>(slot + 16 - b_lo);
+    // virtual map base: cell (r, c) of the staged rows lives at g[r * 20 + c]; 16 B aligned like the slot
+    uint8_t* g = slot + 16 - b_lo;
     mbar_wait(bar, 0);
 
     // ---- the six cells the decision reads: four neighbours (check_sur :88-102), second and third cell in the
     // action's direction (move_step).  Unconditional reads at an index clamped into the staged span; whether a cell
-    // is frame follows from one coordinate.
+    // is frame follows from one coordinate.  The decision only asks "== 0 / > 0 / frame": saturated bytes answer it.
     int c6[6];
     {
         const int lo_cell = row_lo * 20, hi_cell = row_hi * 20 + 19;
@@ -117,7 +147,7 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
         c6[5] = ((unsigned)(coord + 3 * sgn) < 20u) ? v3 : -1;
     }
     const bool boxed = (c6[0] != 0) && (c6[1] != 0) && (c6[2] != 0) && (c6[3] != 0);     // check_sur
-    const int nsel = (dir == 0) ? c6[0] : (dir == 1) ? c6[1] : (dir == 2) ? c6[2] : c6[3];
+    int nsel = (dir == 0) ? c6[0] : (dir == 1) ? c6[1] : (dir == 2) ? c6[2] : c6[3];
 
     bool done = false, tail = true;
     bool built = false, boxed_penalty = false;
@@ -132,6 +162,7 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
         // (b) build on neighbour a-4 unless it is frame
         bool open_after = (c6[0] == 0) || (c6[1] == 0) || (c6[2] == 0) || (c6[3] == 0);
         if (a <= 7 && nsel != -1) {
+            if (nsel == 255) nsel = (int)__ldcg(ge + ti);             // saturated byte: the true height (never in practice)
             built = true;
             newh = nsel + 1;
             e.cb += 1;
@@ -149,24 +180,56 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
     }
     if (tail) done = (e.cs >= st.total_step) || (!dynamic && boxed);
     if (built) {
-        g[ti] = (uint16_t)newh;                          // patch the staged rows ...
-        if (live) ge[ti] = (uint16_t)newh;               // ... and write the brick through to HBM
+        g[ti] = sat_u8(newh);                            // patch the staged rows ...
+        if (live) {
+            ge[ti] = (uint16_t)newh;                     // ... and write the brick through to both maps
+            be[ti] = sat_u8(newh);
+        }
     }
 
     // ---- (c) observation: window -> registers, then the warp's [32][51] tile over the drained slots ----------
     bool bulk_pending = false;
     if (io.obs) {
-        uint32_t u[7][4];
-        window_regs(g, e, u);
+        // the seven window rows as 2 words of biased bytes each (height + 1, 0 = frame)
+        uint32_t u0[7], u1[7];
+        uint32_t big = 0;                                // OR of the window's bytes: bit 7 set = some height >= 128
+        {
+            const uint32_t cv = (COLVALID >> (e.pc - 3)) & 0x7Fu;     // window column j lies inside the plan area
+            const uint64_t one = spread7(cv);                          // 0x01 per valid byte
+            const uint32_t b0 = (uint32_t)one, b1 = (uint32_t)(one >> 32);
+            const uint32_t m0 = b0 * 0xFFu, m1 = b1 * 0xFFu;           // 0xFF per valid byte (no carries)
+            const int c0 = e.pc - 6;                                    // interior column of window column 0 (may be < 0)
+            const int shb = (c0 & 3) * 8;                               // the same for every row: rows are 5 words apart
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const int ir = e.pr - 6 + k;                            // interior row of window row k
+                const bool rowvalid = (unsigned)ir < 20u;
+                const int irc = min(max(ir, row_lo), row_hi);           // rows outside the map re-read a staged row, masked
+                const uint32_t* rw = reinterpret_cast<const uint32_t*>(g + ((irc * 20 + c0) & ~3));
+                const uint32_t x0 = rw[0], x1 = rw[1], x2 = rw[2];     // over-reads stay inside the 16 B guards
+                const uint32_t q0 = __funnelshift_r(x0, x1, shb) & m0, q1 = __funnelshift_r(x1, x2, shb) & m1;
+                big |= rowvalid ? (q0 | q1) : 0u;
+                u0[k] = rowvalid ? (q0 + b0) : 0u;
+                u1[k] = rowvalid ? (q1 + b1) : 0u;
+            }
+        }
+        const bool large = (big & 0x80808080u) != 0u;
         __syncwarp();                                    // every lane has read its slot
         ObsT* row = tile + lane * D3_OBS;
+        if (!large) {
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            ObsT dummy;
-            emit_pair<ObsT>(u[k][0], row[k * 7 + 0], row[k * 7 + 1]);
-            emit_pair<ObsT>(u[k][1], row[k * 7 + 2], row[k * 7 + 3]);
-            emit_pair<ObsT>(u[k][2], row[k * 7 + 4], row[k * 7 + 5]);
-            emit_pair<ObsT>(u[k][3], row[k * 7 + 6], dummy);
+            for (int k = 0; k < 7; ++k) {
+                ObsT* o7 = row + k * 7;
+                o7[0] = obs_from_biased<ObsT, 0>(u0[k]);
+                o7[1] = obs_from_biased<ObsT, 1>(u0[k]);
+                o7[2] = obs_from_biased<ObsT, 2>(u0[k]);
+                o7[3] = obs_from_biased<ObsT, 3>(u0[k]);
+                o7[4] = obs_from_biased<ObsT, 0>(u1[k]);
+                o7[5] = obs_from_biased<ObsT, 1>(u1[k]);
+                o7[6] = obs_from_biased<ObsT, 2>(u1[k]);
+            }
+        } else {
+            observe_u16<ObsT>(ge, e.pr, e.pc, row);      // after the write-through above: sees this step's brick
         }
         obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, st.total_step, row[49], row[50]);
         ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + env0 * D3_OBS;
@@ -212,13 +275,14 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
         e.pr = e.pc = D2_LO; e.cb = e.cs = 0; e.ret = 0.f; e.cross = 0;
     }
     unsigned dm = __ballot_sync(FULL, fin);
-    while (dm) {                                            // the warp clears each finished env's map in HBM
+    while (dm) {                                            // the warp clears each finished env's maps in HBM
         const int src = __ffs(dm) - 1;
         dm &= dm - 1;
         if (lane < 25) {
             uint4* gg = reinterpret_cast<uint4*>(gwarp + src * CELLS3D) + 2 * lane;
             const uint4 z = make_uint4(0, 0, 0, 0);
             gg[0] = z; gg[1] = z;
+            reinterpret_cast<uint4*>(bwarp + src * CELLS3D)[lane] = z;
         }
     }
     if (live) {
@@ -231,28 +295,31 @@ __global__ void __launch_bounds__(32) k3d_step_span(const DmpState st, const Dmp
 }
 
 template <typename ObsT>
-int launch_span(const DmpState& st, const DmpIO& io, cudaStream_t s) {
-    static_assert(32 * D3_OBS * sizeof(ObsT) <= 32 * SLOT2_B, "the observation tile must fit the drained slots");
-    const size_t smem = (size_t)32 * SLOT2_B + 16;
+int launch_bytes(const DmpState& st, const DmpIO& io, cudaStream_t s) {
+    // f64 observations: the tile (13 KB) is larger than the 32 slots
+    constexpr size_t TILE_B = (size_t)32 * D3_OBS * sizeof(ObsT);
+    constexpr size_t SLOTS_B = (size_t)32 * SLOT3_B;
+    static_assert(SLOTS_B % 16 == 0 && TILE_B % 16 == 0, "the mbarrier behind slots / tile must be 8 B aligned");
+    const size_t smem = (TILE_B > SLOTS_B ? TILE_B : SLOTS_B) + 16;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k3d_step_span<ObsT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k3d_step_bytes<ObsT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return dmp_set_error(e);
-        e = cudaFuncSetAttribute(k3d_step_span<ObsT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        e = cudaFuncSetAttribute(k3d_step_bytes<ObsT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return dmp_set_error(e);
         attr_done = true;
     }
     const unsigned blocks = (unsigned)((st.n_envs + 31) / 32);
-    return dmp_set_error(dmp_launch_pdl(k3d_step_span<ObsT>, blocks, 32u, smem, s, st, io));
+    return dmp_set_error(dmp_launch_pdl(k3d_step_bytes<ObsT>, blocks, 32u, smem, s, st, io));
 }
 
 }  // namespace
 
-int dmp3d_step_span(const DmpState& st, const DmpIO& io, cudaStream_t s) {
+int dmp3d_step_bytes(const DmpState& st, const DmpIO& io, cudaStream_t s) {
     switch (io.obs_kind) {
-        case DMP_OBS_F32: return launch_span<float>(st, io, s);
-        case DMP_OBS_F64: return launch_span<double>(st, io, s);
-        case DMP_OBS_I16: return launch_span<int16_t>(st, io, s);
+        case DMP_OBS_F32: return launch_bytes<float>(st, io, s);
+        case DMP_OBS_F64: return launch_bytes<double>(st, io, s);
+        case DMP_OBS_I16: return launch_bytes<int16_t>(st, io, s);
     }
     return DMP_EINVAL;
 }

@@ -220,6 +220,16 @@ inline cudaError_t dmp_launch_pdl(void (*kern)(KArgs...), unsigned blocks, unsig
 }
 
 int dmp_set_error(cudaError_t e);   // records e, returns DMP_OK / DMP_ECUDA
+
+// 3D: the byte shadow of the height maps, u8[n][400] behind the u16 maps (include/dmp.h): byte = min(height, 255).
+// The hot kernels (dmp_3d_roll.cu, dmp_3d_step3.cu) stage it instead of the u16 maps and write every brick through to
+// both; the cross-check kernels, the stage kernels and dmp_import_state only know the u16 maps and are followed by
+// dmp3d_sync_bytes(), which rebuilds the shadow.
+__host__ __device__ inline uint8_t* bmap3(const DmpState& st) {
+    return reinterpret_cast<uint8_t*>(st.cells) + (size_t)st.n_envs * (CELLS3D * 2);
+}
+__device__ __forceinline__ uint8_t sat_u8(int h) { return (uint8_t)min(h, 255); }
+int dmp3d_sync_bytes(const DmpState& st, cudaStream_t s);
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // per-dimension entry points (defined in dmp_1d.cu / dmp_2d.cu / dmp_3d.cu)
@@ -230,6 +240,7 @@ int dmp3d_tile_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t 
 int dmp3d_cache_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);
 int dmp3d_step_rows(const DmpState& st, const DmpIO& io, cudaStream_t s);
 int dmp3d_step_span(const DmpState& st, const DmpIO& io, cudaStream_t s);
+int dmp3d_step_bytes(const DmpState& st, const DmpIO& io, cudaStream_t s);
 int dmp1d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs, int obs_kind, cudaStream_t s);
 int dmp2d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs, int obs_kind, cudaStream_t s);
 int dmp3d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs, int obs_kind, cudaStream_t s);

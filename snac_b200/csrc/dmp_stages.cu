@@ -330,7 +330,8 @@ int dmp_stage_move(const DmpState* st, const DmpIO* io, int32_t* scratch, void* 
 int dmp_stage_deposit(const DmpState* st, const DmpIO* io, int32_t* scratch, void* stream) {
     if (!stage_args_ok(st, io, scratch)) return DMP_EINVAL;
     k_stage_deposit<<<sblocks(st->n_envs), SB, 0, as_stream(stream)>>>(*st, *io, scratch);
-    return dmp_set_error(cudaGetLastError());
+    const int rc = dmp_set_error(cudaGetLastError());
+    return (rc != DMP_OK || st->dim != 3) ? rc : dmp3d_sync_bytes(*st, as_stream(stream));     // byte shadow of the maps
 }
 
 int dmp_stage_observe(const DmpState* st, const DmpIO* io, int32_t* scratch, void* stream) {
@@ -368,7 +369,8 @@ int dmp_stage_done_reset(const DmpState* st, const DmpIO* io, int32_t* scratch, 
     if (!stage_args_ok(st, io, scratch) || !io->done) return DMP_EINVAL;
     if (!st->ep_cnt || !st->ep_len || !st->ep_ret || !st->ep_iou) return DMP_EINVAL;
     k_stage_done_reset<<<sblocks(st->n_envs), SB, 0, as_stream(stream)>>>(*st, *io);
-    return dmp_set_error(cudaGetLastError());
+    const int rc = dmp_set_error(cudaGetLastError());
+    return (rc != DMP_OK || st->dim != 3) ? rc : dmp3d_sync_bytes(*st, as_stream(stream));
 }
 
 }  // extern "C"

@@ -311,7 +311,9 @@ def test_3d_kernels_agree(dynamic, K):
     plans = load_plans(3, "dense", "train") if dynamic else None
     n = 333                                                   # ragged last warp
     outs = {}
-    for kind in "wtcsr":                                     # "s": the default dispatch (row-span kernel for K = 1), "r": first-generation rows kernel
+    # "d": the default dispatch (byte cache for K > 1, byte-row kernel for K = 1); "s" / "r": second- / first-generation
+    # single-step kernels over the u16 maps.  The compared `cells` hold the u16 maps AND their byte shadow.
+    for kind in "wtcdsr":
         env = make_gpu(3, dynamic, n, 0, plans, auto_reset=True, env_base=99, seed=SEED, normalise=dynamic,
                        obs_dtype=torch.float64 if dynamic else torch.float32)
         env.reset()
@@ -324,7 +326,7 @@ def test_3d_kernels_agree(dynamic, K):
         st = env.get_state()
         outs[kind] = (res, st["cells"].clone(), st["aux"].clone(), [x.clone() for x in env.episode_stats()])
         env.check_errors()
-    for kind in "tcsr":
+    for kind in "tcdsr":
         for a, b in zip(outs["w"][0], outs[kind][0]):
             for x, y in zip(a, b):
                 assert torch.equal(x, y), kind
@@ -333,11 +335,11 @@ def test_3d_kernels_agree(dynamic, K):
             assert torch.equal(x, y), kind
 
 
-@pytest.mark.parametrize("kind", ["c", "t", "s1", "r1"])
+@pytest.mark.parametrize("kind", ["c", "t", "d1", "s1", "r1"])
 @pytest.mark.parametrize("dynamic", [False, True])
 def test_3d_tall_columns_match_oracle(kind, dynamic):
-    """Heights around and far beyond the byte range (252..256, 300, 40000) next to the agent: builds on top of
-    them, walks blocked by them and windows over them must equal the oracle's."""
+    """Heights around the byte paths' thresholds and far beyond the byte range (126..129, 252..256, 300, 40000) next to
+    the agent: builds on top of them, walks blocked by them and windows over them must equal the oracle's."""
     plans = load_plans(3, "dense", "train") if dynamic else None
     n, K = 70, 48
     rng = np.random.RandomState(11)
@@ -347,7 +349,7 @@ def test_3d_tall_columns_match_oracle(kind, dynamic):
     env.reset(plan_idx=p0)
     ob.reset(p0)
     g, sc = ob.export()
-    tall_values = [252, 253, 254, 255, 256, 300, 40000]
+    tall_values = [126, 127, 128, 129, 252, 253, 254, 255, 256, 300, 40000]
     for i, e in enumerate(ob.envs):
         r, c = int(rng.randint(5, 21)), int(rng.randint(5, 21))
         e.pos = [r, c]
@@ -364,7 +366,7 @@ def test_3d_tall_columns_match_oracle(kind, dynamic):
 
     def run():
         ta, ts = torch.as_tensor(acts, device=env.device), torch.as_tensor(sizes, device=env.device)
-        if kind in ("s1", "r1"):                              # step by step through a single-step kernel
+        if kind in ("d1", "s1", "r1"):                        # step by step through a single-step kernel
             outs = [[x.clone() for x in env.step(ta[k], ts[k])] for k in range(K)]
             out = [torch.stack([o[i] for o in outs]) for i in range(3)]
         else:
@@ -379,6 +381,10 @@ def test_3d_tall_columns_match_oracle(kind, dynamic):
     st = env.export_state()
     assert np.array_equal(st["grid"].cpu().numpy().reshape(g_ref.shape), g_ref)
     assert np.array_equal(st["scalars"].cpu().numpy()[:, :4], sc_ref[:, :4])
+    # the byte shadow behind the u16 maps is min(height, 255) whichever kernel wrote it
+    raw = env.get_state()["cells"].cpu().numpy()
+    shadow = raw[n * 800:].reshape(n, 20, 20)
+    assert np.array_equal(shadow, np.minimum(g_ref.reshape(n, 26, 26)[:, 3:23, 3:23], 255).astype(np.uint8))
     assert g_ref.max() > 40000 or g_ref.max() >= 254
     assert np.array_equal(env.iou().cpu().numpy(), ob.iou(), equal_nan=True)
 
