@@ -17,6 +17,7 @@
 // never: plan height is 6).  Bricks are written through to both maps.
 // Semantics: Env/3D/DMP_simulator_3d_static_circle.py:67-276 and
 // Env/3D/DMP_simulator_3d_dynamic_triangle_usedata.py:45-277 (see dmp_3d.cu for the line-by-line citations).
+#include <stdlib.h>
 #include "dmp_3d_u16.cuh"
 
 namespace {
@@ -50,7 +51,16 @@ __device__ __noinline__ void observe_u16(const uint16_t* ge, int pr, int pc, Obs
         }
 }
 
-template <typename ObsT>
+// 16 B global -> shared copy on the load/store path (LDGSTS), L1 bypassed
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+
+// LSU = true: the byte rows of a lane come in as up to 14 per-lane 16 B cp.async copies (LDGSTS) instead of one bulk
+// async copy per lane.  A bulk copy occupies the SM's copy engine for tens of cycles whatever its size, and a vector step
+// issues one per env: 1 771 per SM and step, which bounded the u16 span kernel and the first cut of this one at ~29 us per
+// step whatever the occupancy.  LDGSTS runs on the load/store path at ~8 cycles per warp instruction.
+template <typename ObsT, bool LSU>
 __global__ void __launch_bounds__(32) k3d_step_bytes(const DmpState st, const DmpIO io) {
     extern __shared__ uint4 smem_raw[];
     const int lane = threadIdx.x;
@@ -74,7 +84,7 @@ __global__ void __launch_bounds__(32) k3d_step_bytes(const DmpState st, const Dm
     uint4* aux = reinterpret_cast<uint4*>(st.aux);
     const uint8_t* __restrict__ plans = reinterpret_cast<const uint8_t*>(st.plans);
 
-    if (lane == 0) mbar_init(bar, 32);
+    if (!LSU && lane == 0) mbar_init(bar, 32);
     pdl_launch_dependents();
     pdl_wait();                                                       // the previous step's state is visible from here
     // ---- round trip 1: scalar state (the draws do not depend on it and overlap its latency).  16 B per env: the whole
@@ -112,12 +122,22 @@ __global__ void __launch_bounds__(32) k3d_step_bytes(const DmpState st, const Dm
     const int row_lo = max(e.pr - 6 - (a == 3 ? ext : 0), 0);
     const int row_hi = min(e.pr + (a == 2 ? ext : 0), 19);
     const int b_lo = (row_lo * 20) & ~15, b_hi = ((row_hi + 1) * 20 + 15) & ~15;      // 16 B granules, <= 224 B
-    __syncwarp();                                                                       // mbarrier init visible
-    if (live) {
-        mbar_arrive_expect_tx(bar, (uint32_t)(b_hi - b_lo));
-        bulk_g2s(slot + 16, be + b_lo, (uint32_t)(b_hi - b_lo), bar);
+    if constexpr (LSU) {
+        const uint32_t sdst = smem_u32(slot + 16);
+        const uint8_t* src = be + b_lo;
+        const int ng = live ? ((b_hi - b_lo) >> 4) : 0;                                 // 16 B granules: <= 14
+#pragma unroll
+        for (int i = 0; i < 14; ++i)
+            if (i < ng) cp_async16(sdst + 16 * i, src + 16 * i);
+        asm volatile("cp.async.commit_group;" ::: "memory");
     } else {
-        mbar_arrive(bar);
+        __syncwarp();                                                                   // mbarrier init visible
+        if (live) {
+            mbar_arrive_expect_tx(bar, (uint32_t)(b_hi - b_lo));
+            bulk_g2s(slot + 16, be + b_lo, (uint32_t)(b_hi - b_lo), bar);
+        } else {
+            mbar_arrive(bar);
+        }
     }
     const int total_brick = __ldg(st.plan_total + e.plan_idx);
     const int o = (e.pr - 3) * 20 + (e.pc - 3);
@@ -126,7 +146,8 @@ __global__ void __launch_bounds__(32) k3d_step_bytes(const DmpState st, const Dm
     if (a >= 4) pplan = __ldg(plans + e.plan_idx * CELLS3D + ti);     // consumed after the observation
     // virtual map base: cell (r, c) of the staged rows lives at g[r * 20 + c]; 16 B aligned like the slot
     uint8_t* g = slot + 16 - b_lo;
-    mbar_wait(bar, 0);
+    if constexpr (LSU) asm volatile("cp.async.wait_group 0;" ::: "memory");             // a lane reads only its own slot
+    else mbar_wait(bar, 0);
 
     // ---- the six cells the decision reads: four neighbours (check_sur :88-102), second and third cell in the
     // action's direction (move_step).  Unconditional reads at an index clamped into the staged span; whether a cell
@@ -294,23 +315,31 @@ __global__ void __launch_bounds__(32) k3d_step_bytes(const DmpState st, const Dm
     if (bulk_pending) warp_tile_bulk_wait(lane);                        // the tile must outlive the copy that reads it
 }
 
-template <typename ObsT>
-int launch_bytes(const DmpState& st, const DmpIO& io, cudaStream_t s) {
+template <typename ObsT, bool LSU>
+int launch_bytes_t(const DmpState& st, const DmpIO& io, cudaStream_t s) {
     // f64 observations: the tile (13 KB) is larger than the 32 slots
     constexpr size_t TILE_B = (size_t)32 * D3_OBS * sizeof(ObsT);
     constexpr size_t SLOTS_B = (size_t)32 * SLOT3_B;
     static_assert(SLOTS_B % 16 == 0 && TILE_B % 16 == 0, "the mbarrier behind slots / tile must be 8 B aligned");
     const size_t smem = (TILE_B > SLOTS_B ? TILE_B : SLOTS_B) + 16;
-    static bool attr_done = false;
+    static bool attr_done = false;           // per instantiation
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k3d_step_bytes<ObsT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k3d_step_bytes<ObsT, LSU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return dmp_set_error(e);
-        e = cudaFuncSetAttribute(k3d_step_bytes<ObsT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        e = cudaFuncSetAttribute(k3d_step_bytes<ObsT, LSU>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return dmp_set_error(e);
         attr_done = true;
     }
     const unsigned blocks = (unsigned)((st.n_envs + 31) / 32);
-    return dmp_set_error(dmp_launch_pdl(k3d_step_bytes<ObsT>, blocks, 32u, smem, s, st, io));
+    return dmp_set_error(dmp_launch_pdl(k3d_step_bytes<ObsT, LSU>, blocks, 32u, smem, s, st, io));
+}
+
+// DMP_3D_STEP_COPY (tuning switch): a = per-lane cp.async copies of the byte rows (default), b = one bulk async copy per lane
+template <typename ObsT>
+int launch_bytes(const DmpState& st, const DmpIO& io, cudaStream_t s) {
+    const char* v = getenv("DMP_3D_STEP_COPY");
+    if (v && v[0] == 'b') return launch_bytes_t<ObsT, false>(st, io, s);
+    return launch_bytes_t<ObsT, true>(st, io, s);
 }
 
 }  // namespace
