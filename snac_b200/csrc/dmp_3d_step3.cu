@@ -24,7 +24,8 @@ namespace {
 
 using namespace u16map;
 
-constexpr int SLOT3_B = 272;                 // per-lane staging: 16 B guard | <= 224 B of byte rows | 16 B guard + pad
+constexpr int SLOT3_B = 240;                 // per-lane staging: 16 B guard | <= 224 B of byte rows.  Word reads of the window
+                                             // run up to 8 B past the rows: into the next lane's guard (masked columns)
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint64_t spread7(uint32_t x) {       // bit j -> byte j (see dmp_2d.cu)
@@ -51,6 +52,12 @@ __device__ __noinline__ void observe_u16(const uint16_t* ge, int pr, int pc, Obs
         }
 }
 
+// per-warp shared memory: 32 slots, or the observation tile built over them when that is larger (f64)
+template <typename ObsT>
+__host__ __device__ constexpr size_t warp_area_bytes() {
+    return (size_t)32 * D3_OBS * sizeof(ObsT) > (size_t)32 * SLOT3_B ? (size_t)32 * D3_OBS * sizeof(ObsT) : (size_t)32 * SLOT3_B;
+}
+
 // 16 B global -> shared copy on the load/store path (LDGSTS), L1 bypassed
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
@@ -61,20 +68,22 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
 // issues one per env: 1 771 per SM and step, which bounded the u16 span kernel and the first cut of this one at ~29 us per
 // step whatever the occupancy.  LDGSTS runs on the load/store path at ~8 cycles per warp instruction.
 template <typename ObsT, bool LSU>
-__global__ void __launch_bounds__(32) k3d_step_bytes(const DmpState st, const DmpIO io) {
+__global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, const DmpIO io) {
     extern __shared__ uint4 smem_raw[];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int64_t n = st.n_envs;
-    const int64_t env0 = (int64_t)blockIdx.x * 32;
+    const int64_t env0 = ((int64_t)blockIdx.x * wpb + warp) * 32;
+    if (env0 >= n) return;                                            // whole warp leaves together (no block-wide sync below)
     const int nvalid = (int)min((int64_t)32, n - env0);
     const bool live = lane < nvalid;
     const int64_t env = env0 + (live ? lane : 0);                     // idle lanes shadow env0 but never store
 
-    uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw);
+    // shared memory: [wpb] warp areas (32 slots, re-used as the warp's observation tile) | [wpb] mbarriers | 16 B pad
+    constexpr size_t AREA_B = warp_area_bytes<ObsT>();
+    uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw) + (size_t)warp * AREA_B;
     uint8_t* slot = base + (size_t)lane * SLOT3_B;
     ObsT* tile = reinterpret_cast<ObsT*>(base);                       // aliases the slots (used after they are drained)
-    constexpr size_t TILE_B = (size_t)32 * D3_OBS * sizeof(ObsT), SLOTS_B = (size_t)32 * SLOT3_B;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(base + (TILE_B > SLOTS_B ? TILE_B : SLOTS_B));     // behind slots AND tile
+    uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_raw) + (size_t)wpb * AREA_B) + warp;
 
     uint16_t* cells = reinterpret_cast<uint16_t*>(st.cells);
     uint16_t* gwarp = cells + env0 * CELLS3D;
@@ -315,23 +324,28 @@ __global__ void __launch_bounds__(32) k3d_step_bytes(const DmpState st, const Dm
     if (bulk_pending) warp_tile_bulk_wait(lane);                        // the tile must outlive the copy that reads it
 }
 
+// Launch shape: what matters is how many warps are resident per SM, because the grid of a vector step is only a few
+// waves deep (8 192 warps at BASELINE's 262 144 envs): 23 resident warps per SM are 2.4 waves and cost three rounds,
+// 28 are 1.98 waves and cost two.  Two-warp blocks of 240 B slots fit 14 blocks = 28 warps per SM (the driver reserves
+// 1 KB per block, so single-warp blocks stop at 27).  DMP_3D_STEP_WPB overrides the warps per block.
 template <typename ObsT, bool LSU>
 int launch_bytes_t(const DmpState& st, const DmpIO& io, cudaStream_t s) {
-    // f64 observations: the tile (13 KB) is larger than the 32 slots
-    constexpr size_t TILE_B = (size_t)32 * D3_OBS * sizeof(ObsT);
-    constexpr size_t SLOTS_B = (size_t)32 * SLOT3_B;
-    static_assert(SLOTS_B % 16 == 0 && TILE_B % 16 == 0, "the mbarrier behind slots / tile must be 8 B aligned");
-    const size_t smem = (TILE_B > SLOTS_B ? TILE_B : SLOTS_B) + 16;
-    static bool attr_done = false;           // per instantiation
-    if (!attr_done) {
+    static_assert(warp_area_bytes<ObsT>() % 16 == 0, "warp areas and the mbarriers behind them must stay 16 B aligned");
+    const char* wv = getenv("DMP_3D_STEP_WPB");
+    int wpb = wv ? atoi(wv) : 2;
+    if (wpb < 1 || wpb > 4) wpb = 2;                         // __launch_bounds__(128)
+    const size_t smem = (size_t)wpb * warp_area_bytes<ObsT>() + (size_t)wpb * 8 + 16;
+    static size_t attr_smem = 0;                             // per instantiation
+    if (smem > attr_smem) {
         cudaError_t e = cudaFuncSetAttribute(k3d_step_bytes<ObsT, LSU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return dmp_set_error(e);
         e = cudaFuncSetAttribute(k3d_step_bytes<ObsT, LSU>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return dmp_set_error(e);
-        attr_done = true;
+        attr_smem = smem;
     }
-    const unsigned blocks = (unsigned)((st.n_envs + 31) / 32);
-    return dmp_set_error(dmp_launch_pdl(k3d_step_bytes<ObsT, LSU>, blocks, 32u, smem, s, st, io));
+    const int64_t warps = (st.n_envs + 31) / 32;
+    const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
+    return dmp_set_error(dmp_launch_pdl(k3d_step_bytes<ObsT, LSU>, blocks, (unsigned)(wpb * 32), smem, s, st, io));
 }
 
 // DMP_3D_STEP_COPY (tuning switch): a = per-lane cp.async copies of the byte rows (default), b = one bulk async copy per lane
