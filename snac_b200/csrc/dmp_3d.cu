@@ -26,7 +26,7 @@ struct Env3 {
 };
 
 __device__ __forceinline__ void unpack3(const uint4& a, Env3& e) {
-    e.pr = a.x & 0xFF; e.pc = (a.x >> 8) & 0xFF; e.plan_idx = a.x >> 16;
+    e.pr = a.x & 0x7F; e.pc = (a.x >> 8) & 0xFF; e.plan_idx = a.x >> 16;      // bit 7: AUX3_TALL, not this struct's business
     e.cb = a.y & 0xFFFF; e.cs = a.y >> 16;
     e.ret = __uint_as_float(a.z);
     e.cross = (int)a.w;
@@ -316,21 +316,54 @@ __global__ void k3d_import(const DmpState st, const int32_t* __restrict__ grid, 
     if (lane == 0) aux[env] = pack3(e);
 }
 
-// byte shadow := min(height, 255) for every env (one 16 B vector of bytes per thread)
+// bytes := min(wide, 255) and flag := any(wide >= TALL3) for every env; one warp per env
 __global__ void k3d_sync_bytes(const DmpState st) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;                 // vector index: 25 per env
-    if (i >= st.n_envs * (CELLS3D / 16)) return;
-    const uint4* src = reinterpret_cast<const uint4*>(st.cells) + 2 * i;
-    const uint4 a = src[0], b = src[1];
-    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    uint32_t o[4];
+    const int lane = threadIdx.x & 31;
+    const int64_t env = (int64_t)blockIdx.x * WPB3 + (threadIdx.x >> 5);
+    if (env >= st.n_envs) return;
+    bool tall = false;
+    if (lane < 25) {                                     // 16 cells per lane
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(st.cells) + env * CELLS3D) + 2 * lane;
+        const uint4 a = src[0], b = src[1];
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t o[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const uint32_t h0 = min(w[2 * q] & 0xFFFFu, 255u), h1 = min(w[2 * q] >> 16, 255u);
-        const uint32_t h2 = min(w[2 * q + 1] & 0xFFFFu, 255u), h3 = min(w[2 * q + 1] >> 16, 255u);
-        o[q] = h0 | (h1 << 8) | (h2 << 16) | (h3 << 24);
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t h0 = w[2 * q] & 0xFFFFu, h1 = w[2 * q] >> 16, h2 = w[2 * q + 1] & 0xFFFFu, h3 = w[2 * q + 1] >> 16;
+            tall |= max(max(h0, h1), max(h2, h3)) >= (uint32_t)TALL3;
+            o[q] = min(h0, 255u) | (min(h1, 255u) << 8) | (min(h2, 255u) << 16) | (min(h3, 255u) << 24);
+        }
+        reinterpret_cast<uint4*>(bmap3(st) + env * CELLS3D)[lane] = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    reinterpret_cast<uint4*>(bmap3(st))[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    const bool any = __any_sync(FULL, tall);
+    if (lane == 0) {
+        uint32_t* ax = reinterpret_cast<uint32_t*>(reinterpret_cast<uint4*>(st.aux) + env);
+        *ax = (*ax & ~AUX3_TALL) | (any ? AUX3_TALL : 0u);
+    }
+}
+
+// wide := bytes for every env that is not tall (whose bytes are exact); optionally drops all flags afterwards
+__global__ void k3d_widen(const DmpState st, const int clear_flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t env = (int64_t)blockIdx.x * WPB3 + (threadIdx.x >> 5);
+    if (env >= st.n_envs) return;
+    uint32_t* ax = reinterpret_cast<uint32_t*>(reinterpret_cast<uint4*>(st.aux) + env);
+    const uint32_t x = *ax;
+    if (!(x & AUX3_TALL) && lane < 25) {
+        const uint4 b = reinterpret_cast<const uint4*>(bmap3(st) + env * CELLS3D)[lane];
+        const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+        uint32_t o[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            o[2 * q] = (w[q] & 0xFFu) | ((w[q] & 0xFF00u) << 8);
+            o[2 * q + 1] = ((w[q] >> 16) & 0xFFu) | ((w[q] >> 24) << 16);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(st.cells) + env * CELLS3D) + 2 * lane;
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    __syncwarp();
+    if (clear_flags && lane == 0 && (x & AUX3_TALL)) *ax = x & ~AUX3_TALL;
 }
 
 inline unsigned blocks3(int64_t n) { return (unsigned)((n + WPB3 - 1) / WPB3); }
@@ -350,24 +383,30 @@ static int dmp3d_wpe_rollout(const DmpState& st, const DmpIO& io, int K, cudaStr
 }
 
 int dmp3d_sync_bytes(const DmpState& st, cudaStream_t s) {
-    const int64_t nvec = st.n_envs * (CELLS3D / 16);
-    k3d_sync_bytes<<<(unsigned)((nvec + 255) / 256), 256, 0, s>>>(st);
+    k3d_sync_bytes<<<blocks3(st.n_envs), WPB3 * 32, 0, s>>>(st);
+    return dmp_set_error(cudaGetLastError());
+}
+int dmp3d_widen(const DmpState& st, bool clear_flags, cudaStream_t s) {
+    k3d_widen<<<blocks3(st.n_envs), WPB3 * 32, 0, s>>>(st, clear_flags ? 1 : 0);
     return dmp_set_error(cudaGetLastError());
 }
 
 int dmp3d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
     // DMP_3D_KERNEL = w (warp per env) | t (u16 tile, whole maps by bulk async copies) | c (byte cache) |
     // r / s (single step, first / second generation over the u16 maps; K == 1) forces one kernel.  Default: the
-    // byte-cache kernel for rollouts (K > 1), the byte-row kernel (dmp_3d_step3.cu) for single steps.  The forced
-    // cross-check kernels only know the u16 maps; the byte shadow is rebuilt after them.
+    // byte-cache kernel for rollouts (K > 1), the byte-row kernel (dmp_3d_step3.cu) for single steps.
     const char* v = getenv("DMP_3D_KERNEL");             // read per call: tests switch kernels in-process
     const int forced = v ? (int)v[0] : 0;
-    int rc = -1;
-    if (forced == 'w') rc = dmp3d_wpe_rollout(st, io, K, s);
-    else if (forced == 't') rc = dmp3d_tile_rollout(st, io, K, s);
-    else if (forced == 'r' && K == 1) rc = dmp3d_step_rows(st, io, s);
-    else if (forced == 's' && K == 1) rc = dmp3d_step_span(st, io, s);
-    if (rc >= 0) return rc != DMP_OK ? rc : dmp3d_sync_bytes(st, s);
+    const bool legacy = forced == 'w' || forced == 't' || ((forced == 'r' || forced == 's') && K == 1);
+    if (legacy) {                                        // these only know the wide (u16) maps
+        int rc = dmp3d_widen(st, true, s);
+        if (rc != DMP_OK) return rc;
+        if (forced == 'w') rc = dmp3d_wpe_rollout(st, io, K, s);
+        else if (forced == 't') rc = dmp3d_tile_rollout(st, io, K, s);
+        else if (forced == 'r') rc = dmp3d_step_rows(st, io, s);
+        else rc = dmp3d_step_span(st, io, s);
+        return rc != DMP_OK ? rc : dmp3d_sync_bytes(st, s);
+    }
     if (forced == 'c') return dmp3d_cache_rollout(st, io, K, s);
     return K > 1 ? dmp3d_cache_rollout(st, io, K, s) : dmp3d_step_bytes(st, io, s);
 }
@@ -385,15 +424,23 @@ int dmp3d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx
 }
 
 int dmp3d_iou(const DmpState& st, double* out, cudaStream_t s) {
+    const int rc = dmp3d_widen(st, false, s);            // the kernel reads the wide maps
+    if (rc != DMP_OK) return rc;
     k3d_iou<<<blocks3(st.n_envs), WPB3 * 32, 0, s>>>(st, out);
     return dmp_set_error(cudaGetLastError());
 }
 int dmp3d_export(const DmpState& st, int32_t* grid, int32_t* scalars, float* ret, cudaStream_t s) {
+    if (grid) {
+        const int rc = dmp3d_widen(st, false, s);
+        if (rc != DMP_OK) return rc;
+    }
     k3d_export<<<blocks3(st.n_envs), WPB3 * 32, 0, s>>>(st, grid, scalars, ret);
     return dmp_set_error(cudaGetLastError());
 }
 int dmp3d_import(const DmpState& st, const int32_t* grid, const int32_t* scalars, const float* ret, cudaStream_t s) {
+    int rc = dmp3d_widen(st, true, s);                   // the kernel rewrites aux.x and sums over the wide map
+    if (rc != DMP_OK) return rc;
     k3d_import<<<blocks3(st.n_envs), WPB3 * 32, 0, s>>>(st, grid, scalars, ret);
-    const int rc = dmp_set_error(cudaGetLastError());
-    return (rc != DMP_OK || !grid) ? rc : dmp3d_sync_bytes(st, s);
+    rc = dmp_set_error(cudaGetLastError());
+    return rc != DMP_OK ? rc : dmp3d_sync_bytes(st, s);
 }

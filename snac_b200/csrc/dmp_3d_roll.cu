@@ -6,11 +6,12 @@
 // to stack 254 bricks on one cell to leave the byte range).  Halving the cache (404 B instead of 816 B per env)
 // lifts the number of resident warps per SM from 7 to 11 (f32 observations; 14 with i16), which is what this
 // latency-bound kernel needs, and an odd word stride (101) makes same-offset accesses of the 32 lanes
-// bank-conflict free.  HBM keeps the canonical u16 maps; every brick is written through.
-//   * state in : the warp's 32 byte maps are one contiguous 12 800 B span of the byte shadow (include/dmp.h): 25
-//                coalesced 128-bit loads per lane in one round trip, four 32-bit shared stores per 16 B.  An env that
-//                holds a byte >= 128 anywhere is flagged "tall" and runs entirely from the u16 map in HBM (exact,
-//                slow, practically never).
+// bank-conflict free.  HBM keeps the same bytes (dmp_common.cuh); every brick is written through.
+//   * state in : the warp's 32 byte maps are one contiguous 12 800 B span (include/dmp.h): 25 coalesced 128-bit
+//                loads per lane in one round trip, four 32-bit shared stores per 16 B.  An env whose tall flag is set
+//                (a height >= 254 somewhere) runs entirely from its wide u16 map in HBM (exact, slow, practically
+//                never); an env that reaches that height inside the launch writes its wide map out and carries on
+//                like that.  Bricks of all other envs are written through to the byte map only.
 //   * step     : neighbours / walk cells / 7x7 window are shared-memory byte reads;
 //   * obs out  : window rows are cut out of the byte map with funnel shifts, biased by +1 (0 = frame), each byte
 //                is dropped into the mantissa of 2^23 (PRMT) and turned into -1/0/h by one FADD; the warp's
@@ -29,7 +30,6 @@ constexpr int MAP_B = 404;                    // bytes per env in the cache: 400
 constexpr int FRONT = 80;                     // guard in front of env 0 of a warp: unclamped reads reach 64 B back
 constexpr int WARP_MAP_B = FRONT + 32 * MAP_B;  // 13 008 (multiple of 16); reads past the end land in the next
                                               // warp's guard or in the tiles
-constexpr int TALL = 254;                     // heights >= TALL do not fit the byte cache (+1 bias included)
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr uint32_t COLVALID = 0x7FFFF8u;      // padded columns 3..22 are inside the plan area
 constexpr size_t SMEM_MAX = 232448;           // 227 KB opt-in limit per block
@@ -48,6 +48,11 @@ __device__ __forceinline__ int dir_dc(int d) { return d == 0 ? -1 : (d == 1 ? 1 
 __device__ __forceinline__ int cell_g(const uint16_t* ge, int r, int c) {
     const unsigned ir = (unsigned)(r - 3), ic = (unsigned)(c - 3);
     return (ir < 20u && ic < 20u) ? (int)__ldcg(ge + ir * 20u + ic) : -1;
+}
+
+// an env turns tall: its wide map in HBM := the (still exact) byte cache.  Out of line, practically never.
+__device__ __noinline__ void widen_from_cache(uint16_t* ge, const uint8_t* gb) {
+    for (int i = 0; i < CELLS3D; ++i) ge[i] = gb[i];
 }
 
 // out-of-line copy for the tall-env path (keeps the hot loop small)
@@ -111,9 +116,9 @@ __device__ __forceinline__ void observe_cache(const uint8_t* gb, int pr, int pc,
     }
 }
 
-// shared memory: [WPB][WARP_MAP_B] byte maps | [WPB][32*51] ObsT tiles | [WPB] tall-env flag words
+// shared memory: [WPB][WARP_MAP_B] byte maps | [WPB][32*51] ObsT tiles
 template <typename ObsT>
-__host__ __device__ constexpr size_t warp_smem_bytes() { return (size_t)WARP_MAP_B + 32 * D3_OBS * sizeof(ObsT) + 4; }
+__host__ __device__ constexpr size_t warp_smem_bytes() { return (size_t)WARP_MAP_B + 32 * D3_OBS * sizeof(ObsT); }
 
 // TMA = true: each step's warp tile leaves through one bulk async copy (dmp_common.cuh: warp_tile_bulk_store).
 template <typename ObsT, bool TMA>
@@ -130,7 +135,6 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
     uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw);
     uint8_t* wmap = base + (size_t)warp * WARP_MAP_B + FRONT;
     ObsT* tile = reinterpret_cast<ObsT*>(base + (size_t)wpb * WARP_MAP_B) + warp * (32 * D3_OBS);
-    uint32_t* tallword = reinterpret_cast<uint32_t*>(base + (size_t)wpb * (WARP_MAP_B + 32 * D3_OBS * sizeof(ObsT))) + warp;
     uint8_t* gb = wmap + lane * MAP_B;                                // this lane's byte map
 
     uint16_t* cells = reinterpret_cast<uint16_t*>(st.cells);
@@ -143,18 +147,17 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
     const bool autoreset = io.flags & DMP_F_AUTORESET;
 
     // ---- state in: coalesced 128-bit loads of the warp's contiguous maps, packed to bytes -------------
-    if (lane == 0) *tallword = 0u;
     pdl_launch_dependents();
     pdl_wait();                                                       // the previous launch's state is visible from here
     __syncwarp();
     EnvR e{D2_LO, D2_LO, 0, 0, 0, 0.f, 0};
+    bool tall = false;
     double acc_iou = 0.0;                                             // this env's sum of episode IoUs (sequential, exact)
     {
         // the warp's 32 byte maps are one contiguous 12 800 B span of the byte shadow: 25 coalesced 128-bit loads per
         // lane, all in flight at once (ONE DRAM round trip per launch), four 32-bit shared stores per vector
         const uint4* src = reinterpret_cast<const uint4*>(bwarp);
         const int nvec = nvalid * (CELLS3D / 16);                     // 25 vectors of 16 cells per env
-        uint32_t tallbits = 0;
         constexpr int U = CELLS3D / 16;
         uint4 v[U];
 #pragma unroll
@@ -164,7 +167,8 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
         }
         if (live) {                                                   // scalar state rides along
             const uint4 a = aux[env];
-            e.pr = a.x & 0xFF; e.pc = (a.x >> 8) & 0xFF; e.plan_idx = a.x >> 16;
+            e.pr = a.x & 0x7F; e.pc = (a.x >> 8) & 0xFF; e.plan_idx = a.x >> 16;
+            tall = (a.x & AUX3_TALL) != 0u;                           // this env runs from its wide map in HBM
             e.cb = a.y & 0xFFFF; e.cs = a.y >> 16;
             e.ret = __uint_as_float(a.z);
             e.cross = (int)a.w;
@@ -174,13 +178,9 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
         for (int u = 0; u < U; ++u) {
             const int idx = u * 32 + lane;
             const int el = idx / U, j = idx - el * U;
-            // conservative: an env holding any byte >= 128 runs from the u16 map (false positives only cost speed)
-            const uint32_t any = v[u].x | v[u].y | v[u].z | v[u].w;
-            tallbits |= (any & 0x80808080u) ? (1u << el) : 0u;
             uint32_t* dst = reinterpret_cast<uint32_t*>(wmap + el * MAP_B + j * 16);
             dst[0] = v[u].x; dst[1] = v[u].y; dst[2] = v[u].z; dst[3] = v[u].w;   // lanes beyond nvec write zeros into their own slots
         }
-        if (tallbits) atomicOr(tallword, tallbits);
     }
     int total_brick = __ldg(st.plan_total + e.plan_idx);
     int errbits = 0;
@@ -193,7 +193,6 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
     uint32_t acc_cnt = 0, acc_len = 0;                                // episodes finished by this env in this launch
     float acc_ret = 0.f;                                              // (integer-valued: exact in any order)
     __syncwarp();
-    bool tall = live && ((*tallword >> lane) & 1u);                   // this env runs from HBM
     int64_t idx = env0 + lane;                                        // flat [k][env] index of this step's outputs
 
     StepDraws draws;
@@ -255,9 +254,13 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
                 pplan = ldg_u8(plans + e.plan_idx * CELLS3D + ti);             // consumed after the observation
                 if (!tall) gb[ti] = (uint8_t)newh;
                 if (live) {
-                    ge[ti] = (uint16_t)newh;                                   // write-through: canonical map ...
-                    be[ti] = sat_u8(newh);                                     // ... and its byte shadow
-                    if (newh >= TALL) tall = true;                             // the byte cache stops being exact
+                    be[ti] = sat_u8(newh);                                     // write-through to the byte map
+                    if (tall) {
+                        ge[ti] = (uint16_t)newh;                               // a tall env keeps its wide map exact
+                    } else if (newh >= TALL3) {                                // the bytes stop being exact: the env turns
+                        widen_from_cache(ge, gb);                              // tall, its wide map is made current
+                        tall = true;
+                    }
                 }
                 // neighbours after placement: only neighbour `dir` changed, and it is now > 0
                 open_after = ((dir != 0) && c6[0] == 0) || ((dir != 1) && c6[1] == 0) ||
@@ -310,6 +313,7 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
         // IoU = cross / (total_brick + count_brick - cross) (:257-276); `cross` is kept up to date by every build.
         // Episode statistics accumulate in registers and are folded into HBM once, after the last step.
         const bool fin = done && autoreset && live;
+        const bool fin_wide = fin && tall;                  // a tall env's wide map is cleared with it
         if (fin) {
             const int den = total_brick + e.cb - e.cross;
             const double iou = (e.cross == 0 && den != 0) ? 0.0 : __ddiv_rn((double)e.cross, (double)den);
@@ -327,6 +331,7 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
             tall = false;
         }
         unsigned dm = __ballot_sync(FULL, fin);
+        const unsigned dmw = __ballot_sync(FULL, fin_wide);
         while (dm) {                                        // the warp clears each finished env's map
             const int src = __ffs(dm) - 1;
             dm &= dm - 1;
@@ -334,16 +339,18 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
             sg[0] = 0u; sg[32] = 0u; sg[64] = 0u;
             if (lane < 4) sg[96] = 0u;
             if (lane < 25) {
-                uint4* gg = reinterpret_cast<uint4*>(gwarp + src * CELLS3D) + 2 * lane;
                 const uint4 z = make_uint4(0, 0, 0, 0);
-                gg[0] = z; gg[1] = z;
                 reinterpret_cast<uint4*>(bwarp + src * CELLS3D)[lane] = z;
+                if ((dmw >> src) & 1u) {
+                    uint4* gg = reinterpret_cast<uint4*>(gwarp + src * CELLS3D) + 2 * lane;
+                    gg[0] = z; gg[1] = z;
+                }
             }
         }
         __syncwarp();
     }
     if (live) {
-        aux[env] = make_uint4((uint32_t)e.pr | ((uint32_t)e.pc << 8) | ((uint32_t)e.plan_idx << 16),
+        aux[env] = make_uint4((uint32_t)e.pr | (tall ? AUX3_TALL : 0u) | ((uint32_t)e.pc << 8) | ((uint32_t)e.plan_idx << 16),
                               (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16), __float_as_uint(e.ret), (uint32_t)e.cross);
         if (acc_cnt) {                                      // this thread is the only writer of its env's statistics
             atomicAdd(st.ep_cnt + env, acc_cnt);            // fire-and-forget REDs

@@ -1,5 +1,5 @@
 // dmp_3d_step3.cu -- 3D envs, single-step kernel (K = 1, dmp_step), third generation: the rows a step looks at are
-// staged from the BYTE shadow of the height maps (include/dmp.h: u8[n][400] behind the u16 maps, byte = min(h, 255)).
+// staged from the BYTE maps (include/dmp.h: u8[n][400] behind the wide u16 maps, byte = min(h, 255)).
 //
 // dmp_3d_step2.cu (k3d_step_span) staged u16 rows: <= 416 B per env in a 464 B slot, 14.5 KB of shared memory per
 // warp, 14 resident warps per SM -- too few to hide the two dependent round trips of a step (scalar state, rows);
@@ -12,9 +12,10 @@
 // the six decision cells, the window at the new position and the brick patch are served from that span; every lane
 // pulls its window into registers, then the warp's [32][51] observation tile is built over the drained slots and
 // leaves through one bulk async copy.
-// Exactness: bytes below 255 ARE the heights.  A build on a saturated cell reads the true height from the u16 map, and a
-// lane whose window holds a byte >= 128 builds its observation row from the u16 map (both out of line, practically
-// never: plan height is 6).  Bricks are written through to both maps.
+// Exactness (dmp_common.cuh): the bytes of an env ARE its heights until one reaches 254; from then on the env is
+// flagged tall, its wide u16 map is kept exact as well, a build on a saturated byte reads the true height there and the
+// observation row comes from there (out of line, practically never: plan height is 6).  Bricks of all other envs are
+// written through to the byte map only -- a 2-byte store into a cold u16 line costs 64 B of DRAM traffic.
 // Semantics: Env/3D/DMP_simulator_3d_static_circle.py:67-276 and
 // Env/3D/DMP_simulator_3d_dynamic_triangle_usedata.py:45-277 (see dmp_3d.cu for the line-by-line citations).
 #include <stdlib.h>
@@ -42,7 +43,12 @@ __device__ __forceinline__ ObsT obs_from_biased(uint32_t packed) {
     }
 }
 
-// exact path of a lane whose window holds large bytes: its observation row straight from the u16 map
+// an env turns tall: its wide map := its (still exact) byte map, with the brick just laid.  Out of line, practically never.
+__device__ __noinline__ void widen_env(uint16_t* ge, const uint8_t* be, int ti, int newh) {
+    for (int i = 0; i < CELLS3D; ++i) ge[i] = (i == ti) ? (uint16_t)newh : (uint16_t)__ldcg(be + i);
+}
+
+// a tall env's observation row straight from its wide map
 template <typename ObsT>
 __device__ __noinline__ void observe_u16(const uint16_t* ge, int pr, int pc, ObsT* row) {
     for (int k = 0; k < 7; ++k)
@@ -121,7 +127,8 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
     const int dir = a & 3, dr = dir_dr(dir), dc = dir_dc(dir);
 
     EnvT e;
-    e.pr = ax.x & 0xFF; e.pc = (ax.x >> 8) & 0xFF; e.plan_idx = ax.x >> 16;
+    e.pr = ax.x & 0x7F; e.pc = (ax.x >> 8) & 0xFF; e.plan_idx = ax.x >> 16;
+    bool tall = live && (ax.x & AUX3_TALL);                // a height >= TALL3 somewhere: the wide map is the exact one
     e.cb = ax.y & 0xFFFF; e.cs = (ax.y >> 16) + 1;
     e.ret = __uint_as_float(ax.z);
     e.cross = (int)ax.w;
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
         // (b) build on neighbour a-4 unless it is frame
         bool open_after = (c6[0] == 0) || (c6[1] == 0) || (c6[2] == 0) || (c6[3] == 0);
         if (a <= 7 && nsel != -1) {
-            if (nsel == 255) nsel = (int)__ldcg(ge + ti);             // saturated byte: the true height (never in practice)
+            if (nsel == 255) nsel = (int)__ldcg(ge + ti);             // saturated byte (tall envs only): the true height
             built = true;
             newh = nsel + 1;
             e.cb += 1;
@@ -212,8 +219,13 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
     if (built) {
         g[ti] = sat_u8(newh);                            // patch the staged rows ...
         if (live) {
-            ge[ti] = (uint16_t)newh;                     // ... and write the brick through to both maps
-            be[ti] = sat_u8(newh);
+            be[ti] = sat_u8(newh);                       // ... and write the brick through to the byte map
+            if (tall) {
+                ge[ti] = (uint16_t)newh;                 // a tall env keeps its wide map exact
+            } else if (newh >= TALL3) {                  // the bytes stop being exact: the env turns tall and its
+                widen_env(ge, be, ti, newh);             // wide map is made current
+                tall = true;
+            }
         }
     }
 
@@ -222,7 +234,6 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
     if (io.obs) {
         // the seven window rows as 2 words of biased bytes each (height + 1, 0 = frame)
         uint32_t u0[7], u1[7];
-        uint32_t big = 0;                                // OR of the window's bytes: bit 7 set = some height >= 128
         {
             const uint32_t cv = (COLVALID >> (e.pc - 3)) & 0x7Fu;     // window column j lies inside the plan area
             const uint64_t one = spread7(cv);                          // 0x01 per valid byte
@@ -238,15 +249,13 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
                 const uint32_t* rw = reinterpret_cast<const uint32_t*>(g + ((irc * 20 + c0) & ~3));
                 const uint32_t x0 = rw[0], x1 = rw[1], x2 = rw[2];     // over-reads stay inside the 16 B guards
                 const uint32_t q0 = __funnelshift_r(x0, x1, shb) & m0, q1 = __funnelshift_r(x1, x2, shb) & m1;
-                big |= rowvalid ? (q0 | q1) : 0u;
                 u0[k] = rowvalid ? (q0 + b0) : 0u;
                 u1[k] = rowvalid ? (q1 + b1) : 0u;
             }
         }
-        const bool large = (big & 0x80808080u) != 0u;
         __syncwarp();                                    // every lane has read its slot
         ObsT* row = tile + lane * D3_OBS;
-        if (!large) {
+        if (!tall) {
 #pragma unroll
             for (int k = 0; k < 7; ++k) {
                 ObsT* o7 = row + k * 7;
@@ -259,7 +268,7 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
                 o7[6] = obs_from_biased<ObsT, 2>(u1[k]);
             }
         } else {
-            observe_u16<ObsT>(ge, e.pr, e.pc, row);      // after the write-through above: sees this step's brick
+            observe_u16<ObsT>(ge, e.pr, e.pc, row);      // tall env: the wide map, this step's brick included
         }
         obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, st.total_step, row[49], row[50]);
         ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + env0 * D3_OBS;
@@ -287,7 +296,9 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
 
     // ---- (e) finished episodes: IoU = cross / (total_brick + count_brick - cross) (:257-276) ---------------
     const bool fin = done && autoreset && live;
+    const bool fin_wide = fin && tall;                      // a tall env's wide map is cleared with it
     if (fin) {
+        tall = false;
         const int den = total_brick + e.cb - e.cross;
         const double iou = (e.cross == 0 && den != 0) ? 0.0 : __ddiv_rn((double)e.cross, (double)den);
         atomicAdd(st.ep_cnt + env, 1u);                 // fire-and-forget REDs
@@ -305,18 +316,21 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
         e.pr = e.pc = D2_LO; e.cb = e.cs = 0; e.ret = 0.f; e.cross = 0;
     }
     unsigned dm = __ballot_sync(FULL, fin);
-    while (dm) {                                            // the warp clears each finished env's maps in HBM
+    const unsigned dmw = __ballot_sync(FULL, fin_wide);
+    while (dm) {                                            // the warp clears each finished env's map in HBM
         const int src = __ffs(dm) - 1;
         dm &= dm - 1;
         if (lane < 25) {
-            uint4* gg = reinterpret_cast<uint4*>(gwarp + src * CELLS3D) + 2 * lane;
             const uint4 z = make_uint4(0, 0, 0, 0);
-            gg[0] = z; gg[1] = z;
             reinterpret_cast<uint4*>(bwarp + src * CELLS3D)[lane] = z;
+            if ((dmw >> src) & 1u) {
+                uint4* gg = reinterpret_cast<uint4*>(gwarp + src * CELLS3D) + 2 * lane;
+                gg[0] = z; gg[1] = z;
+            }
         }
     }
     if (live) {
-        stg_keep(aux + env, make_uint4((uint32_t)e.pr | ((uint32_t)e.pc << 8) | ((uint32_t)e.plan_idx << 16),
+        stg_keep(aux + env, make_uint4((uint32_t)e.pr | (tall ? AUX3_TALL : 0u) | ((uint32_t)e.pc << 8) | ((uint32_t)e.plan_idx << 16),
                                        (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16), __float_as_uint(e.ret), (uint32_t)e.cross), keep);
         if (errbits) atomicOr(st.err, errbits);
         if (st.t_dev && env == 0) st.t_dev[tslot ^ 1] = t + 1;

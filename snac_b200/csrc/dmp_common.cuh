@@ -221,15 +221,24 @@ inline cudaError_t dmp_launch_pdl(void (*kern)(KArgs...), unsigned blocks, unsig
 
 int dmp_set_error(cudaError_t e);   // records e, returns DMP_OK / DMP_ECUDA
 
-// 3D: the byte shadow of the height maps, u8[n][400] behind the u16 maps (include/dmp.h): byte = min(height, 255).
-// The hot kernels (dmp_3d_roll.cu, dmp_3d_step3.cu) stage it instead of the u16 maps and write every brick through to
-// both; the cross-check kernels, the stage kernels and dmp_import_state only know the u16 maps and are followed by
-// dmp3d_sync_bytes(), which rebuilds the shadow.
+// 3D height maps (include/dmp.h): the BYTE maps u8[n][400] behind the u16 area are what the hot kernels
+// (dmp_3d_roll.cu, dmp_3d_step3.cu) read and write.  An env is "tall" once a height reaches TALL3: its flag (bit 7 of the
+// position-row byte of aux.x) is set, its u16 "wide" map holds the exact heights and its bytes saturate at 255; the wide
+// map of every other env is stale scratch that nothing reads.  Not writing it is what the layout is for: a 2-byte store
+// into a line that is not in L2 costs a 32 B read and a 32 B write of DRAM traffic (measured: 3D rollouts 15.0 -> 19.8 G
+// env-steps/s, single steps 8.3 -> 12.2 G, profiles/README.md).
+//   dmp3d_widen(st, clear_flags) : wide map := bytes for every env that is not tall; optionally drops all flags
+//   dmp3d_sync_bytes(st)         : bytes := min(wide, 255) and flag := any(wide >= TALL3), for every env
+// The cross-check kernels, the stage kernels and import only know the wide maps: widen(clear) runs before them and
+// sync_bytes after; export / iou read the wide maps after widen(keep).
+constexpr int TALL3 = 254;                   // bytes of a non-tall env are <= 253: the +1 bias of the observation path fits
+constexpr uint32_t AUX3_TALL = 0x80u;        // aux.x bit 7 (pos_row is 3..22)
 __host__ __device__ inline uint8_t* bmap3(const DmpState& st) {
     return reinterpret_cast<uint8_t*>(st.cells) + (size_t)st.n_envs * (CELLS3D * 2);
 }
 __device__ __forceinline__ uint8_t sat_u8(int h) { return (uint8_t)min(h, 255); }
 int dmp3d_sync_bytes(const DmpState& st, cudaStream_t s);
+int dmp3d_widen(const DmpState& st, bool clear_flags, cudaStream_t s);
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // per-dimension entry points (defined in dmp_1d.cu / dmp_2d.cu / dmp_3d.cu)

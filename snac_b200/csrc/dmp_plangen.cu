@@ -200,10 +200,10 @@ __global__ void k_plans_from_state(const DmpState st, void* plans_out, int32_t* 
             dst[q] = v;
         }
     } else {
-        const uint16_t* map = reinterpret_cast<const uint16_t*>(st.cells) + i * CELLS3D;
+        const uint8_t* map = bmap3(st) + i * CELLS3D;        // the byte maps hold min(height, 255) for every env
         uint8_t* dst = reinterpret_cast<uint8_t*>(plans_out) + i * CELLS3D;
         for (int c = 0; c < CELLS3D; ++c) {
-            const int h = min((int)map[c], 255);
+            const int h = map[c];
             total += h;
             dst[c] = (uint8_t)h;
         }

@@ -317,25 +317,39 @@ bool stage_args_ok(const DmpState* st, const DmpIO* io, const int32_t* scratch) 
 }
 inline unsigned sblocks(int64_t n) { return (unsigned)((n + SB - 1) / SB); }
 
+// 3D: the stage kernels read and write the wide (u16) height maps only (dmp_common.cuh): make them current before a
+// stage and fold them back into the byte maps / tall flags after it
+int stage_enter(const DmpState* st, void* stream) {
+    return st->dim == 3 ? dmp3d_widen(*st, true, as_stream(stream)) : DMP_OK;
+}
+int stage_leave(const DmpState* st, void* stream) {
+    const int rc = dmp_set_error(cudaGetLastError());
+    return (rc != DMP_OK || st->dim != 3) ? rc : dmp3d_sync_bytes(*st, as_stream(stream));
+}
+
 }  // namespace
 
 extern "C" {
 
 int dmp_stage_move(const DmpState* st, const DmpIO* io, int32_t* scratch, void* stream) {
     if (!stage_args_ok(st, io, scratch)) return DMP_EINVAL;
+    if (const int rc = stage_enter(st, stream)) return rc;
     k_stage_move<<<sblocks(st->n_envs), SB, 0, as_stream(stream)>>>(*st, *io, scratch);
-    return dmp_set_error(cudaGetLastError());
+    return stage_leave(st, stream);
 }
 
 int dmp_stage_deposit(const DmpState* st, const DmpIO* io, int32_t* scratch, void* stream) {
     if (!stage_args_ok(st, io, scratch)) return DMP_EINVAL;
+    if (const int rc = stage_enter(st, stream)) return rc;
     k_stage_deposit<<<sblocks(st->n_envs), SB, 0, as_stream(stream)>>>(*st, *io, scratch);
-    const int rc = dmp_set_error(cudaGetLastError());
-    return (rc != DMP_OK || st->dim != 3) ? rc : dmp3d_sync_bytes(*st, as_stream(stream));     // byte shadow of the maps
+    return stage_leave(st, stream);
 }
 
 int dmp_stage_observe(const DmpState* st, const DmpIO* io, int32_t* scratch, void* stream) {
     if (!stage_args_ok(st, io, scratch) || !io->obs) return DMP_EINVAL;
+    if (io->obs_kind != DMP_OBS_F32 && io->obs_kind != DMP_OBS_F64 && io->obs_kind != DMP_OBS_I16) return DMP_EINVAL;
+    if (io->obs_kind == DMP_OBS_I16 && (io->flags & DMP_F_NORMALISE)) return DMP_EINVAL;
+    if (const int rc = stage_enter(st, stream)) return rc;
     const int D = st->dim == 1 ? D1_OBS : D2_OBS;
     const unsigned b = sblocks(st->n_envs);
     cudaError_t e = cudaSuccess;
@@ -356,21 +370,22 @@ int dmp_stage_observe(const DmpState* st, const DmpIO* io, int32_t* scratch, voi
             break;
         default: return DMP_EINVAL;
     }
-    return dmp_set_error(cudaGetLastError());
+    return stage_leave(st, stream);
 }
 
 int dmp_stage_reward(const DmpState* st, const DmpIO* io, int32_t* scratch, void* stream) {
     if (!stage_args_ok(st, io, scratch)) return DMP_EINVAL;
+    if (const int rc = stage_enter(st, stream)) return rc;
     k_stage_reward<<<sblocks(st->n_envs), SB, 0, as_stream(stream)>>>(*st, *io, scratch);
-    return dmp_set_error(cudaGetLastError());
+    return stage_leave(st, stream);
 }
 
 int dmp_stage_done_reset(const DmpState* st, const DmpIO* io, int32_t* scratch, void* stream) {
     if (!stage_args_ok(st, io, scratch) || !io->done) return DMP_EINVAL;
     if (!st->ep_cnt || !st->ep_len || !st->ep_ret || !st->ep_iou) return DMP_EINVAL;
+    if (const int rc = stage_enter(st, stream)) return rc;
     k_stage_done_reset<<<sblocks(st->n_envs), SB, 0, as_stream(stream)>>>(*st, *io);
-    const int rc = dmp_set_error(cudaGetLastError());
-    return (rc != DMP_OK || st->dim != 3) ? rc : dmp3d_sync_bytes(*st, as_stream(stream));
+    return stage_leave(st, stream);
 }
 
 }  // extern "C"

@@ -312,7 +312,7 @@ def test_3d_kernels_agree(dynamic, K):
     n = 333                                                   # ragged last warp
     outs = {}
     # "d": the default dispatch (byte cache for K > 1, byte-row kernel for K = 1); "s" / "r": second- / first-generation
-    # single-step kernels over the u16 maps.  The compared `cells` hold the u16 maps AND their byte shadow.
+    # single-step kernels over the wide (u16) maps.
     for kind in "wtcdsr":
         env = make_gpu(3, dynamic, n, 0, plans, auto_reset=True, env_base=99, seed=SEED, normalise=dynamic,
                        obs_dtype=torch.float64 if dynamic else torch.float32)
@@ -324,7 +324,10 @@ def test_3d_kernels_agree(dynamic, K):
             return res
         res = _with_kernel(kind, run)
         st = env.get_state()
-        outs[kind] = (res, st["cells"].clone(), st["aux"].clone(), [x.clone() for x in env.episode_stats()])
+        # heights as exported, the byte maps behind the wide maps (the wide map of an env that is not tall is scratch),
+        # scalar state incl. the tall flags
+        outs[kind] = (res, torch.cat([env.export_state()["grid"].reshape(-1), st["cells"][n * 800:].to(torch.int32)]),
+                      st["aux"].clone(), [x.clone() for x in env.episode_stats()])
         env.check_errors()
     for kind in "tcdsr":
         for a, b in zip(outs["w"][0], outs[kind][0]):
@@ -381,10 +384,14 @@ def test_3d_tall_columns_match_oracle(kind, dynamic):
     st = env.export_state()
     assert np.array_equal(st["grid"].cpu().numpy().reshape(g_ref.shape), g_ref)
     assert np.array_equal(st["scalars"].cpu().numpy()[:, :4], sc_ref[:, :4])
-    # the byte shadow behind the u16 maps is min(height, 255) whichever kernel wrote it
+    # the byte maps behind the wide maps are min(height, 255) whichever kernel wrote them, and exactly the envs holding
+    # a height >= 254 carry the tall flag (bit 7 of aux.x)
     raw = env.get_state()["cells"].cpu().numpy()
     shadow = raw[n * 800:].reshape(n, 20, 20)
-    assert np.array_equal(shadow, np.minimum(g_ref.reshape(n, 26, 26)[:, 3:23, 3:23], 255).astype(np.uint8))
+    interior = g_ref.reshape(n, 26, 26)[:, 3:23, 3:23]
+    assert np.array_equal(shadow, np.minimum(interior, 255).astype(np.uint8))
+    flags = (env.get_state()["aux"].cpu().numpy().view(np.uint32).reshape(n, 4)[:, 0] >> 7) & 1
+    assert np.array_equal(flags.astype(bool), interior.reshape(n, -1).max(axis=1) >= 254)
     assert g_ref.max() > 40000 or g_ref.max() >= 254
     assert np.array_equal(env.iou().cpu().numpy(), ob.iou(), equal_nan=True)
 
