@@ -328,6 +328,17 @@ def run_ours(args):
         S, grid = {1: (5, 60), 2: (6, 50), 3: (6, 800)}[dim]
         return act + D * 4 + 5 + (2 * S + 8 + 2 * grid) / KL + E
 
+    def b_layout_of(KL, mean_len=None):
+        """The same formula with the bytes of THIS repo's 3D layout (byte maps: window 49 x 1 B + 1 B brick, 400 B maps,
+        E = 800/L): what a kernel on this layout has to move at least.  1D/2D: identical to b_alg_of."""
+        if dim != 3:
+            return b_alg_of(KL, mean_len)
+        act = 0 if act_pool is None else 1
+        E = (800.0 / mean_len) if mean_len else 0.0
+        if KL == 1:
+            return b_alg_step - 50 - 1 + act + E
+        return act + D * 4 + 5 + (2 * 6 + 8 + 2 * 400) / KL + E
+
     KL = 1 if args.mode == "step" else args.rollout_k
     ms, K_eff, W_eff, launches, ring, clocks = timed_run(KL, K, W)
     other = None
@@ -345,9 +356,11 @@ def run_ours(args):
         ob = b_alg_of(1 if KL > 1 else args.rollout_k, mean_len)
         other["bytes_per_env_step"] = ob
         other["roofline_frac"] = (other["value"] / world) * ob / 1e9 / peak
+        other["roofline_frac_this_layout"] = (other["value"] / world) * b_layout_of(1 if KL > 1 else args.rollout_k, mean_len) / 1e9 / peak
     value = total_envs * K_eff / (ms * 1e-3)
     per_gpu_steps_s = n * K_eff / (ms * 1e-3)
     achieved = per_gpu_steps_s * b_alg / 1e9
+    b_lay = b_layout_of(KL, mean_len)
 
     # ---- e2e: the reference-facing call with HOST buffers (actions in, obs/reward/done out) -------
     from snac_b200.compat import HostStepper
@@ -420,7 +433,9 @@ def run_ours(args):
                          "traffic": traffic, "traffic_note": "bytes per launch from the committed ncu capture (profiles/), not measured live; algorithmic bytes per launch = %d" % int(b_alg * n * KL),
                          "peak_source": peak_src, "kernel": ("k3d_step_bytes<float> (K=1)" if (dim == 3 and KL == 1) else
                                     "k%dd%s_rollout<float> (K=%d)" % (dim, "_cache" if dim == 3 else "", KL)),
-                         "bytes_per_env_step": b_alg, "envs_per_launch": n},
+                         "bytes_per_env_step": b_alg, "envs_per_launch": n,
+                         "bytes_per_env_step_this_layout": b_lay, "frac_this_layout": per_gpu_steps_s * b_lay / 1e9 / peak,
+                         "layout_note": None if dim != 3 else "frac uses SURVEY 8(d)'s canonical u16 maps (800 B, window 98 B, E = 1600/L); this repo's 3D state is byte maps (400 B, window 49 B, E = 800/L): frac_this_layout is the fraction by those bytes"},
             "episode_stats": {"sum_return": float(stats[0]), "sum_iou": float(stats[1]), "episodes": float(stats[2]),
                               "steps": float(stats[3])}}
     if other is not None:

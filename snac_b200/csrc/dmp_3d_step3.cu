@@ -1,17 +1,18 @@
 // dmp_3d_step3.cu -- 3D envs, single-step kernel (K = 1, dmp_step), third generation: the rows a step looks at are
 // staged from the BYTE maps (include/dmp.h: u8[n][400] behind the wide u16 maps, byte = min(h, 255)).
 //
-// dmp_3d_step2.cu (k3d_step_span) staged u16 rows: <= 416 B per env in a 464 B slot, 14.5 KB of shared memory per
-// warp, 14 resident warps per SM -- too few to hide the two dependent round trips of a step (scalar state, rows);
-// it reached 0.55 of the HBM roofline with 463 B of DRAM traffic per env-step.  Byte rows halve both: <= 224 B per
-// env in a 272 B slot (17 granules of 16 B: an odd count spreads same-offset words of the 32 lanes over 8 bank groups),
-// 8.7 KB per warp, 23 resident warps per SM, and the window is cut out with 3 word reads + 2 funnel shifts per row
-// instead of 5 + 4.  Everything else follows the span kernel: the action and the step size are known before anything is
-// loaded, so ONE bulk async copy per env (cp.async.bulk -> UBLKCP, completion on the warp's mbarrier) right after the
-// scalar state fetches the 7 rows under the old window plus `step_size` more rows in the direction of a vertical move;
-// the six decision cells, the window at the new position and the brick patch are served from that span; every lane
-// pulls its window into registers, then the warp's [32][51] observation tile is built over the drained slots and
-// leaves through one bulk async copy.
+// dmp_3d_step2.cu (k3d_step_span) staged u16 rows (<= 416 B per env, 14.5 KB of shared memory per warp) and wrote every
+// brick into the u16 map: 0.55 of the HBM roofline.  What held it back was not occupancy but DRAM traffic of the worst
+// kind: a 2-byte store into a line that is not in L2 costs a 32 B read and a 32 B write, and clearing an 800 B map per
+// episode adds 35 B per env-step.  Here a step touches bytes only: <= 224 B of rows per env in a 240 B slot (15 granules
+// of 16 B: an odd count spreads same-offset words of the 32 lanes over 8 bank groups), 7.7 KB per warp, 28 resident
+// warps per SM, the window is cut out with 3 word reads + 2 funnel shifts per row instead of 5 + 4, the brick goes to
+// the byte map, whose line the step has just read.  Everything else follows the span kernel: the action and the step
+// size are known before anything is loaded, so ONE bulk async copy per env (cp.async.bulk -> UBLKCP, completion on the
+// warp's mbarrier) right after the scalar state fetches the 7 rows under the old window plus `step_size` more rows in
+// the direction of a vertical move; the six decision cells, the window at the new position and the brick patch are
+// served from that span; every lane pulls its window into registers, then the warp's [32][51] observation tile is
+// built over the drained slots and leaves through one bulk async copy.
 // Exactness (dmp_common.cuh): the bytes of an env ARE its heights until one reaches 254; from then on the env is
 // flagged tall, its wide u16 map is kept exact as well, a build on a saturated byte reads the true height there and the
 // observation row comes from there (out of line, practically never: plan height is 6).  Bricks of all other envs are
@@ -70,9 +71,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
 }
 
 // LSU = true: the byte rows of a lane come in as up to 14 per-lane 16 B cp.async copies (LDGSTS) instead of one bulk
-// async copy per lane.  A bulk copy occupies the SM's copy engine for tens of cycles whatever its size, and a vector step
-// issues one per env: 1 771 per SM and step, which bounded the u16 span kernel and the first cut of this one at ~29 us per
-// step whatever the occupancy.  LDGSTS runs on the load/store path at ~8 cycles per warp instruction.
+// async copy per lane (tuning switch; the bulk copy is faster, see launch_bytes).
 template <typename ObsT, bool LSU>
 __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, const DmpIO io) {
     extern __shared__ uint4 smem_raw[];
@@ -338,10 +337,9 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
     if (bulk_pending) warp_tile_bulk_wait(lane);                        // the tile must outlive the copy that reads it
 }
 
-// Launch shape: what matters is how many warps are resident per SM, because the grid of a vector step is only a few
-// waves deep (8 192 warps at BASELINE's 262 144 envs): 23 resident warps per SM are 2.4 waves and cost three rounds,
-// 28 are 1.98 waves and cost two.  Two-warp blocks of 240 B slots fit 14 blocks = 28 warps per SM (the driver reserves
-// 1 KB per block, so single-warp blocks stop at 27).  DMP_3D_STEP_WPB overrides the warps per block.
+// Launch shape: two-warp blocks of 240 B slots fit 14 blocks = 28 warps per SM (the driver reserves 1 KB per block, so
+// single-warp blocks stop at 27): 8 192 warps (BASELINE's 262 144 envs) are 1.98 waves.  Measured 12.2 G env-steps/s
+// against 12.0 G with single-warp blocks; DMP_3D_STEP_WPB overrides the warps per block.
 template <typename ObsT, bool LSU>
 int launch_bytes_t(const DmpState& st, const DmpIO& io, cudaStream_t s) {
     static_assert(warp_area_bytes<ObsT>() % 16 == 0, "warp areas and the mbarriers behind them must stay 16 B aligned");
@@ -362,12 +360,13 @@ int launch_bytes_t(const DmpState& st, const DmpIO& io, cudaStream_t s) {
     return dmp_set_error(dmp_launch_pdl(k3d_step_bytes<ObsT, LSU>, blocks, (unsigned)(wpb * 32), smem, s, st, io));
 }
 
-// DMP_3D_STEP_COPY (tuning switch): a = per-lane cp.async copies of the byte rows (default), b = one bulk async copy per lane
+// DMP_3D_STEP_COPY (tuning switch): b = one bulk async copy of the byte rows per lane (default: 12.2 G env-steps/s at
+// 262 144 envs), a = up to 14 per-lane 16 B cp.async copies (10.9 G: MIO-throttled)
 template <typename ObsT>
 int launch_bytes(const DmpState& st, const DmpIO& io, cudaStream_t s) {
     const char* v = getenv("DMP_3D_STEP_COPY");
-    if (v && v[0] == 'b') return launch_bytes_t<ObsT, false>(st, io, s);
-    return launch_bytes_t<ObsT, true>(st, io, s);
+    if (v && v[0] == 'a') return launch_bytes_t<ObsT, true>(st, io, s);
+    return launch_bytes_t<ObsT, false>(st, io, s);
 }
 
 }  // namespace

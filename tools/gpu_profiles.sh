@@ -16,6 +16,6 @@ cap() {  # name, kernel regex, skip, bench args...
 cap prof_2d_roll16 k2d_rollout 10 --workload 2d_static_dense
 cap prof_2d_step k2d_rollout 40 --workload 2d_static_dense --mode step
 cap prof_3d_roll16 k3d_cache_rollout 10 --workload 3d_static_dense
-cap prof_3d_step k3d_step_span 40 --workload 3d_static_dense --mode step
+cap prof_3d_step k3d_step_bytes 40 --workload 3d_static_dense --mode step
 cap prof_1d_roll64 k1d_rollout 6 --workload 1d_dynamic
 ls -la $O
