@@ -225,7 +225,7 @@ def run_ours(args):
     env = BatchedDMPEnv(dim, dynamic=dynamic, plan_choose=plan_choose,
                         plans=load_plans_fixture(dim, density) if dynamic else None,
                         num_envs=n, device=dev, auto_reset=True, env_base=env_base,
-                        obs_dtype=torch.float32)
+                        obs_dtype=torch.float32, action_dist=args.action_dist)
     D, A = env.obs_dim, env.action_dim
     K, W = args.steps, args.warmup
 
@@ -422,7 +422,8 @@ def run_ours(args):
             "ms_per_step": ms / K_eff, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32 bit-grid / i32 counters, f32 observations", "data": "synthetic",
             "config": {"workload": wl, "total_envs": total_envs, "envs_per_gpu": n, "mode": ("step: one dmp_step launch per vector step" if KL == 1 else "rollout: dmp_rollout, %d steps per launch, every step's obs/reward/done materialised" % KL) + ", CUDA-graph replay",
-                       "actions": ("uniform over %d actions, " % A) + ("pool of %d pre-generated vectors in HBM" % RA if act_pool is not None
+                       "actions": (("uniform over %d actions, " % A) if args.action_dist == "uniform" else
+                                   "the reference's p = [.2, .2, .2, .2, .05, .05, .05, .05] (Env/3D/DMP_simulator_3d_static_circle.py:361-362), ") + ("pool of %d pre-generated vectors in HBM" % RA if act_pool is not None
                                                                           else "Philox4x32-10 in-kernel, counter (global env id, step)"),
                        "step_size": "Philox4x32-10 in-kernel", "auto_reset": True,
                        "l2": ring,
@@ -436,7 +437,9 @@ def run_ours(args):
                          "bytes_per_env_step": b_alg, "envs_per_launch": n,
                          "bytes_per_env_step_this_layout": b_lay, "frac_this_layout": per_gpu_steps_s * b_lay / 1e9 / peak,
                          "layout_note": None if dim != 3 else "frac uses SURVEY 8(d)'s canonical u16 maps (800 B, window 98 B, E = 1600/L); this repo's 3D state is byte maps (400 B, window 49 B, E = 800/L): frac_this_layout is the fraction by those bytes"},
-            "episode_stats": {"sum_return": float(stats[0]), "sum_iou": float(stats[1]), "episodes": float(stats[2]),
+            "episode_stats": {"mean_episode_length": mean_len, "mean_iou": (float(stats[1] / stats[2]) if stats[2] > 0 else None),
+                              "mean_return": (float(stats[0] / stats[2]) if stats[2] > 0 else None),
+                              "sum_return": float(stats[0]), "sum_iou": float(stats[1]), "episodes": float(stats[2]),
                               "steps": float(stats[3])}}
     if other is not None:
         line["other_mode"] = other
@@ -468,6 +471,9 @@ def main():
     ap.add_argument("--single-mode", action="store_true", help="skip the secondary measurement of the other mode")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="2d_static_dense", choices=sorted(WORKLOADS))
+    ap.add_argument("--action-dist", default="uniform", choices=["uniform", "ref3d"],
+                    help="in-kernel action distribution: uniform over the env's actions, or (3D) the reference's own "
+                         "p = [.2, .2, .2, .2, .05, .05, .05, .05] (SURVEY.md 8(d) cfg 5)")
     ap.add_argument("--envs", type=int, default=0, help="total envs over all GPUs (default: the BASELINE config's)")
     ap.add_argument("--e2e-steps", type=int, default=48)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -476,6 +482,8 @@ def main():
     args = ap.parse_args()
     if not args.rollout_k:
         args.rollout_k = 64 if WORKLOADS[args.workload][0] == 1 else 16
+    if args.action_dist == "ref3d" and (WORKLOADS[args.workload][0] != 3 or args.actions != "philox"):
+        ap.error("--action-dist ref3d needs a 3D workload and in-kernel (philox) actions")
     if args.impl == "reference":
         run_reference(args)
     else:
