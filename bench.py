@@ -195,6 +195,15 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def plan_launches(K, KL, G):
+    """How K timed steps are executed with KL steps per launch and G launches per CUDA graph:
+    (replays of the main graph, full launches in the tail graph, steps of the tail's short last launch or 0).
+    n_replay * G * KL + n_tail * KL + rem == K exactly."""
+    full, rem = divmod(K, KL)
+    n_replay, n_tail = divmod(full, G)
+    return n_replay, n_tail, rem
+
+
 # ------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------
@@ -266,8 +275,7 @@ def run_ours(args):
 
         # EXACTLY K steps are timed: n_replay replays of a graph of G full launches, then one replay of a tail graph
         # holding the remaining full launches and (when KL does not divide K) one shorter launch
-        full, rem = divmod(K, KL)
-        n_replay, n_tail = divmod(full, G)
+        n_replay, n_tail, rem = plan_launches(K, KL, G)
         with torch.cuda.stream(stream):
             for i in range(4):
                 launch(i)                                    # sets func attributes before capture

@@ -1,0 +1,52 @@
+"""Host-side logic of bench.py that needs no GPU: the launch plan that times EXACTLY K steps, the workload table and
+the reference arm's JSON contract on a tiny sample."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+@pytest.mark.parametrize("K,KL,G", [(16384, 16, 16), (8192, 1, 32), (100, 16, 16), (3, 16, 16), (1, 1, 32), (4097, 64, 16),
+                                    (6000, 16, 16), (7500, 64, 16)])
+def test_launch_plan_times_exactly_k_steps(K, KL, G):
+    n_replay, n_tail, rem = bench.plan_launches(K, KL, G)
+    assert n_replay * G * KL + n_tail * KL + rem == K
+    assert 0 <= n_tail < G and 0 <= rem < KL
+
+
+def test_workload_table_matches_baseline_configs():
+    with open(os.path.join(ROOT, "BASELINE.json")) as f:
+        base = json.load(f)
+    assert "env-steps/sec" in base["metric"] and bench.METRIC == "env-steps/sec"
+    w = bench.WORKLOADS
+    assert w["1d_dynamic"][4] == 65536 and w["2d_static_dense"][4] == 1048576 and w["3d_static_dense"][4] == 262144
+    # algorithmic bytes per env-step, fp32 observations, step mode
+    assert (w["1d_static_step"][5], w["1d_dynamic"][5]) == (64, 67)
+    assert (w["2d_static_dense"][5], w["2d_dynamic_dense"][5]) == (262, 268)
+    assert (w["3d_static_dense"][5], w["3d_dynamic_dense"][5]) == (330, 336)
+
+
+def test_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores) on a tiny sample: one JSON line with the
+    contract's keys; non-zero ranks print nothing."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "30", "--warmup", "3",
+                          "--workload", "2d_static_dense"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "env-steps/sec" and d["higher_is_better"] is True
+    assert d["steps"] == 30 and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "30", "--warmup", "3"],
+                         capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip() == ""
