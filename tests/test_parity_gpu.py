@@ -443,23 +443,14 @@ def test_2d_bulk_copy_out_step_mode(dynamic):
 
 
 # ------------------------------------------------------------------------------------------------
-# 9. 1D rollouts with the bulk (TMA) copy-out of the observation tile (a ring of tiles per warp, DMP_TILE_COPY=b):
-#    equal to the oracle and to the load/store copy-out for every observation dtype, ragged last warp, K beyond the ring
+# 9. 1D rollouts run in blocks of four steps (state chain, then four observation rows at once): K that is not a multiple
+#    of four, K below four, ragged last warp, both block shapes (32 / 128 envs per block), every observation dtype --
+#    equal to the oracle and independent of how a rollout is cut into launches
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dynamic,n", [(False, 32 * 37 + 20), (True, 128 * 148 * 4 + 64)])
-def test_1d_bulk_copy_out_rollout(dynamic, n):
+def test_1d_blocked_rollout(dynamic, n):
     plans = load_plans(1, "dense", "train") if dynamic else None
     K = 23 if n > 10000 else 70
-    def with_tile(mode, fn):
-        old = os.environ.get("DMP_TILE_COPY")
-        os.environ["DMP_TILE_COPY"] = mode
-        try:
-            return fn()
-        finally:
-            if old is None:
-                del os.environ["DMP_TILE_COPY"]
-            else:
-                os.environ["DMP_TILE_COPY"] = old
     ref = None
     if n < 10000:
         ob = OracleBatch(1, dynamic, n, 2, plans)
@@ -469,11 +460,20 @@ def test_1d_bulk_copy_out_rollout(dynamic, n):
         ref = philox_rollout(ob, K, SEED, 5, 0, 3)
     outs = {}
     for dt in (torch.float32, torch.int16, torch.float64):
-        for mode in ("b", "l"):
+        for mode in ("b", "l"):                                           # "l": the same steps cut into launches of 1, 2, 5, ...
             env = make_gpu(1, dynamic, n, 2, plans, auto_reset=True, env_base=5, seed=SEED, obs_dtype=dt, total_step=30)
             env.reset()
-            o, r, d = with_tile(mode, lambda: env.rollout(K))
-            o2, r2, d2 = with_tile(mode, lambda: env.rollout(3))          # K below the ring depth
+            if mode == "b":
+                o, r, d = env.rollout(K)
+            else:
+                parts, left, c = [], K, 1
+                while left:
+                    kk = min(left, c)
+                    parts.append([x.clone() for x in env.rollout(kk)])
+                    left -= kk
+                    c = c * 2 + (c & 1)
+                o, r, d = (torch.cat([p[i] for p in parts]) for i in range(3))
+            o2, r2, d2 = env.rollout(3)                                   # K below the block length
             torch.cuda.synchronize()
             env.check_errors()
             outs[(dt, mode)] = (o, r, d, o2, r2, d2, env.export_state())
