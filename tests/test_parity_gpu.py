@@ -443,12 +443,11 @@ def test_2d_bulk_copy_out_step_mode(dynamic):
 
 
 # ------------------------------------------------------------------------------------------------
-# 9. 1D rollouts run in blocks of four steps (state chain, then four observation rows at once): K that is not a multiple
-#    of four, K below four, ragged last warp, both block shapes (32 / 128 envs per block), every observation dtype --
-#    equal to the oracle and independent of how a rollout is cut into launches
+# 9. 1D rollouts: ragged last warp, both block shapes (32 / 128 envs per block), every observation dtype, load/store and
+#    bulk (TMA) copy-out of the observation tile -- equal to the oracle and independent of how a rollout is cut into launches
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dynamic,n", [(False, 32 * 37 + 20), (True, 128 * 148 * 4 + 64)])
-def test_1d_blocked_rollout(dynamic, n):
+def test_1d_rollout_shapes_and_cuts(dynamic, n):
     plans = load_plans(1, "dense", "train") if dynamic else None
     K = 23 if n > 10000 else 70
     ref = None
@@ -460,11 +459,24 @@ def test_1d_blocked_rollout(dynamic, n):
         ref = philox_rollout(ob, K, SEED, 5, 0, 3)
     outs = {}
     for dt in (torch.float32, torch.int16, torch.float64):
-        for mode in ("b", "l"):                                           # "l": the same steps cut into launches of 1, 2, 5, ...
+        # "b": one launch; "t": one launch with the bulk (TMA) copy-out of the tile (DMP_TILE_COPY=b, off by default);
+        # "l": the same steps cut into launches of 1, 3, 7, ...
+        for mode in ("b", "t", "l"):
             env = make_gpu(1, dynamic, n, 2, plans, auto_reset=True, env_base=5, seed=SEED, obs_dtype=dt, total_step=30)
             env.reset()
             if mode == "b":
                 o, r, d = env.rollout(K)
+            elif mode == "t":
+                old = os.environ.get("DMP_TILE_COPY")
+                os.environ["DMP_TILE_COPY"] = "b"
+                try:
+                    o, r, d = env.rollout(K)
+                    torch.cuda.synchronize()
+                finally:
+                    if old is None:
+                        del os.environ["DMP_TILE_COPY"]
+                    else:
+                        os.environ["DMP_TILE_COPY"] = old
             else:
                 parts, left, c = [], K, 1
                 while left:
@@ -477,10 +489,12 @@ def test_1d_blocked_rollout(dynamic, n):
             torch.cuda.synchronize()
             env.check_errors()
             outs[(dt, mode)] = (o, r, d, o2, r2, d2, env.export_state())
-        a, b = outs[(dt, "b")], outs[(dt, "l")]
-        for x, y in zip(a[:6], b[:6]):
-            assert torch.equal(x, y), dt
-        assert torch.equal(a[6]["grid"], b[6]["grid"]) and torch.equal(a[6]["scalars"], b[6]["scalars"])
+        a = outs[(dt, "b")]
+        for other in ("t", "l"):
+            b = outs[(dt, other)]
+            for x, y in zip(a[:6], b[:6]):
+                assert torch.equal(x, y), (dt, other)
+            assert torch.equal(a[6]["grid"], b[6]["grid"]) and torch.equal(a[6]["scalars"], b[6]["scalars"])
         if ref is not None:
             assert np.array_equal(a[0].cpu().numpy().astype(np.float64), ref[0]), dt
             assert np.array_equal(a[1].cpu().numpy(), ref[1]) and np.array_equal(a[2].cpu().numpy(), ref[2])
