@@ -19,6 +19,13 @@ constexpr int S1_WORDS = 17;          // padded 34 halfwords: word 0 and 16 are 
 #define DMP_1D_TMA_DEFAULT 0          // load/store copy-out unless DMP_TILE_COPY=b (see profiles/README.md)
 #endif
 
+// plan byte as a bare 32-bit load result: nothing touches the register until the reward is computed
+__device__ __forceinline__ int ldg_u8(const uint8_t* p) {
+    int v;
+    asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 struct Env1 {
     int pos, plan_idx, cb, cs;
     float ret;
@@ -119,9 +126,11 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
 
     StepDraws draws;
     const uint64_t gid = (uint64_t)(st.env_base + env);
-    for (int k = 0; k < K; ++k) {
+    int64_t idx = env;                                      // flat [k][env] index of this step's inputs / outputs
+    ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + env0 * D1_OBS;          // this step's 32 observation rows
+    const int64_t dst_step = n * D1_OBS;
+    for (int k = 0; k < K; ++k, idx += n, dst += dst_step) {
         const uint64_t t = t0 + (uint64_t)k;
-        const int64_t idx = (int64_t)k * n + env;
         uint32_t dw = 0;
         if (need_draw) dw = draws.word(st.seed, gid, t);
         int a, s;
@@ -131,30 +140,28 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
 
         // ---- step(): Env/1D/DMP_Env_1D_static.py:85-136 ---------------------------------------
         e.cs += 1;
-        float reward = 0.f;
-        bool done;
+        bool done, rewarded = false;
+        int h = 0, p = 0;
         if (a < 2) {                                        // (a) move left / right
             stage_move1(e, a, s);
             done = e.cs >= st.total_step;
-        } else if (a == 2) {                                // (b) drop + (d) reward
+        } else if (a == 2) {                                // (b) drop
             e.cb += 1;
-            const int h = stage_deposit1<B1>(g, e);
+            h = stage_deposit1<B1>(g, e);
             dirty |= 1u << ((e.pos - D1_HW) >> 3);          // 8 heights per 128-bit plane
             if (e.cb >= total_brick) {                      // :107-114
                 done = true;
-            } else {                                        // :116-123
-                done = e.cs >= st.total_step;
-                const int p = plans[e.plan_idx * PLAN1D_BYTES + (e.pos - D1_HW)];
-                reward = (h > p) ? -1.f : (h == p ? 10.f : 1.f);
+            } else {                                        // :116-123; the plan byte is requested here and consumed after
+                done = e.cs >= st.total_step;               // the observation, which hides the load's latency (it was the
+                p = ldg_u8(plans + e.plan_idx * PLAN1D_BYTES + (e.pos - D1_HW));      // kernel's largest single stall)
+                rewarded = true;
             }
         } else {
             errbits |= DMP_ERR_ACTION;
             done = e.cs >= st.total_step;
         }
-        e.ret += reward;
 
         if (io.obs) {
-            ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * D1_OBS;
             if constexpr (TMA) {
                 ObsT* tk = tile + (k & (NT1 - 1)) * (32 * D1_OBS);
                 if (k >= NT1) {                             // the copy that read this ring slot NT1 steps ago has drained it
@@ -177,6 +184,9 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
                 __syncwarp();
             }
         }
+        // (d) reward: -1 / 10 / 1 for a column above / at / below its plan height (:117-123)
+        const float reward = rewarded ? ((h > p) ? -1.f : (h == p ? 10.f : 1.f)) : 0.f;
+        e.ret += reward;
         if (live) {
             if (io.reward) io.reward[idx] = reward;
             if (io.done) io.done[idx] = done ? 1 : 0;

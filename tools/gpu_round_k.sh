@@ -1,4 +1,5 @@
 #!/bin/bash
+# GPU test-suite + the 1D benches
 set -u
 O=gpurun_out/${1:-rk}; mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest exit $?" >> $O/pytest.log; tail -12 $O/pytest.log
