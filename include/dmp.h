@@ -72,7 +72,7 @@ extern "C" {
 #define DMP_PLAN_SEQUENTIAL  1   /* random_choose_paln=False: (plan_idx + 1) % n_plans            */
 #define DMP_PLAN_KEEP        2   /* keep the current plan (static envs)                           */
 
-/* DmpState.action_dist: distribution of in-kernel synthetic actions (DmpIO.actions == NULL) */
+/* DmpState.action_dist: distribution of in-kernel synthetic actions (DmpIO.actions == NULL); 3D only, 1D/2D draw uniformly */
 #define DMP_ACT_UNIFORM  0
 #define DMP_ACT_REF3D    1   /* p = [.2,.2,.2,.2,.05,.05,.05,.05], Env/3D/DMP_simulator_3d_static_circle.py:361-362 */
 

@@ -134,9 +134,13 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
         uint32_t dw = 0;
         if (need_draw) dw = draws.word(st.seed, gid, t);
         int a, s;
-        if (io.actions) a = live ? io.actions[idx] : 0; else a = draw_action(dw, D1_ACT, st.action_dist);
-        if (io.step_sizes) s = live ? io.step_sizes[idx] : 1; else s = draw_step_size(dw);
-        if ((unsigned)(s - 1) > 2u) errbits |= DMP_ERR_STEPSIZE;
+        if (io.actions) a = live ? io.actions[idx] : 0; else a = draw_action(dw, D1_ACT, DMP_ACT_UNIFORM);
+        if (io.step_sizes) {
+            s = live ? io.step_sizes[idx] : 1;
+            if ((unsigned)(s - 1) > 2u) errbits |= DMP_ERR_STEPSIZE;     // a drawn step size is always 1..3
+        } else {
+            s = draw_step_size(dw);
+        }
 
         // ---- step(): Env/1D/DMP_Env_1D_static.py:85-136 ---------------------------------------
         e.cs += 1;

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(B2, TMA ? 6 : 7) k2d_rollout(const DmpState st
         uint32_t dw = 0;
         if (need_draw) dw = draws.word(st.seed, (uint64_t)(st.env_base + env), t);
         int a, s;
-        if (io.actions) a = live ? io.actions[idx] : 0; else a = draw_action(dw, D2_ACT, st.action_dist);
+        if (io.actions) a = live ? io.actions[idx] : 0; else a = draw_action(dw, D2_ACT, DMP_ACT_UNIFORM);
         if (io.step_sizes) s = live ? io.step_sizes[idx] : 1; else s = draw_step_size(dw);
         if ((unsigned)(s - 1) > 2u) errbits |= DMP_ERR_STEPSIZE;
 

@@ -93,7 +93,7 @@ __device__ __forceinline__ void step_inputs(const DmpState& st, const DmpIO& io,
     StepDraws draws;
     uint32_t dw = 0;
     if (!io.actions || !io.step_sizes) dw = draws.word(st.seed, (uint64_t)(st.env_base + env), st.t);
-    a = io.actions ? (int)io.actions[env] : draw_action(dw, A, st.action_dist);
+    a = io.actions ? (int)io.actions[env] : draw_action(dw, A, st.dim == 3 ? st.action_dist : DMP_ACT_UNIFORM);
     s = io.step_sizes ? (int)io.step_sizes[env] : draw_step_size(dw);
 }
 

@@ -209,6 +209,9 @@ class BatchedDMPEnv:
         st.dim, st.dynamic, st.n_plans, st.total_step = dim, int(self.dynamic_rules), self.n_plans, self.total_step
         st.plan_mode = (L.PLAN_KEEP if not self.dynamic else
                         (L.PLAN_PHILOX if random_choose_paln else L.PLAN_SEQUENTIAL))
+        if action_dist == "ref3d" and dim != 3:
+            raise ValueError('action_dist="ref3d" is the 3D envs\' own action distribution '
+                             '(Env/3D/DMP_simulator_3d_static_circle.py:361-362); 1D/2D envs draw uniformly')
         st.action_dist = {"uniform": L.ACT_UNIFORM, "ref3d": L.ACT_REF3D}[action_dist]
         st.n_envs, st.env_base, st.seed, st.t = n, int(env_base), int(seed), 0
         st.t_dev = None
