@@ -21,11 +21,13 @@
  *                              20x20 interior), word 13 = pos_row | pos_col << 8 | plan_idx << 16,
  *                              word 14 = count_brick | count_step << 16, word 15 = episode return (f32)
  *       aux   : unused (NULL)
- *   3D  cells : u16 [n][400]   per-env contiguous 20x20 height map (row-major), 800 B, 16 B aligned (canonical),
- *               followed at byte offset 800 n by its byte shadow u8 [n][400], byte = min(height, 255): single steps
- *               and rollouts stage these 400 B maps (half the traffic and shared memory); a saturated or large
- *               byte sends the env to an exact path over the u16 map.  Every kernel keeps both in step.
- *       aux   : uint4 [n]      .x = pos_row | pos_col << 8 | plan_idx << 16 ; .y = count_brick | count_step << 16 ;
+ *   3D  cells : two areas.  At byte offset 800 n: the BYTE maps u8 [n][400], per-env contiguous 20x20 (row-major, 400 B,
+ *               16 B aligned), byte = min(height, 255) -- what single steps and rollouts read and write.  At offset 0:
+ *               the WIDE maps u16 [n][400] (800 B per env), exact and maintained only for envs whose tall flag is set
+ *               (a height >= 254 somewhere); for every other env the wide map is scratch (the bytes ARE the heights).
+ *               dmp_export_state / dmp_iou / dmp_import_state convert as needed; callers never see the difference.
+ *       aux   : uint4 [n]      .x = pos_row | tall flag << 7 | pos_col << 8 | plan_idx << 16 ;
+ *                              .y = count_brick | count_step << 16 ;
  *                              .z = episode return (f32 bits) ; .w = running sum(min(height, plan)), the IoU
  *                              numerator, +1 for every brick laid at or below the plan height
  *   positions are stored in the reference's padded coordinates (1D: 2..31, 2D/3D: 3..22).
