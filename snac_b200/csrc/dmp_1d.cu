@@ -19,13 +19,6 @@ constexpr int S1_WORDS = 17;          // padded 34 halfwords: word 0 and 16 are 
 #define DMP_1D_TMA_DEFAULT 0          // load/store copy-out unless DMP_TILE_COPY=b (see profiles/README.md)
 #endif
 
-// plan byte as a bare 32-bit load result: nothing touches the register until the reward is computed
-__device__ __forceinline__ int ldg_u8(const uint8_t* p) {
-    int v;
-    asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-
 struct Env1 {
     int pos, plan_idx, cb, cs;
     float ret;

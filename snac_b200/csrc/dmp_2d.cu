@@ -63,24 +63,6 @@ __device__ __forceinline__ uint32_t stage_deposit2(uint32_t* g, const Env2& e, i
     return old & bit;
 }
 
-// spread the 7 bits of x into the low bits of 7 bytes (byte j = bit j): the partial products of
-// x * 0x0002040810204081 never overlap, so one wide IMAD (FMA pipe) + one mask does it.
-__device__ __forceinline__ uint64_t spread7(uint32_t x) {
-    return ((uint64_t)x * 0x0002040810204081ull) & 0x0101010101010101ull;
-}
-
-// code byte (0 frame, 1 empty, 2 occupied) -> observation value code-1
-template <typename ObsT, int BYTE>
-__device__ __forceinline__ ObsT obs_from_code(uint32_t packed) {
-    if constexpr (sizeof(ObsT) == 4) {
-        // float: drop the byte into the mantissa of 2^23 (one PRMT), subtract 2^23 + 1 (one FADD): exact,
-        // and keeps the per-element work off the conversion (XU) pipe
-        return __uint_as_float(__byte_perm(packed, 0x4B000000u, 0x7650u + BYTE)) - 8388609.0f;
-    } else {
-        return obs_from_int<ObsT>((int)((packed >> (8 * BYTE)) & 0xFFu) - 1);
-    }
-}
-
 // stage (c): observation window -> this thread's row of the warp tile.  observation_ :78-82 + hstack.
 template <typename ObsT>
 __device__ __forceinline__ void stage_observe2(const uint32_t* g, const Env2& e, ObsT* row,
@@ -115,13 +97,13 @@ __device__ __forceinline__ void stage_observe2(const uint32_t* g, const Env2& e,
         const uint64_t code = rowvalid ? spread7(occ) + vcode : 0ull;
         const uint32_t lo = (uint32_t)code, hi = (uint32_t)(code >> 32);
         ObsT* o = row + k * 7;
-        o[0] = obs_from_code<ObsT, 0>(lo);
-        o[1] = obs_from_code<ObsT, 1>(lo);
-        o[2] = obs_from_code<ObsT, 2>(lo);
-        o[3] = obs_from_code<ObsT, 3>(lo);
-        o[4] = obs_from_code<ObsT, 0>(hi);
-        o[5] = obs_from_code<ObsT, 1>(hi);
-        o[6] = obs_from_code<ObsT, 2>(hi);
+        o[0] = obs_from_biased<ObsT, 0>(lo);
+        o[1] = obs_from_biased<ObsT, 1>(lo);
+        o[2] = obs_from_biased<ObsT, 2>(lo);
+        o[3] = obs_from_biased<ObsT, 3>(lo);
+        o[4] = obs_from_biased<ObsT, 0>(hi);
+        o[5] = obs_from_biased<ObsT, 1>(hi);
+        o[6] = obs_from_biased<ObsT, 2>(hi);
     }
     obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, total_step, row[49], row[50]);
 }

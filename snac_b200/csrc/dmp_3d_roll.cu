@@ -64,28 +64,6 @@ __device__ __noinline__ void observe_tall(const uint16_t* ge, int pr, int pc, Ob
         for (int j = 0; j < 7; ++j) row[k * 7 + j] = obs_from_int<ObsT>(cell_g(ge, pr - 3 + k, pc - 3 + j));
 }
 
-// plan byte as a bare 32-bit load result: nothing touches the register until the reward is computed, so the
-// load's latency hides behind the observation stage
-__device__ __forceinline__ int ldg_u8(const uint8_t* p) {
-    int v;
-    asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-
-__device__ __forceinline__ uint64_t spread7(uint32_t x) {       // bit j -> byte j (see dmp_2d.cu)
-    return ((uint64_t)x * 0x0002040810204081ull) & 0x0101010101010101ull;
-}
-
-// biased byte (height + 1, 0 = frame) -> observation value
-template <typename ObsT, int BYTE>
-__device__ __forceinline__ ObsT obs_from_biased(uint32_t packed) {
-    if constexpr (sizeof(ObsT) == 4) {
-        return __uint_as_float(__byte_perm(packed, 0x4B000000u, 0x7650u + BYTE)) - 8388609.0f;
-    } else {
-        return obs_from_int<ObsT>((int)((packed >> (8 * BYTE)) & 0xFFu) - 1);
-    }
-}
-
 // stage (c): 7x7 window of this lane's env (byte cache) -> its row of the warp tile.  The seven rows are
 // read at fixed word offsets from one base (rows outside the map land in the guards / the neighbouring
 // env and are masked), so no per-row clamping or address arithmetic is needed.

@@ -30,20 +30,6 @@ constexpr int SLOT3_B = 240;                 // per-lane staging: 16 B guard | <
                                              // run up to 8 B past the rows: into the next lane's guard (masked columns)
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
-__device__ __forceinline__ uint64_t spread7(uint32_t x) {       // bit j -> byte j (see dmp_2d.cu)
-    return ((uint64_t)x * 0x0002040810204081ull) & 0x0101010101010101ull;
-}
-
-// biased byte (height + 1, 0 = frame) -> observation value
-template <typename ObsT, int BYTE>
-__device__ __forceinline__ ObsT obs_from_biased(uint32_t packed) {
-    if constexpr (sizeof(ObsT) == 4) {
-        return __uint_as_float(__byte_perm(packed, 0x4B000000u, 0x7650u + BYTE)) - 8388609.0f;
-    } else {
-        return obs_from_int<ObsT>((int)((packed >> (8 * BYTE)) & 0xFFu) - 1);
-    }
-}
-
 // an env turns tall: its wide map := its (still exact) byte map, with the brick just laid.  Out of line, practically never.
 __device__ __noinline__ void widen_env(uint16_t* ge, const uint8_t* be, int ti, int newh) {
     for (int i = 0; i < CELLS3D; ++i) ge[i] = (i == ti) ? (uint16_t)newh : (uint16_t)__ldcg(be + i);

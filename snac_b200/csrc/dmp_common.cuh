@@ -94,6 +94,32 @@ template <> __device__ __forceinline__ float   obs_from_ratio<float>(int n, int 
 template <> __device__ __forceinline__ double  obs_from_ratio<double>(int n, int d)  { return __ddiv_rn((double)n, (double)d); }
 template <> __device__ __forceinline__ int16_t obs_from_ratio<int16_t>(int n, int)   { return (int16_t)n; }
 
+// spread the 7 bits of x into the low bits of 7 bytes (byte j = bit j): the partial products of
+// x * 0x0002040810204081 never overlap, so one wide IMAD (FMA pipe) + one mask does it.
+__device__ __forceinline__ uint64_t spread7(uint32_t x) {
+    return ((uint64_t)x * 0x0002040810204081ull) & 0x0101010101010101ull;
+}
+
+// biased byte (value + 1: 2D codes 0 frame / 1 empty / 2 occupied, 3D height + 1 with 0 = frame) -> observation value
+template <typename ObsT, int BYTE>
+__device__ __forceinline__ ObsT obs_from_biased(uint32_t packed) {
+    if constexpr (sizeof(ObsT) == 4) {
+        // float: drop the byte into the mantissa of 2^23 (one PRMT), subtract 2^23 + 1 (one FADD): exact,
+        // and keeps the per-element work off the conversion (XU) pipe
+        return __uint_as_float(__byte_perm(packed, 0x4B000000u, 0x7650u + BYTE)) - 8388609.0f;
+    } else {
+        return obs_from_int<ObsT>((int)((packed >> (8 * BYTE)) & 0xFFu) - 1);
+    }
+}
+
+// a plan byte as a bare 32-bit load result: nothing touches the register until the reward is computed, so the
+// load's latency hides behind the observation stage (1D and 3D rollouts)
+__device__ __forceinline__ int ldg_u8(const uint8_t* p) {
+    int v;
+    asm("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 // counters -> the two trailing obs columns
 template <typename T>
 __device__ __forceinline__ void obs_counters(bool normalise, int cb, int cs, int total_brick, int total_step, T& o_cb, T& o_cs) {
