@@ -60,3 +60,31 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_header_is_plain_c_and_offsets_match_ctypes(tmp_path):
+    """include/dmp.h compiles as C (a C or cgo caller can include it) and every struct field sits where the ctypes
+    mirrors of snac_b200/_lib.py put it."""
+    import shutil
+    import subprocess
+    from snac_b200 import _lib as L
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the build image"
+    structs = {"DmpState": L.DmpState, "DmpIO": L.DmpIO, "DmpLayout": L.DmpLayout}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dmp.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append('  printf("%s.sizeof %%zu\\n", sizeof(%s));' % (name, name))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, fname, name, fname))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "offsets.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "offsets"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = dict(l.split() for l in out.splitlines())
+    for name, cls in structs.items():
+        assert int(got[name + ".sizeof"]) == ctypes.sizeof(cls), name
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (name, fname)]) == getattr(cls, fname).offset, (name, fname)
