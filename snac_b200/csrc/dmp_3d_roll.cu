@@ -116,9 +116,9 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
     uint8_t* gb = wmap + lane * MAP_B;                                // this lane's byte map
 
     uint16_t* cells = reinterpret_cast<uint16_t*>(st.cells);
-    uint16_t* gwarp = cells + env0 * CELLS3D;                         // the warp's 32 maps in HBM (contiguous)
-    uint16_t* ge = cells + env * CELLS3D;                             // this lane's map in HBM
-    uint8_t* bwarp = bmap3(st) + env0 * CELLS3D;                      // the warp's 32 byte maps (the byte shadow, contiguous)
+    uint16_t* gwarp = cells + env0 * CELLS3D;                         // the warp's 32 WIDE maps in HBM (tall envs only)
+    uint16_t* ge = cells + env * CELLS3D;                             // this lane's wide map in HBM
+    uint8_t* bwarp = bmap3(st) + env0 * CELLS3D;                      // the warp's 32 byte maps in HBM (contiguous)
     uint8_t* be = bmap3(st) + env * CELLS3D;
     uint4* aux = reinterpret_cast<uint4*>(st.aux);
     const uint8_t* __restrict__ plans = reinterpret_cast<const uint8_t*>(st.plans);
