@@ -49,7 +49,7 @@
 extern "C" {
 #endif
 
-#define DMP_ABI_VERSION 2
+#define DMP_ABI_VERSION 3
 
 /* return codes */
 #define DMP_OK       0
@@ -60,6 +60,19 @@ extern "C" {
 #define DMP_OBS_F32  0
 #define DMP_OBS_F64  1
 #define DMP_OBS_I16  2   /* raw counters only */
+#define DMP_OBS_REC  3   /* packed step record: window + counters + reward + done in one contiguous record per env -- the
+                            host-facing kind: a step's whole result is one buffer and one device-to-host copy, 3.9x
+                            smaller than f32 observations + reward + done.  Raw counters only.
+                            2D / 3D: 56 B  { u8 win[49]; u8 flags; u16 count_brick; u16 count_step; i8 reward; u8 done; }
+                                     win = window value + 1 (0 = the -1 frame, 1 = empty, 2D: 2 = occupied, 3D: height + 1)
+                                     flags = DMP_REC_DONE | DMP_REC_SATURATED ; done = 0 / 1 (a bool the host can view in place)
+                            1D     : 16 B  { i16 win[5]; u16 count_brick; u16 count_step; i8 reward; u8 done; }
+                                     win = raw heights (-1 = wall)
+                            Every reward of the six classes (-100, -1, 0, 1, 5, 10) fits the i8.  DmpIO.reward / DmpIO.done
+                            are still written when they are not NULL. */
+#define DMP_REC_DONE       1
+#define DMP_REC_SATURATED  2   /* 3D only: the env holds a height >= 254 ("tall"), so a window byte may have saturated
+                                  at 255; read that env's exact observation through another obs kind / dmp_export_state */
 
 /* DmpIO.flags */
 #define DMP_F_AUTORESET  1   /* on done: fold the episode into ep_* and reset the env in the same launch */
@@ -68,6 +81,13 @@ extern "C" {
                                 computed as an IEEE fp64 division, then cast to the obs type. f32/f64 only */
 #define DMP_F_TSLOT1     4   /* read the step counter from t_dev[1] (see DmpState.t_dev) */
 #define DMP_F_NO_L2_HINT 8   /* tuning switch: plain loads/stores for the env state instead of L2 evict_last */
+#define DMP_F_NO_PDL     16  /* tuning switch: plain stream-ordered launch instead of programmatic dependent launch */
+#define DMP_F_TILE_LDST  32  /* tuning switch: the observation tile leaves shared memory through 128-bit load/store pairs
+                                instead of one bulk async copy per warp and step (2D, 3D) */
+#define DMP_F_GENERIC    64  /* tuning switch: never pick a specialised instantiation of a kernel (1D: the throughput
+                                configuration has one with its launch-uniform branches folded) */
+#define DMP_F_ROLLOUT_K1 128 /* tuning switch: 3D single steps run through the rollout kernel (whole maps staged) instead
+                                of the single-step kernel (only the rows a step can look at) */
 
 /* DmpState.plan_mode: which plan an env gets when it auto-resets and DmpIO.next_plan is NULL */
 #define DMP_PLAN_PHILOX      0   /* random_choose_paln=True : counter-based draw                */
@@ -83,6 +103,9 @@ extern "C" {
                                 Env/1D/DMP_Env_1D_static.py:130-133) */
 #define DMP_ERR_STEPSIZE 2   /* injected step size outside {1,2,3} */
 #define DMP_ERR_PLANIDX  4   /* injected plan index outside [0, n_plans) */
+#define DMP_ERR_OVERFLOW 8   /* count_step or count_brick of an env passed 65 535 (the packed state holds 16 bits; reference
+                                episodes end after <= 1 300 steps -- only envs stepped on after done without a reset get
+                                there); the stored counter saturates */
 
 typedef struct DmpState {
     int32_t  dim;          /* 1, 2 or 3 */
@@ -113,7 +136,7 @@ typedef struct DmpIO {
     const uint8_t* actions;     /* [K][n] ; NULL -> Philox synthetic actions                              */
     const uint8_t* step_sizes;  /* [K][n] in {1,2,3}; NULL -> Philox (replaces np.random.randint(1,4))     */
     const int32_t* next_plan;   /* [K][n] plan index to use if the env auto-resets at that step; NULL -> plan_mode */
-    void*    obs;               /* [K][n][D] of obs_kind ; NULL -> not materialised ("state-only" mode)     */
+    void*    obs;               /* [K][n][D] of obs_kind ([K][n] records for DMP_OBS_REC) ; NULL -> not materialised */
     float*   reward;            /* [K][n] ; NULL -> not materialised                                        */
     uint8_t* done;              /* [K][n] ; NULL -> not materialised                                        */
     int32_t  obs_kind;          /* DMP_OBS_* */
@@ -126,6 +149,7 @@ typedef struct DmpLayout {
     int32_t obs_dim, n_actions;            /* D and A of the env family          */
     int32_t grid_rows, grid_cols;          /* padded grid of dmp_export_state    */
     int32_t total_step_static, total_step_dynamic;
+    int32_t rec_bytes, reserved;           /* bytes of one DMP_OBS_REC record (16 / 56)   */
 } DmpLayout;
 
 /* version / diagnostics */
@@ -180,7 +204,9 @@ int dmp_plans_from_state(const DmpState* st, void* plans_out, int32_t* plan_tota
  * Env/3D/DMP_simulator_3d_static_circle.py:67-86, Env/3D/DMP_simulator_3d_dynamic_triangle_usedata.py:45-75
  * and VectorizedEnvWrapper.reset / reset_at (multiprocess.py:20-23).
  *   mask     : u8[n] nullable (NULL = all envs); only envs with mask != 0 are touched
- *   plan_idx : i32[n] nullable; NULL -> by plan_mode (Philox draw keyed by (env, t_draw) / +1 / keep)
+ *   plan_idx : i32[n] nullable; NULL -> by plan_mode (Philox draw keyed by (env, t_draw) / +1 / keep).  Sequential
+ *              mode starts at plan 0 on an env that has never been reset (zero-initialised state), like the reference's
+ *              index_for_non_random = 0 (Env/2D/DMP_Env_2D_dynamic_usedata_plan.py:39-44)
  *   obs      : [n][D] nullable; rows of reset envs are written (raw counters are 0 either way)
  * Episode statistics ep_* are NOT touched (use dmp_stats_clear). */
 int dmp_reset(const DmpState* st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw,
@@ -216,7 +242,7 @@ int dmp_stats_clear(const DmpState* st, void* stream);
 int dmp_export_state(const DmpState* st, int32_t* grid, int32_t* scalars, float* ret_acc, void* stream);
 int dmp_import_state(const DmpState* st, const int32_t* grid, const int32_t* scalars, const float* ret_acc, void* stream);
 
-/* ---- standalone stage kernels (a)-(e) of the step, for unit parity and per-stage timing ----------
+/* ---- standalone stage kernels (a)-(e) of the step, for unit parity and per-stage timing (obs kinds F32/F64/I16) ---
  * They run the same __device__ stage functions the fused kernels are built from, one stage per launch,
  * communicating through `scratch` (i32 [n][4]: action-valid/brick-placed flag, target cell row, col, reserved).
  *   (a) move      : position update + boundary clamp (+3D collision walk)       [clip_position, move_step]

@@ -1,9 +1,9 @@
 """Import the UNMODIFIED reference env classes (TEST INFRASTRUCTURE ONLY).
 
-Works only where ``/root/reference`` exists (the build container); the GPU box has no
-reference tree, so nothing on the ``-m gpu`` / smoke / bench path may call this.  Used by
-``tests/golden/make_golden.py`` to produce the committed golden traces and by the
-container-only live cross-check in ``tests/test_oracle_vs_reference.py``.
+Default root: ``/root/reference`` (the build container).  The GPU box has no reference tree, so nothing on the
+``-m gpu`` / smoke path may call this.  Used by ``tests/golden/make_golden.py`` to produce the committed golden
+traces, by the container-only live cross-check in ``tests/test_oracle_vs_reference.py`` and -- after ``use_root()`` has
+pointed it at the files unpacked from ``oracle/_ref`` (oracle/stage_ref.py) -- by the CPU arm of ``bench.py``.
 
 Two third-party imports of the reference are not installed here and are stubbed in
 ``sys.modules`` before the import: ``gym`` (only ``gym.Env`` / ``gym.Wrapper`` base
@@ -25,6 +25,12 @@ REF_ROOT = os.environ.get("SNAC_REFERENCE", "/root/reference")
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "Env", "1D"))
+
+
+def use_root(path: str) -> None:
+    """Import the reference from ``path`` instead (call before the first load_class / load_multiprocess)."""
+    global REF_ROOT
+    REF_ROOT = path
 
 
 def _install_stubs():
@@ -129,9 +135,12 @@ def load_multiprocess():
         p = os.path.join(REF_ROOT, "Env", sub)
         if p not in sys.path:
             sys.path.append(p)
-    if REF_ROOT not in sys.path:
-        sys.path.append(REF_ROOT)
-    return importlib.import_module("multiprocess")
+    # loaded by path under a private name: a third-party package called ``multiprocess`` may be installed
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("snac_reference_multiprocess", os.path.join(REF_ROOT, "multiprocess.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def dataset_path(dim: str, density: str = "dense", split: str = "train") -> str:

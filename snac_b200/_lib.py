@@ -8,13 +8,18 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libdmp.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, EINVAL, ECUDA = 0, 1, 2
-OBS_F32, OBS_F64, OBS_I16 = 0, 1, 2
+OBS_F32, OBS_F64, OBS_I16, OBS_REC = 0, 1, 2, 3
+REC_DONE, REC_SATURATED = 1, 2
 F_AUTORESET, F_NORMALISE, F_TSLOT1, F_NO_L2_HINT = 1, 2, 4, 8
+F_NO_PDL, F_TILE_LDST, F_GENERIC, F_ROLLOUT_K1 = 16, 32, 64, 128
+# tuning switches by name (BatchedDMPEnv(tuning=...)); decided once on the host, passed as DmpIO.flags bits
+TUNING_FLAGS = {"no_l2_hint": F_NO_L2_HINT, "no_pdl": F_NO_PDL, "tile_ldst": F_TILE_LDST, "generic": F_GENERIC,
+                "rollout_k1": F_ROLLOUT_K1}
 PLAN_PHILOX, PLAN_SEQUENTIAL, PLAN_KEEP = 0, 1, 2
 ACT_UNIFORM, ACT_REF3D = 0, 1
-ERR_ACTION, ERR_STEPSIZE, ERR_PLANIDX = 1, 2, 4
+ERR_ACTION, ERR_STEPSIZE, ERR_PLANIDX, ERR_OVERFLOW = 1, 2, 4, 8
 T_INIT = 0xFFFFFFFFFFFFFFFF
 SEED_DEFAULT = 0x534E4143
 
@@ -43,6 +48,7 @@ class DmpLayout(C.Structure):
         ("cells_bytes", C.c_int64), ("aux_bytes", C.c_int64), ("plan_row_bytes", C.c_int64),
         ("obs_dim", C.c_int32), ("n_actions", C.c_int32), ("grid_rows", C.c_int32), ("grid_cols", C.c_int32),
         ("total_step_static", C.c_int32), ("total_step_dynamic", C.c_int32),
+        ("rec_bytes", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -15,8 +15,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libdmp.so")
-SOURCES = ["dmp_api.cu", "dmp_1d.cu", "dmp_2d.cu", "dmp_3d.cu", "dmp_3d_tile.cu", "dmp_3d_roll.cu", "dmp_3d_step.cu", "dmp_3d_step2.cu", "dmp_3d_step3.cu", "dmp_stages.cu", "dmp_plangen.cu"]
-HEADERS = [os.path.join(CSRC, h) for h in ("dmp_common.cuh", "dmp_3d_u16.cuh")] + [os.path.join(ROOT, "include", "dmp.h")]
+SOURCES = ["dmp_api.cu", "dmp_1d.cu", "dmp_2d.cu", "dmp_3d.cu", "dmp_3d_roll.cu", "dmp_3d_step.cu", "dmp_stages.cu", "dmp_plangen.cu"]
+HEADERS = [os.path.join(CSRC, h) for h in ("dmp_common.cuh", "dmp_3d_bulk.cuh")] + [os.path.join(ROOT, "include", "dmp.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

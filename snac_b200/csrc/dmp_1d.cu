@@ -15,9 +15,6 @@ namespace {
 // B1 = threads (= envs) per block is a template parameter: 128 for large batches, 32 when the batch is too small
 // to give every SM several blocks (BASELINE config 2: 65 536 envs = 2 048 warps for 592 schedulers)
 constexpr int S1_WORDS = 17;          // padded 34 halfwords: word 0 and 16 are the -1 walls
-#ifndef DMP_1D_TMA_DEFAULT
-#define DMP_1D_TMA_DEFAULT 0          // load/store copy-out unless DMP_TILE_COPY=b (see profiles/README.md)
-#endif
 
 struct Env1 {
     int pos, plan_idx, cb, cs;
@@ -41,19 +38,30 @@ __device__ __forceinline__ int stage_deposit1(uint32_t* g, const Env1& e) {
 }
 
 // stage (c): window [pos-2, pos+2] + counters (:131-133)
-template <typename ObsT, int B1>
-__device__ __forceinline__ void stage_observe1(const uint32_t* g, const Env1& e, ObsT* row, bool normalise,
-                                               int total_brick, int total_step) {
+template <int B1>
+__device__ __forceinline__ void window1(const uint32_t* g, const Env1& e, uint32_t& q0, uint32_t& q1, uint32_t& q2) {
     const int p0 = e.pos - D1_HW;
     const int w = p0 >> 1, sh = (p0 & 1) * 16;
     const uint32_t x0 = g[w * B1], x1 = g[(w + 1) * B1], x2 = g[(w + 2) * B1];
-    const uint32_t q0 = __funnelshift_r(x0, x1, sh), q1 = __funnelshift_r(x1, x2, sh), q2 = x2 >> sh;
+    q0 = __funnelshift_r(x0, x1, sh); q1 = __funnelshift_r(x1, x2, sh); q2 = x2 >> sh;     // five halfwords: q0, q1, low q2
+}
+template <typename ObsT, int B1>
+__device__ __forceinline__ void stage_observe1(const uint32_t* g, const Env1& e, ObsT* row, bool normalise,
+                                               int total_brick, int total_step) {
+    uint32_t q0, q1, q2;
+    window1<B1>(g, e, q0, q1, q2);
     row[0] = obs_from_int<ObsT>((int)(int16_t)(q0 & 0xFFFF));
     row[1] = obs_from_int<ObsT>((int)(int16_t)(q0 >> 16));
     row[2] = obs_from_int<ObsT>((int)(int16_t)(q1 & 0xFFFF));
     row[3] = obs_from_int<ObsT>((int)(int16_t)(q1 >> 16));
     row[4] = obs_from_int<ObsT>((int)(int16_t)(q2 & 0xFFFF));
     obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, total_step, row[5], row[6]);
+}
+// DMP_OBS_REC: the 16 B step record of one env (include/dmp.h); written straight to global memory, one coalesced
+// 128-bit store per lane (no tile)
+__device__ __forceinline__ uint4 make_rec16(uint32_t q0, uint32_t q1, uint32_t q2, int cb, int cs, float reward, bool done) {
+    return make_uint4(q0, q1, (q2 & 0xFFFFu) | ((uint32_t)(cb & 0xFFFF) << 16),
+                      (uint32_t)(cs & 0xFFFF) | (((uint32_t)(int)reward & 0xFFu) << 16) | (done ? (uint32_t)DMP_REC_DONE << 24 : 0u));
 }
 
 // IoU, Env/1D/DMP_Env_1D_static.py:138-151: cross = sum(min(g, p)); iou = cross / (sum p + sum g - cross)
@@ -70,23 +78,25 @@ __device__ __forceinline__ double iou1_words(const uint32_t (&hw)[15], const uin
     return __ddiv_rn((double)cross, (double)(a1 + a2 - cross));
 }
 
-// TMA = true: the warp's observation tile leaves through one bulk async copy per step (dmp_common.cuh:
-// warp_tile_bulk_store) out of a ring of NT1 tiles, so a step never waits for the previous step's copy; TMA = false:
-// 2 x (LDS.128 + STG.128) per lane out of a single tile.
-constexpr int NT1 = 4;
-
-template <typename ObsT, int B1, bool TMA>
+// The warp's [32][7] observation tile leaves through 2 x (LDS.128 + STG.128) per lane.  (A bulk async copy out of a ring of
+// tiles was measured 20 % slower -- the 896 B tile is too small to pay for fence + elected-lane issue -- and is gone.)
+// FAST = true: the throughput configuration with everything that is uniform over a launch folded at compile time --
+// in-kernel Philox draws, observations / rewards / done flags all materialised, auto-reset, raw counters, full warps
+// (n a multiple of the block size), 16 B aligned observation buffer.  The launcher checks those conditions.
+template <typename ObsT, int B1, bool FAST>
 __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO io, const int K) {
+    constexpr bool REC = is_rec<ObsT>::value;
+    constexpr int ROW = row_elems<ObsT, D1_OBS>();
     extern __shared__ uint4 smem_raw[];
     uint32_t* G = reinterpret_cast<uint32_t*>(smem_raw);                 // [S1_WORDS][B1]
-    ObsT* tiles = reinterpret_cast<ObsT*>(G + S1_WORDS * B1);            // [B1/32][TMA ? NT1 : 1][32*7]
+    ObsT* tiles = reinterpret_cast<ObsT*>(G + S1_WORDS * B1);            // [B1/32][32*7] (no tile for records)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t n = st.n_envs;
     const int64_t env = (int64_t)blockIdx.x * B1 + tid;
     const int64_t env0 = env - lane;
-    const int nvalid = (int)min((int64_t)32, n - env0);
-    const bool live = env < n;
-    ObsT* tile = tiles + warp * ((TMA ? NT1 : 1) * 32 * D1_OBS);
+    const int nvalid = FAST ? 32 : (int)min((int64_t)32, n - env0);
+    const bool live = FAST ? true : (env < n);
+    ObsT* tile = tiles + warp * (32 * ROW);
     uint32_t* g = G + tid;
 
     uint4* cells = reinterpret_cast<uint4*>(st.cells);
@@ -111,25 +121,30 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
     unsigned dirty = 0;
     int errbits = 0;
 
-    const bool autoreset = io.flags & DMP_F_AUTORESET;
-    const bool normalise = io.flags & DMP_F_NORMALISE;
-    const bool need_draw = (io.actions == nullptr) || (io.step_sizes == nullptr);
+    const bool autoreset = FAST ? true : (bool)(io.flags & DMP_F_AUTORESET);
+    const bool normalise = FAST ? false : (bool)(io.flags & DMP_F_NORMALISE);
+    const uint8_t* act_in = FAST ? nullptr : io.actions;
+    const uint8_t* size_in = FAST ? nullptr : io.step_sizes;
+    const bool need_draw = FAST ? true : ((act_in == nullptr) || (size_in == nullptr));
+    const bool want_obs = FAST ? true : (io.obs != nullptr);
+    const bool want_rew = FAST ? true : (io.reward != nullptr);
+    const bool want_done = FAST ? true : (io.done != nullptr);
     const int tslot = (io.flags & DMP_F_TSLOT1) ? 1 : 0;
     const uint64_t t0 = st.t_dev ? st.t_dev[tslot] : st.t;
 
     StepDraws draws;
     const uint64_t gid = (uint64_t)(st.env_base + env);
     int64_t idx = env;                                      // flat [k][env] index of this step's inputs / outputs
-    ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + env0 * D1_OBS;          // this step's 32 observation rows
-    const int64_t dst_step = n * D1_OBS;
+    ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + env0 * ROW;             // this step's 32 observation rows / records
+    const int64_t dst_step = n * ROW;
     for (int k = 0; k < K; ++k, idx += n, dst += dst_step) {
         const uint64_t t = t0 + (uint64_t)k;
         uint32_t dw = 0;
         if (need_draw) dw = draws.word(st.seed, gid, t);
         int a, s;
-        if (io.actions) a = live ? io.actions[idx] : 0; else a = draw_action(dw, D1_ACT, DMP_ACT_UNIFORM);
-        if (io.step_sizes) {
-            s = live ? io.step_sizes[idx] : 1;
+        if (act_in) a = live ? act_in[idx] : 0; else a = draw_action(dw, D1_ACT, DMP_ACT_UNIFORM);
+        if (size_in) {
+            s = live ? size_in[idx] : 1;
             if ((unsigned)(s - 1) > 2u) errbits |= DMP_ERR_STEPSIZE;     // a drawn step size is always 1..3
         } else {
             s = draw_step_size(dw);
@@ -158,25 +173,15 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
             done = e.cs >= st.total_step;
         }
 
-        if (io.obs) {
-            if constexpr (TMA) {
-                ObsT* tk = tile + (k & (NT1 - 1)) * (32 * D1_OBS);
-                if (k >= NT1) {                             // the copy that read this ring slot NT1 steps ago has drained it
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NT1 - 1) : "memory");
-                    __syncwarp();
-                }
-                stage_observe1<ObsT, B1>(g, e, tk + lane * D1_OBS, normalise, total_brick, st.total_step);
-                if (nvalid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-                    warp_tile_bulk_store(dst, tk, 32 * D1_OBS * sizeof(ObsT), lane);
-                } else {
-                    __syncwarp();
-                    if (nvalid > 0) warp_tile_store<ObsT>(dst, tk, nvalid * D1_OBS, lane);
-                    __syncwarp();
-                }
+        uint32_t q0 = 0, q1 = 0, q2 = 0;
+        if (want_obs) {
+            if constexpr (REC) {
+                window1<B1>(g, e, q0, q1, q2);                  // the record is assembled once the reward is known
             } else {
                 stage_observe1<ObsT, B1>(g, e, tile + lane * D1_OBS, normalise, total_brick, st.total_step);
                 __syncwarp();
-                if (nvalid == 32) warp_tile_store_full<ObsT, 32 * D1_OBS>(dst, tile, lane);
+                if constexpr (FAST) warp_tile_store_aligned<ObsT, 32 * D1_OBS>(dst, tile, lane);
+                else if (nvalid == 32) warp_tile_store_full<ObsT, 32 * D1_OBS>(dst, tile, lane);
                 else if (nvalid > 0) warp_tile_store<ObsT>(dst, tile, nvalid * D1_OBS, lane);
                 __syncwarp();
             }
@@ -185,8 +190,11 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
         const float reward = rewarded ? ((h > p) ? -1.f : (h == p ? 10.f : 1.f)) : 0.f;
         e.ret += reward;
         if (live) {
-            if (io.reward) io.reward[idx] = reward;
-            if (io.done) io.done[idx] = done ? 1 : 0;
+            if constexpr (REC) {
+                if (want_obs) __stcs(reinterpret_cast<uint4*>(dst) + lane, make_rec16(q0, q1, q2, e.cb, e.cs, reward, done));
+            }
+            if (want_rew) io.reward[idx] = reward;
+            if (want_done) io.done[idx] = done ? 1 : 0;
         }
 
         if (done && autoreset && live) {
@@ -215,6 +223,10 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
     }
 
     if (live) {
+        if ((e.cb | e.cs) > 0xFFFF) {                                    // 16-bit packed counters (include/dmp.h)
+            errbits |= DMP_ERR_OVERFLOW;
+            e.cb = min(e.cb, 0xFFFF); e.cs = min(e.cs, 0xFFFF);
+        }
         if (dirty & 1u) cells[env] = make_uint4(g[1 * B1], g[2 * B1], g[3 * B1], g[4 * B1]);
         if (dirty & 2u) cells[n + env] = make_uint4(g[5 * B1], g[6 * B1], g[7 * B1], g[8 * B1]);
         if (dirty & 4u) cells[2 * n + env] = make_uint4(g[9 * B1], g[10 * B1], g[11 * B1], g[12 * B1]);
@@ -224,7 +236,6 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
         if (errbits) atomicOr(st.err, errbits);
     }
     if (st.t_dev && blockIdx.x == 0 && tid == 0) st.t_dev[tslot ^ 1] = t0 + (uint64_t)K;
-    if constexpr (TMA) warp_tile_bulk_wait(lane);                        // the tiles must outlive the copies that read them
 }
 
 template <typename ObsT>
@@ -242,17 +253,24 @@ __global__ void k1d_reset(const DmpState st, const uint8_t* __restrict__ mask, c
     } else if (st.plan_mode == DMP_PLAN_PHILOX) {
         p = draw_plan(env_draw(st.seed, (uint64_t)(st.env_base + env), t_draw).x3, st.n_plans);
     } else {
-        p = (int)(aux[env].x >> 16);
-        if (st.plan_mode == DMP_PLAN_SEQUENTIAL) p = (p + 1 >= st.n_plans) ? 0 : p + 1;
+        const uint32_t ax = aux[env].x;
+        p = (int)(ax >> 16);
+        // sequential order starts at plan 0 on an env that has never been reset (zeroed state: 0 is not a position),
+        // index_for_non_random = 0 of Env/1D/DMP_Env_1D_dynamic_usedata_plan.py:46-50
+        if (st.plan_mode == DMP_PLAN_SEQUENTIAL) p = ((ax & 0xFFFFu) == 0u) ? 0 : ((p + 1 >= st.n_plans) ? 0 : p + 1);
         if ((unsigned)p >= (unsigned)st.n_plans) p = 0;
     }
     const uint4 z = make_uint4(0, 0, 0, 0);
     cells[env] = z; cells[n + env] = z; cells[2 * n + env] = z; cells[3 * n + env] = z;
     aux[env] = make_uint2((uint32_t)D1_LO | ((uint32_t)p << 16), 0u);
     if (obs) {                       // window at pos 2: [-1, -1, 0, 0, 0], counters 0 (:81-83)
-        ObsT* o = obs + env * D1_OBS;
-        o[0] = obs_from_int<ObsT>(-1); o[1] = obs_from_int<ObsT>(-1);
-        for (int j = 2; j < 7; ++j) o[j] = obs_from_int<ObsT>(0);
+        if constexpr (is_rec<ObsT>::value) {
+            reinterpret_cast<uint4*>(obs)[env] = make_rec16(0xFFFFFFFFu, 0u, 0u, 0, 0, 0.f, false);
+        } else {
+            ObsT* o = obs + env * D1_OBS;
+            o[0] = obs_from_int<ObsT>(-1); o[1] = obs_from_int<ObsT>(-1);
+            for (int j = 2; j < 7; ++j) o[j] = obs_from_int<ObsT>(0);
+        }
     }
 }
 
@@ -315,31 +333,37 @@ __global__ void k1d_import(const DmpState st, const int32_t* __restrict__ grid, 
     aux[env] = ax;
 }
 
-template <typename ObsT, int B1, bool TMA>
-int launch_rollout1_b(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
-    const size_t smem = (size_t)S1_WORDS * B1 * 4 + (size_t)(B1 / 32) * (TMA ? NT1 : 1) * 32 * D1_OBS * sizeof(ObsT);
+template <typename ObsT, int B1, bool FAST>
+int launch_rollout1_k(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    const size_t smem = (size_t)S1_WORDS * B1 * 4 + (is_rec<ObsT>::value ? 0 : (size_t)(B1 / 32) * 32 * D1_OBS * sizeof(ObsT));
     const unsigned blocks = (unsigned)((st.n_envs + B1 - 1) / B1);
     static bool attr_done = false;           // per instantiation
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k1d_rollout<ObsT, B1, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k1d_rollout<ObsT, B1, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return dmp_set_error(e);
         attr_done = true;
     }
     // plain stream-ordered launch: with programmatic dependent launch the next grid's single-warp blocks become
     // resident early and unbalance the SMs (measured: 47 vs 61 G env-steps/s at 65 536 envs, K = 16)
-    k1d_rollout<ObsT, B1, TMA><<<blocks, B1, smem, s>>>(st, io, K);
+    k1d_rollout<ObsT, B1, FAST><<<blocks, B1, smem, s>>>(st, io, K);
     return dmp_set_error(cudaGetLastError());
+}
+
+template <typename ObsT, int B1>
+int launch_rollout1_b(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    // the throughput configuration (see k1d_rollout, FAST) gets the kernel with its launch-uniform branches folded
+    const bool fast = !(io.flags & DMP_F_GENERIC) && !io.actions && !io.step_sizes && io.obs && io.reward && io.done &&
+                      (io.flags & DMP_F_AUTORESET) && !(io.flags & DMP_F_NORMALISE) && st.n_envs % B1 == 0 &&
+                      (reinterpret_cast<uintptr_t>(io.obs) & 15) == 0 && (st.n_envs * (int64_t)D1_OBS * (int64_t)sizeof(ObsT)) % 16 == 0;
+    if (fast) return launch_rollout1_k<ObsT, B1, true>(st, io, K, s);
+    return launch_rollout1_k<ObsT, B1, false>(st, io, K, s);
 }
 
 template <typename ObsT>
 int launch_rollout1(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
-    // DMP_TILE_COPY (tuning switch): b = bulk async copy-out of the observation tile, l = load/store copy-out
-    const char* v = getenv("DMP_TILE_COPY");
-    const bool tma = DMP_1D_TMA_DEFAULT ? !(v && v[0] == 'l') : (v && v[0] == 'b');
     // fewer than ~4 blocks of 128 per SM: single-warp blocks spread the warps evenly over the 148 SMs
     const bool small = st.n_envs < (int64_t)128 * 148 * 4;
-    if (tma) return small ? launch_rollout1_b<ObsT, 32, true>(st, io, K, s) : launch_rollout1_b<ObsT, 128, true>(st, io, K, s);
-    return small ? launch_rollout1_b<ObsT, 32, false>(st, io, K, s) : launch_rollout1_b<ObsT, 128, false>(st, io, K, s);
+    return small ? launch_rollout1_b<ObsT, 32>(st, io, K, s) : launch_rollout1_b<ObsT, 128>(st, io, K, s);
 }
 
 }  // namespace
@@ -349,6 +373,7 @@ int dmp1d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
         case DMP_OBS_F32: return launch_rollout1<float>(st, io, K, s);
         case DMP_OBS_F64: return launch_rollout1<double>(st, io, K, s);
         case DMP_OBS_I16: return launch_rollout1<int16_t>(st, io, K, s);
+        case DMP_OBS_REC: return launch_rollout1<Rec16>(st, io, K, s);
     }
     return DMP_EINVAL;
 }
@@ -360,6 +385,7 @@ int dmp1d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx
         case DMP_OBS_F32: k1d_reset<float><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (float*)obs); break;
         case DMP_OBS_F64: k1d_reset<double><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (double*)obs); break;
         case DMP_OBS_I16: k1d_reset<int16_t><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (int16_t*)obs); break;
+        case DMP_OBS_REC: k1d_reset<Rec16><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (Rec16*)obs); break;
         default: return DMP_EINVAL;
     }
     return dmp_set_error(cudaGetLastError());

@@ -10,7 +10,6 @@
 // cut out of the bit grid with funnel shifts, expanded into the warp's [32][51] observation tile in
 // shared memory and streamed out as one contiguous, 16 B aligned span with 128-bit stores.
 // K > 1 keeps the state on chip between steps (rollout mode).
-#include <stdlib.h>
 #include "dmp_common.cuh"
 
 namespace {
@@ -64,9 +63,11 @@ __device__ __forceinline__ uint32_t stage_deposit2(uint32_t* g, const Env2& e, i
 }
 
 // stage (c): observation window -> this thread's row of the warp tile.  observation_ :78-82 + hstack.
+// For a record row (Rec56) the seven row codes ARE the window bytes; reward and done ride along.
 template <typename ObsT>
 __device__ __forceinline__ void stage_observe2(const uint32_t* g, const Env2& e, ObsT* row,
-                                               bool normalise, int total_brick, int total_step) {
+                                               bool normalise, int total_brick, int total_step,
+                                               float reward = 0.f, bool done = false) {
     // rows pr-3 .. pr+3 of the padded grid are interior rows pr-6 .. pr; the grid words are stored
     // behind 64 zero bits so that the 143-bit span [B0, B0+143) is always in range.  Starting 3 bits
     // early puts interior column c of every row at bit c+3 = its padded column.
@@ -88,24 +89,36 @@ __device__ __forceinline__ void stage_observe2(const uint32_t* g, const Env2& e,
     const int sh = e.pc - D2_HW;                       // window column 0 = padded column pc-3
     const uint32_t colvalid = (COLVALID >> sh) & 0x7Fu;
     const uint64_t vcode = spread7(colvalid);          // 1 where the window column is inside the plan area
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
+    // inside: 0/1 ; frame: -1  (environment_memory[...] = -1, :61-64)  ->  code = value + 1
+    auto row_code = [&](int k) -> uint64_t {
         const int p = e.pr - D2_HW + k;                // padded row of window row k
         const bool rowvalid = (unsigned)(p - D2_HW) < (unsigned)D2_W;
         const uint32_t occ = (R[k] >> sh) & colvalid;
-        // inside: 0/1 ; frame: -1  (environment_memory[...] = -1, :61-64)  ->  code = value + 1
-        const uint64_t code = rowvalid ? spread7(occ) + vcode : 0ull;
-        const uint32_t lo = (uint32_t)code, hi = (uint32_t)(code >> 32);
-        ObsT* o = row + k * 7;
-        o[0] = obs_from_biased<ObsT, 0>(lo);
-        o[1] = obs_from_biased<ObsT, 1>(lo);
-        o[2] = obs_from_biased<ObsT, 2>(lo);
-        o[3] = obs_from_biased<ObsT, 3>(lo);
-        o[4] = obs_from_biased<ObsT, 0>(hi);
-        o[5] = obs_from_biased<ObsT, 1>(hi);
-        o[6] = obs_from_biased<ObsT, 2>(hi);
+        return rowvalid ? spread7(occ) + vcode : 0ull;
+    };
+    if constexpr (is_rec<ObsT>::value) {
+        uint64_t codes[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) codes[k] = row_code(k);
+        uint32_t w[13];
+        pack49(codes, w);
+        rec56_store(row, w, e.cb, e.cs, reward, done, false);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const uint64_t code = row_code(k);
+            const uint32_t lo = (uint32_t)code, hi = (uint32_t)(code >> 32);
+            ObsT* o = row + k * 7;
+            o[0] = obs_from_biased<ObsT, 0>(lo);
+            o[1] = obs_from_biased<ObsT, 1>(lo);
+            o[2] = obs_from_biased<ObsT, 2>(lo);
+            o[3] = obs_from_biased<ObsT, 3>(lo);
+            o[4] = obs_from_biased<ObsT, 0>(hi);
+            o[5] = obs_from_biased<ObsT, 1>(hi);
+            o[6] = obs_from_biased<ObsT, 2>(hi);
+        }
+        obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, total_step, row[49], row[50]);
     }
-    obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, total_step, row[49], row[50]);
 }
 
 // stage (d) helper: IoU = |G & P| / |G | P| over the interior (render :169-175) with warp-free popc.
@@ -122,18 +135,20 @@ __device__ __forceinline__ double iou2(const uint32_t* g, const uint32_t* __rest
 
 // TMA = true: the warp tile leaves through one bulk async copy (dmp_common.cuh: warp_tile_bulk_store) instead of 13 x
 // (LDS.128 + STG.128) per lane: the L1 data pipe was the busiest unit of this kernel (ncu: 69 %).
+// ObsT = float / double / int16_t: [n][51] observation rows; ObsT = Rec56: one packed 56 B step record per env.
 template <typename ObsT, bool TMA>
 __global__ void __launch_bounds__(B2, TMA ? 6 : 7) k2d_rollout(const DmpState st, const DmpIO io, const int K) {
+    constexpr int ROW = row_elems<ObsT, D2_OBS>();                       // tile elements per env (51 values or 1 record)
     extern __shared__ uint4 smem_raw[];
     uint32_t* G = reinterpret_cast<uint32_t*>(smem_raw);                 // [S2_WORDS][B2]
-    ObsT* tiles = reinterpret_cast<ObsT*>(G + S2_WORDS * B2);            // [B2/32][32*51]
+    ObsT* tiles = reinterpret_cast<ObsT*>(G + S2_WORDS * B2);            // [B2/32][32*ROW]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t n = st.n_envs;
     const int64_t env = (int64_t)blockIdx.x * B2 + tid;
     const int64_t env0 = env - lane;                                     // first env of this warp
     const int nvalid = (int)min((int64_t)32, n - env0);                  // <= 0: idle warp
     const bool live = env < n;
-    ObsT* tile = tiles + warp * (32 * D2_OBS);
+    ObsT* tile = tiles + warp * (32 * ROW);
     uint32_t* g = G + tid;
 
     uint4* cells = reinterpret_cast<uint4*>(st.cells);
@@ -211,21 +226,21 @@ __global__ void __launch_bounds__(B2, TMA ? 6 : 7) k2d_rollout(const DmpState st
 
         // ---- (c) observation ------------------------------------------------------------------
         if (io.obs) {
-            ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * D2_OBS;
+            ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * ROW;
             if constexpr (TMA) {
                 if (k > 0) warp_tile_bulk_wait(lane);               // the previous step's copy has drained the tile
-                stage_observe2<ObsT>(g, e, tile + lane * D2_OBS, normalise, total_brick, st.total_step);
+                stage_observe2<ObsT>(g, e, tile + lane * ROW, normalise, total_brick, st.total_step, reward, done);
                 if (nvalid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-                    warp_tile_bulk_store(dst, tile, 32 * D2_OBS * sizeof(ObsT), lane);
+                    warp_tile_bulk_store(dst, tile, 32 * ROW * sizeof(ObsT), lane);
                 } else {
                     __syncwarp();
-                    if (nvalid > 0) warp_tile_store<ObsT>(dst, tile, nvalid * D2_OBS, lane);
+                    if (nvalid > 0) tile_rows_store<ObsT, D2_OBS>(dst, tile, nvalid, lane);
                 }
             } else {
-                stage_observe2<ObsT>(g, e, tile + lane * D2_OBS, normalise, total_brick, st.total_step);
+                stage_observe2<ObsT>(g, e, tile + lane * ROW, normalise, total_brick, st.total_step, reward, done);
                 __syncwarp();
-                if (nvalid == 32) warp_tile_store_full<ObsT, 32 * D2_OBS>(dst, tile, lane);
-                else if (nvalid > 0) warp_tile_store<ObsT>(dst, tile, nvalid * D2_OBS, lane);
+                if (nvalid == 32) tile_rows_store_full<ObsT, D2_OBS>(dst, tile, lane);
+                else if (nvalid > 0) tile_rows_store<ObsT, D2_OBS>(dst, tile, nvalid, lane);
             }
             __syncwarp();
         }
@@ -260,6 +275,10 @@ __global__ void __launch_bounds__(B2, TMA ? 6 : 7) k2d_rollout(const DmpState st
     }
 
     if (live) {
+        if ((e.cb | e.cs) > 0xFFFF) {                                    // 16-bit packed counters (include/dmp.h)
+            errbits |= DMP_ERR_OVERFLOW;
+            e.cb = min(e.cb, 0xFFFF); e.cs = min(e.cs, 0xFFFF);
+        }
         pack2(e, g[14 * B2], v3);
         if (hint) {
             if (dirty & 1u) stg_keep(cells + env, make_uint4(g[2 * B2], g[3 * B2], g[4 * B2], g[5 * B2]), keep);
@@ -295,8 +314,11 @@ __global__ void k2d_reset(const DmpState st, const uint8_t* __restrict__ mask, c
     } else if (st.plan_mode == DMP_PLAN_PHILOX) {
         p = draw_plan(env_draw(st.seed, (uint64_t)(st.env_base + env), t_draw).x3, st.n_plans);
     } else {
-        p = (int)(cells[3 * n + env].y >> 16);
-        if (st.plan_mode == DMP_PLAN_SEQUENTIAL) p = (p + 1 >= st.n_plans) ? 0 : p + 1;
+        const uint32_t w13 = cells[3 * n + env].y;
+        p = (int)(w13 >> 16);
+        // sequential order starts at plan 0 on an env that has never been reset (zeroed state: row 0 is not a position),
+        // index_for_non_random = 0 of Env/2D/DMP_Env_2D_dynamic_usedata_plan.py:39-44
+        if (st.plan_mode == DMP_PLAN_SEQUENTIAL) p = ((w13 & 0xFFu) == 0u) ? 0 : ((p + 1 >= st.n_plans) ? 0 : p + 1);
         if ((unsigned)p >= (unsigned)st.n_plans) p = 0;
     }
     const uint4 z = make_uint4(0, 0, 0, 0);
@@ -305,11 +327,16 @@ __global__ void k2d_reset(const DmpState st, const uint8_t* __restrict__ mask, c
     uint4 v3; pack2(e, 0u, v3);
     cells[3 * n + env] = v3;
     if (obs) {                       // window at [3,3] of an empty grid: rows/cols 0..2 are frame
-        ObsT* o = obs + env * D2_OBS;
-        for (int k = 0; k < 7; ++k)
-            for (int j = 0; j < 7; ++j) o[k * 7 + j] = obs_from_int<ObsT>((k < 3 || j < 3) ? -1 : 0);
-        o[49] = obs_from_int<ObsT>(0);
-        o[50] = obs_from_int<ObsT>(0);
+        if constexpr (is_rec<ObsT>::value) {
+            uint8_t* o = reinterpret_cast<uint8_t*>(obs + env);
+            for (int i = 0; i < 56; ++i) o[i] = (i < 49 && i / 7 >= 3 && i % 7 >= 3) ? 1 : 0;
+        } else {
+            ObsT* o = obs + env * D2_OBS;
+            for (int k = 0; k < 7; ++k)
+                for (int j = 0; j < 7; ++j) o[k * 7 + j] = obs_from_int<ObsT>((k < 3 || j < 3) ? -1 : 0);
+            o[49] = obs_from_int<ObsT>(0);
+            o[50] = obs_from_int<ObsT>(0);
+        }
     }
 }
 
@@ -385,7 +412,7 @@ __global__ void k2d_import(const DmpState st, const int32_t* __restrict__ grid, 
 
 template <typename ObsT, bool TMA>
 int launch_rollout2_t(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
-    const size_t smem = (size_t)S2_WORDS * B2 * 4 + (size_t)(B2 / 32) * 32 * D2_OBS * sizeof(ObsT);
+    const size_t smem = (size_t)S2_WORDS * B2 * 4 + (size_t)(B2 / 32) * 32 * row_elems<ObsT, D2_OBS>() * sizeof(ObsT);
     static bool attr_done = false;           // per instantiation
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k2d_rollout<ObsT, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -393,14 +420,14 @@ int launch_rollout2_t(const DmpState& st, const DmpIO& io, int K, cudaStream_t s
         attr_done = true;
     }
     const unsigned blocks = (unsigned)((st.n_envs + B2 - 1) / B2);
-    return dmp_set_error(dmp_launch_pdl(k2d_rollout<ObsT, TMA>, blocks, (unsigned)B2, smem, s, st, io, K));
+    return dmp_set_error(dmp_launch_pdl(!(io.flags & DMP_F_NO_PDL), k2d_rollout<ObsT, TMA>, blocks, (unsigned)B2, smem, s,
+                                        st, io, K));
 }
 
+// the observation tile leaves through one bulk async copy per warp and step unless DMP_F_TILE_LDST asks for load/store pairs
 template <typename ObsT>
 int launch_rollout2(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
-    // DMP_TILE_COPY (tuning switch): l = load/store copy-out of the observation tile, b = bulk async copy (default)
-    const char* v = getenv("DMP_TILE_COPY");
-    if (v && v[0] == 'l') return launch_rollout2_t<ObsT, false>(st, io, K, s);
+    if (io.flags & DMP_F_TILE_LDST) return launch_rollout2_t<ObsT, false>(st, io, K, s);
     return launch_rollout2_t<ObsT, true>(st, io, K, s);
 }
 
@@ -411,6 +438,7 @@ int dmp2d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
         case DMP_OBS_F32: return launch_rollout2<float>(st, io, K, s);
         case DMP_OBS_F64: return launch_rollout2<double>(st, io, K, s);
         case DMP_OBS_I16: return launch_rollout2<int16_t>(st, io, K, s);
+        case DMP_OBS_REC: return launch_rollout2<Rec56>(st, io, K, s);
     }
     return DMP_EINVAL;
 }
@@ -422,6 +450,7 @@ int dmp2d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx
         case DMP_OBS_F32: k2d_reset<float><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (float*)obs); break;
         case DMP_OBS_F64: k2d_reset<double><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (double*)obs); break;
         case DMP_OBS_I16: k2d_reset<int16_t><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (int16_t*)obs); break;
+        case DMP_OBS_REC: k2d_reset<Rec56><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (Rec56*)obs); break;
         default: return DMP_EINVAL;
     }
     return dmp_set_error(cudaGetLastError());

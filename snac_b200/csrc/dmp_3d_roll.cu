@@ -19,19 +19,17 @@
 //   * done     : IoU needs no scan (`cross` is maintained by every build); the warp clears a finished env's
 //                map cooperatively in shared memory and in HBM.
 // Semantics: Env/3D/DMP_simulator_3d_static_circle.py:67-276 and
-// Env/3D/DMP_simulator_3d_dynamic_triangle_usedata.py:45-277 (same citations as dmp_3d.cu, whose warp-per-env
-// kernel and dmp_3d_tile.cu's u16 tile kernel remain as cross-checks; tests compare all three).
-#include <stdlib.h>
-#include "dmp_common.cuh"
+// Env/3D/DMP_simulator_3d_dynamic_triangle_usedata.py:45-277 (line-by-line citations in the kernel body).
+#include "dmp_3d_bulk.cuh"
 
 namespace {
+
+using namespace d3;
 
 constexpr int MAP_B = 404;                    // bytes per env in the cache: 400 cells + 4 pad = 101 words (odd)
 constexpr int FRONT = 80;                     // guard in front of env 0 of a warp: unclamped reads reach 64 B back
 constexpr int WARP_MAP_B = FRONT + 32 * MAP_B;  // 13 008 (multiple of 16); reads past the end land in the next
                                               // warp's guard or in the tiles
-constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr uint32_t COLVALID = 0x7FFFF8u;      // padded columns 3..22 are inside the plan area
 constexpr size_t SMEM_MAX = 232448;           // 227 KB opt-in limit per block
 
 struct EnvR {
@@ -39,9 +37,6 @@ struct EnvR {
     float ret;
     int cross;      // running sum(min(height, plan)): +1 per brick laid at or below the plan height
 };
-
-__device__ __forceinline__ int dir_dr(int d) { return d == 2 ? 1 : (d == 3 ? -1 : 0); }
-__device__ __forceinline__ int dir_dc(int d) { return d == 0 ? -1 : (d == 1 ? 1 : 0); }
 
 // environment_memory[r][c] (padded coordinates) from HBM (tall envs only); -1 on the frame (:72-75).
 // .cg: other lanes of the warp clear maps with plain stores.
@@ -63,12 +58,19 @@ __device__ __noinline__ void observe_tall(const uint16_t* ge, int pr, int pc, Ob
     for (int k = 0; k < 7; ++k)
         for (int j = 0; j < 7; ++j) row[k * 7 + j] = obs_from_int<ObsT>(cell_g(ge, pr - 3 + k, pc - 3 + j));
 }
+// the same as record bytes (value + 1, saturating at 255; the record carries DMP_REC_SATURATED)
+__device__ __noinline__ void window_tall_bytes(const uint16_t* ge, int pr, int pc, uint64_t (&c)[7]) {
+    for (int k = 0; k < 7; ++k) {
+        uint64_t v = 0;
+        for (int j = 0; j < 7; ++j) v |= (uint64_t)min(cell_g(ge, pr - 3 + k, pc - 3 + j) + 1, 255) << (8 * j);
+        c[k] = v;
+    }
+}
 
 // stage (c): 7x7 window of this lane's env (byte cache) -> its row of the warp tile.  The seven rows are
 // read at fixed word offsets from one base (rows outside the map land in the guards / the neighbouring
 // env and are masked), so no per-row clamping or address arithmetic is needed.
-template <typename ObsT>
-__device__ __forceinline__ void observe_cache(const uint8_t* gb, int pr, int pc, ObsT* row) {
+__device__ __forceinline__ void window_cache(const uint8_t* gb, int pr, int pc, uint32_t (&u0)[7], uint32_t (&u1)[7]) {
     const uint32_t cv = (COLVALID >> (pc - 3)) & 0x7Fu;           // window column j lies inside the plan area
     const uint64_t one = spread7(cv);                              // 0x01 per valid byte
     const uint32_t b0 = (uint32_t)one, b1 = (uint32_t)(one >> 32);
@@ -81,27 +83,37 @@ __device__ __forceinline__ void observe_cache(const uint8_t* gb, int pr, int pc,
         const bool rowvalid = (unsigned)(pr - 6 + k) < 20u;        // interior row of window row k
         const uint32_t x0 = rw[5 * k], x1 = rw[5 * k + 1], x2 = rw[5 * k + 2];
         const uint32_t q0 = __funnelshift_r(x0, x1, shb), q1 = __funnelshift_r(x1, x2, shb);
-        const uint32_t u0 = rowvalid ? ((q0 & m0) + b0) : 0u;
-        const uint32_t u1 = rowvalid ? ((q1 & m1) + b1) : 0u;
+        u0[k] = rowvalid ? ((q0 & m0) + b0) : 0u;                  // biased bytes: height + 1, 0 = frame
+        u1[k] = rowvalid ? ((q1 & m1) + b1) : 0u;
+    }
+}
+template <typename ObsT>
+__device__ __forceinline__ void observe_cache(const uint8_t* gb, int pr, int pc, ObsT* row) {
+    uint32_t u0[7], u1[7];
+    window_cache(gb, pr, pc, u0, u1);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
         ObsT* o7 = row + k * 7;
-        o7[0] = obs_from_biased<ObsT, 0>(u0);
-        o7[1] = obs_from_biased<ObsT, 1>(u0);
-        o7[2] = obs_from_biased<ObsT, 2>(u0);
-        o7[3] = obs_from_biased<ObsT, 3>(u0);
-        o7[4] = obs_from_biased<ObsT, 0>(u1);
-        o7[5] = obs_from_biased<ObsT, 1>(u1);
-        o7[6] = obs_from_biased<ObsT, 2>(u1);
+        o7[0] = obs_from_biased<ObsT, 0>(u0[k]);
+        o7[1] = obs_from_biased<ObsT, 1>(u0[k]);
+        o7[2] = obs_from_biased<ObsT, 2>(u0[k]);
+        o7[3] = obs_from_biased<ObsT, 3>(u0[k]);
+        o7[4] = obs_from_biased<ObsT, 0>(u1[k]);
+        o7[5] = obs_from_biased<ObsT, 1>(u1[k]);
+        o7[6] = obs_from_biased<ObsT, 2>(u1[k]);
     }
 }
 
 // shared memory: [WPB][WARP_MAP_B] byte maps | [WPB][32*51] ObsT tiles
 template <typename ObsT>
-__host__ __device__ constexpr size_t warp_smem_bytes() { return (size_t)WARP_MAP_B + 32 * D3_OBS * sizeof(ObsT); }
+__host__ __device__ constexpr size_t warp_smem_bytes() { return (size_t)WARP_MAP_B + 32 * row_elems<ObsT, D3_OBS>() * sizeof(ObsT); }
 
 // TMA = true: each step's warp tile leaves through one bulk async copy (dmp_common.cuh: warp_tile_bulk_store).
 template <typename ObsT, bool TMA>
-__global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, const DmpIO io, const int K) {
+__global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const DmpIO io, const int K) {
     extern __shared__ uint4 smem_raw[];
+    constexpr bool REC = is_rec<ObsT>::value;
+    constexpr int ROW = row_elems<ObsT, D3_OBS>();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int64_t n = st.n_envs;
     const int64_t env0 = ((int64_t)blockIdx.x * wpb + warp) * 32;
@@ -112,7 +124,7 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
 
     uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw);
     uint8_t* wmap = base + (size_t)warp * WARP_MAP_B + FRONT;
-    ObsT* tile = reinterpret_cast<ObsT*>(base + (size_t)wpb * WARP_MAP_B) + warp * (32 * D3_OBS);
+    ObsT* tile = reinterpret_cast<ObsT*>(base + (size_t)wpb * WARP_MAP_B) + warp * (32 * ROW);
     uint8_t* gb = wmap + lane * MAP_B;                                // this lane's byte map
 
     uint16_t* cells = reinterpret_cast<uint16_t*>(st.cells);
@@ -255,32 +267,53 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
         }
         if (tail) done = (e.cs >= st.total_step) || (!dynamic && boxed);
 
-        // ---- (c) observation --------------------------------------------------------------------
+        // ---- (c) observation; (d) reward (reward_check :232-239) -------------------------------------------
+        // The plan byte requested at build time is consumed only after the window has been formatted, which hides its
+        // latency.  A record row (DMP_OBS_REC) carries the reward, so it is closed after (d); observation rows leave first.
+        float reward = 0.f;
+        auto reward_now = [&]() {
+            if (built) {
+                if (newh <= pplan) e.cross += 1;
+                if (!tail && !done) reward = (newh > pplan) ? -1.f : (newh == pplan ? 10.f : 1.f);
+            }
+            if (boxed_penalty) reward = -100.f;
+        };
         if (io.obs) {
             if (TMA && bulk_pending) { warp_tile_bulk_wait(lane); bulk_pending = false; }   // previous copy has drained the tile
-            ObsT* row = tile + lane * D3_OBS;
-            if (!tall) observe_cache<ObsT>(gb, e.pr, e.pc, row);
-            else observe_tall<ObsT>(ge, e.pr, e.pc, row);
-            obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, st.total_step, row[49], row[50]);
-            ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * D3_OBS;
+            ObsT* row = tile + lane * ROW;
+            if constexpr (REC) {
+                uint64_t c[7];
+                if (!tall) {
+                    uint32_t u0[7], u1[7];
+                    window_cache(gb, e.pr, e.pc, u0, u1);
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) c[k] = (uint64_t)u0[k] | ((uint64_t)u1[k] << 32);
+                } else {
+                    window_tall_bytes(ge, e.pr, e.pc, c);
+                }
+                uint32_t w[13];
+                pack49(c, w);
+                reward_now();
+                rec56_store(row, w, e.cb, e.cs, reward, done, tall);
+            } else {
+                if (!tall) observe_cache<ObsT>(gb, e.pr, e.pc, row);
+                else observe_tall<ObsT>(ge, e.pr, e.pc, row);
+                obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, st.total_step, row[49], row[50]);
+            }
+            ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * ROW;
             if (TMA && nvalid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-                warp_tile_bulk_store(dst, tile, 32 * D3_OBS * sizeof(ObsT), lane);
+                warp_tile_bulk_store(dst, tile, 32 * ROW * sizeof(ObsT), lane);
                 bulk_pending = true;
             } else {
                 __syncwarp();
-                if (nvalid == 32) warp_tile_store_full<ObsT, 32 * D3_OBS>(dst, tile, lane);
-                else warp_tile_store<ObsT>(dst, tile, nvalid * D3_OBS, lane);
+                if (nvalid == 32) tile_rows_store_full<ObsT, D3_OBS>(dst, tile, lane);
+                else tile_rows_store<ObsT, D3_OBS>(dst, tile, nvalid, lane);
                 __syncwarp();
             }
+            if constexpr (!REC) reward_now();
+        } else {
+            reward_now();
         }
-
-        // ---- (d) reward (reward_check :232-239); the plan byte requested above has arrived by now -------
-        float reward = 0.f;
-        if (built) {
-            if (newh <= pplan) e.cross += 1;
-            if (!tail && !done) reward = (newh > pplan) ? -1.f : (newh == pplan ? 10.f : 1.f);
-        }
-        if (boxed_penalty) reward = -100.f;
         e.ret += reward;
         if (live) {
             if (io.reward) io.reward[idx] = reward;
@@ -328,6 +361,10 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
         __syncwarp();
     }
     if (live) {
+        if ((e.cb | e.cs) > 0xFFFF) {                                 // 16-bit packed counters (include/dmp.h)
+            errbits |= DMP_ERR_OVERFLOW;
+            e.cb = min(e.cb, 0xFFFF); e.cs = min(e.cs, 0xFFFF);
+        }
         aux[env] = make_uint4((uint32_t)e.pr | (tall ? AUX3_TALL : 0u) | ((uint32_t)e.pc << 8) | ((uint32_t)e.plan_idx << 16),
                               (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16), __float_as_uint(e.ret), (uint32_t)e.cross);
         if (acc_cnt) {                                      // this thread is the only writer of its env's statistics
@@ -342,37 +379,32 @@ __global__ void __launch_bounds__(352) k3d_cache_rollout(const DmpState st, cons
     if (TMA && bulk_pending) warp_tile_bulk_wait(lane);                 // the tile must outlive the copy that reads it
 }
 
-// Launch shape.  Every warp is an independent tile of 32 envs, so blocks are single warps unless DMP_3D_WPB
-// says otherwise: the block scheduler then refills an SM warp by warp instead of waiting for the slowest
-// warp of a big block.  Shared memory alone limits residency (11 warps per SM for f32 observations).
+// Launch shape.  Every warp is an independent tile of 32 envs, so blocks are single warps: the block scheduler then refills
+// an SM warp by warp instead of waiting for the slowest warp of a big block (three-warp blocks: 16.6 vs 19.3 G env-steps/s).
+// Shared memory alone limits residency (11 warps per SM for f32 observations).
 template <typename ObsT, bool TMA>
 int launch_cache_t(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
-    const char* wv = getenv("DMP_3D_WPB");
-    const int wpb_env = wv ? atoi(wv) : 0;
-    const size_t per_warp = warp_smem_bytes<ObsT>();
-    const int wmax = (int)((SMEM_MAX - 16) / per_warp);
-    int wpb = wpb_env > 0 ? wpb_env : 1;
-    if (wpb > wmax) wpb = wmax;
-    if (wpb > 11) wpb = 11;                                  // __launch_bounds__(352)
-    const size_t smem = (size_t)wpb * per_warp + 16;
-    static size_t attr_smem = 0;                             // per instantiation
-    if (smem > attr_smem) {
+    constexpr int wpb = 1;
+    const size_t smem = (size_t)wpb * warp_smem_bytes<ObsT>() + 16;
+    static_assert(warp_smem_bytes<ObsT>() + 16 <= SMEM_MAX, "one warp's byte cache + tile must fit a block");
+    static bool attr_done = false;                           // per instantiation
+    if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k3d_cache_rollout<ObsT, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return dmp_set_error(e);
         e = cudaFuncSetAttribute(k3d_cache_rollout<ObsT, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return dmp_set_error(e);
-        attr_smem = smem;
+        attr_done = true;
     }
     const int64_t warps = (st.n_envs + 31) / 32;
     const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
-    return dmp_set_error(dmp_launch_pdl(k3d_cache_rollout<ObsT, TMA>, blocks, (unsigned)(wpb * 32), smem, s, st, io, K));
+    return dmp_set_error(dmp_launch_pdl(!(io.flags & DMP_F_NO_PDL), k3d_cache_rollout<ObsT, TMA>, blocks,
+                                        (unsigned)(wpb * 32), smem, s, st, io, K));
 }
 
-// DMP_TILE_COPY (tuning switch): l = load/store copy-out of the observation tile, b = bulk async copy (default)
+// the observation tile leaves through one bulk async copy per warp and step unless DMP_F_TILE_LDST asks for load/store pairs
 template <typename ObsT>
 int launch_cache(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
-    const char* v = getenv("DMP_TILE_COPY");
-    if (v && v[0] == 'l') return launch_cache_t<ObsT, false>(st, io, K, s);
+    if (io.flags & DMP_F_TILE_LDST) return launch_cache_t<ObsT, false>(st, io, K, s);
     return launch_cache_t<ObsT, true>(st, io, K, s);
 }
 
@@ -383,6 +415,7 @@ int dmp3d_cache_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t
         case DMP_OBS_F32: return launch_cache<float>(st, io, K, s);
         case DMP_OBS_F64: return launch_cache<double>(st, io, K, s);
         case DMP_OBS_I16: return launch_cache<int16_t>(st, io, K, s);
+        case DMP_OBS_REC: return launch_cache<Rec56>(st, io, K, s);
     }
     return DMP_EINVAL;
 }

@@ -1,59 +1,101 @@
-// dmp_3d_step.cu -- 3D envs, single-step kernel (K = 1, dmp_step): one env per lane; only the bytes one step
-// can look at are fetched.
+// dmp_3d_step.cu -- 3D envs, single-step kernel (K = 1, dmp_step): the rows a step looks at are
+// staged from the BYTE maps (include/dmp.h: u8[n][400] behind the wide u16 maps, byte = min(h, 255)).
 //
-// A step reads the agent's movement cross (<= 6 cells, all within 3 cells of the agent) and the 7x7 window at
-// the NEW position.  Staging the whole 800 B map for that (dmp_3d_tile.cu) triples the HBM traffic of a step
-// (B_alg = 330 B); here
-//   * the six cells are plain 2-byte loads (the other coordinate is the agent's, so one test decides "frame");
-//   * the <= 7 map rows under the new window (<= 280 contiguous bytes) come in as ONE bulk async copy per env
-//     (cp.async.bulk -> UBLKCP, 16 B granules, completion on the warp's mbarrier) into a 336 B slot per lane;
-//   * a brick is patched into the staged rows after the copy has landed and written through to HBM with one
-//     2-byte store; observation tile / copy-out / finished-episode handling are those of the tile kernel.
+// A step touches bytes only.  (An earlier generation staged u16 rows and wrote every brick into a u16 map: 0.55 of the HBM
+// roofline -- a 2-byte store into a line that is not in L2 costs a 32 B read and a 32 B write of DRAM traffic, and clearing
+// an 800 B map per episode added 35 B per env-step.)  <= 224 B of byte rows per env land in a 240 B slot (15 granules of
+// 16 B: an odd count spreads same-offset words of the 32 lanes over 8 bank groups), 7.7 KB per warp, 28 resident warps
+// per SM; the window is cut out with 3 word reads + 2 funnel shifts per row; the brick goes to the byte map, whose line the
+// step has just read.  The action and the step size are known before anything is loaded, so ONE bulk async copy per env
+// (cp.async.bulk -> UBLKCP, completion on the warp's mbarrier) right after the scalar state fetches the 7 rows under the
+// old window plus `step_size` more rows in the direction of a vertical move; the six decision cells, the window at the new
+// position and the brick patch are served from that span; every lane pulls its window into registers, then the warp's
+// [32][51] observation tile is built over the drained slots and leaves through one bulk async copy.
+// Exactness (dmp_common.cuh): the bytes of an env ARE its heights until one reaches 254; from then on the env is
+// flagged tall, its wide u16 map is kept exact as well, a build on a saturated byte reads the true height there and the
+// observation row comes from there (out of line, practically never: plan height is 6).  Bricks of all other envs are
+// written through to the byte map only -- a 2-byte store into a cold u16 line costs 64 B of DRAM traffic.
 // Semantics: Env/3D/DMP_simulator_3d_static_circle.py:67-276 and
 // Env/3D/DMP_simulator_3d_dynamic_triangle_usedata.py:45-277 (see dmp_3d.cu for the line-by-line citations).
-#include "dmp_3d_u16.cuh"
+#include "dmp_3d_bulk.cuh"
 
 namespace {
 
-using namespace u16map;
+using namespace d3;
 
-constexpr int SLOT_B = 336;                  // per-lane staging: 16 B guard | <= 304 B of rows | 16 B guard
-constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr int WPB_STEP = 4;
+constexpr int SLOT3_B = 240;                 // per-lane staging: 16 B guard | <= 224 B of byte rows.  Word reads of the window
+                                             // run up to 8 B past the rows: into the next lane's guard (masked columns)
+
+// an env turns tall: its wide map := its (still exact) byte map, with the brick just laid.  Out of line, practically never.
+__device__ __noinline__ void widen_env(uint16_t* ge, const uint8_t* be, int ti, int newh) {
+    for (int i = 0; i < CELLS3D; ++i) ge[i] = (i == ti) ? (uint16_t)newh : (uint16_t)__ldcg(be + i);
+}
+
+// a tall env's observation row straight from its wide map
+template <typename ObsT>
+__device__ __noinline__ void observe_u16(const uint16_t* ge, int pr, int pc, ObsT* row) {
+    for (int k = 0; k < 7; ++k)
+        for (int j = 0; j < 7; ++j) {
+            const unsigned ir = (unsigned)(pr - 6 + k), ic = (unsigned)(pc - 6 + j);
+            row[k * 7 + j] = obs_from_int<ObsT>((ir < 20u && ic < 20u) ? (int)__ldcg(ge + ir * 20u + ic) : -1);
+        }
+}
+
+// the same as record bytes (value + 1, saturating at 255; the record carries DMP_REC_SATURATED)
+__device__ __noinline__ void window_u16_bytes(const uint16_t* ge, int pr, int pc, uint64_t (&c)[7]) {
+    for (int k = 0; k < 7; ++k) {
+        uint64_t v = 0;
+        for (int j = 0; j < 7; ++j) {
+            const unsigned ir = (unsigned)(pr - 6 + k), ic = (unsigned)(pc - 6 + j);
+            const int h = (ir < 20u && ic < 20u) ? (int)__ldcg(ge + ir * 20u + ic) : -1;
+            v |= (uint64_t)min(h + 1, 255) << (8 * j);
+        }
+        c[k] = v;
+    }
+}
+
+// per-warp shared memory: 32 slots, or the observation tile built over them when that is larger (f64)
+template <typename ObsT>
+__host__ __device__ constexpr size_t warp_area_bytes() {
+    return (size_t)32 * row_elems<ObsT, D3_OBS>() * sizeof(ObsT) > (size_t)32 * SLOT3_B
+               ? (size_t)32 * row_elems<ObsT, D3_OBS>() * sizeof(ObsT) : (size_t)32 * SLOT3_B;
+}
 
 template <typename ObsT>
-__global__ void __launch_bounds__(WPB_STEP * 32) k3d_step_rows(const DmpState st, const DmpIO io) {
+__global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, const DmpIO io) {
+    constexpr bool REC = is_rec<ObsT>::value;
+    constexpr int ROW = row_elems<ObsT, D3_OBS>();
     extern __shared__ uint4 smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int64_t n = st.n_envs;
-    const int64_t env0 = ((int64_t)blockIdx.x * WPB_STEP + warp) * 32;
-    if (env0 >= n) return;                                            // whole warp leaves together
+    const int64_t env0 = ((int64_t)blockIdx.x * wpb + warp) * 32;
+    if (env0 >= n) return;                                            // whole warp leaves together (no block-wide sync below)
     const int nvalid = (int)min((int64_t)32, n - env0);
     const bool live = lane < nvalid;
     const int64_t env = env0 + (live ? lane : 0);                     // idle lanes shadow env0 but never store
 
-    uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw);
-    uint8_t* slot = base + (size_t)(warp * 32 + lane) * SLOT_B;
-    ObsT* tile = reinterpret_cast<ObsT*>(base + (size_t)WPB_STEP * 32 * SLOT_B) + warp * (32 * D3_OBS);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(base + (size_t)WPB_STEP * 32 * (SLOT_B + D3_OBS * sizeof(ObsT))) + warp;
+    // shared memory: [wpb] warp areas (32 slots, re-used as the warp's observation tile) | [wpb] mbarriers | 16 B pad
+    constexpr size_t AREA_B = warp_area_bytes<ObsT>();
+    uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw) + (size_t)warp * AREA_B;
+    uint8_t* slot = base + (size_t)lane * SLOT3_B;
+    ObsT* tile = reinterpret_cast<ObsT*>(base);                       // aliases the slots (used after they are drained)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(smem_raw) + (size_t)wpb * AREA_B) + warp;
 
     uint16_t* cells = reinterpret_cast<uint16_t*>(st.cells);
     uint16_t* gwarp = cells + env0 * CELLS3D;
-    uint16_t* ge = cells + env * CELLS3D;                             // this lane's map in HBM
+    uint16_t* ge = cells + env * CELLS3D;                             // this lane's u16 map in HBM (canonical)
+    uint8_t* bwarp = bmap3(st) + env0 * CELLS3D;
+    uint8_t* be = bmap3(st) + env * CELLS3D;                          // ... and its byte shadow
     uint4* aux = reinterpret_cast<uint4*>(st.aux);
     const uint8_t* __restrict__ plans = reinterpret_cast<const uint8_t*>(st.plans);
 
     if (lane == 0) mbar_init(bar, 32);
-    EnvT e{D2_LO, D2_LO, 0, 0, 0, 0.f, 0};
-    {
-        const uint4 a = aux[env];
-        e.pr = a.x & 0xFF; e.pc = (a.x >> 8) & 0xFF; e.plan_idx = a.x >> 16;
-        e.cb = a.y & 0xFFFF; e.cs = a.y >> 16;
-        e.ret = __uint_as_float(a.z);
-        e.cross = (int)a.w;
-    }
-    int total_brick = __ldg(st.plan_total + e.plan_idx);
-    int errbits = 0;
+    pdl_launch_dependents();
+    pdl_wait();                                                       // the previous step's state is visible from here
+    // ---- round trip 1: scalar state (the draws do not depend on it and overlap its latency).  16 B per env: the whole
+    // array (4 MB at 262 144 envs) is kept in L2 (evict_last), so this round trip is an L2 hit, not a DRAM access
+    const uint64_t keep = l2_policy_keep();
+    const uint4 ax = ldg_keep(aux + env, keep);
     const bool dynamic = st.dynamic != 0;
     const bool autoreset = io.flags & DMP_F_AUTORESET;
     const bool normalise = io.flags & DMP_F_NORMALISE;
@@ -62,6 +104,7 @@ __global__ void __launch_bounds__(WPB_STEP * 32) k3d_step_rows(const DmpState st
     const uint64_t t = st.t_dev ? st.t_dev[tslot] : st.t;
     const uint64_t gid = (uint64_t)(st.env_base + env0) + (uint64_t)lane;
     const int64_t idx = env0 + lane;
+    int errbits = 0;
 
     StepDraws draws;
     uint32_t dw = 0;
@@ -71,18 +114,45 @@ __global__ void __launch_bounds__(WPB_STEP * 32) k3d_step_rows(const DmpState st
     if (io.step_sizes) s = live ? (int)io.step_sizes[idx] : 1; else s = draw_step_size(dw);
     if ((unsigned)(s - 1) > 2u) errbits |= DMP_ERR_STEPSIZE;
     if (a > 7) errbits |= DMP_ERR_ACTION;                  // reference: an unbuilt brick (:187-208)
-
-    e.cs += 1;
-    // ---- the six cells this step can depend on: the four neighbours (check_sur :88-102) and the second and third
-    // cell in the action's direction (move_step :104-134).  Loads are unconditional at a clamped index; whether a
-    // cell is frame follows from one coordinate.
     const int dir = a & 3, dr = dir_dr(dir), dc = dir_dc(dir);
+
+    EnvT e;
+    e.pr = ax.x & 0x7F; e.pc = (ax.x >> 8) & 0xFF; e.plan_idx = ax.x >> 16;
+    bool tall = live && (ax.x & AUX3_TALL);                // a height >= TALL3 somewhere: the wide map is the exact one
+    e.cb = ax.y & 0xFFFF; e.cs = (ax.y >> 16) + 1;
+    e.ret = __uint_as_float(ax.z);
+    e.cross = (int)ax.w;
+
+    // ---- round trip 2: every map row this step can look at, one bulk copy of byte rows per env ----------------
+    const int ext = min(max(s, 1), 3);                     // a move covers at most min(s, 3) cells (move_step :104-134)
+    const int row_lo = max(e.pr - 6 - (a == 3 ? ext : 0), 0);
+    const int row_hi = min(e.pr + (a == 2 ? ext : 0), 19);
+    const int b_lo = (row_lo * 20) & ~15, b_hi = ((row_hi + 1) * 20 + 15) & ~15;      // 16 B granules, <= 224 B
+    __syncwarp();                                                                       // mbarrier init visible
+    if (live) {
+        mbar_arrive_expect_tx(bar, (uint32_t)(b_hi - b_lo));
+        bulk_g2s(slot + 16, be + b_lo, (uint32_t)(b_hi - b_lo), bar);
+    } else {
+        mbar_arrive(bar);
+    }
+    const int total_brick = __ldg(st.plan_total + e.plan_idx);
     const int o = (e.pr - 3) * 20 + (e.pc - 3);
+    const int ti = min(max(o + dr * 20 + dc, 0), CELLS3D - 1);        // build target (valid whenever a brick is laid)
+    int pplan = 0;
+    if (a >= 4) pplan = __ldg(plans + e.plan_idx * CELLS3D + ti);     // consumed after the observation
+    // virtual map base: cell (r, c) of the staged rows lives at g[r * 20 + c]; 16 B aligned like the slot
+    uint8_t* g = slot + 16 - b_lo;
+    mbar_wait(bar, 0);
+
+    // ---- the six cells the decision reads: four neighbours (check_sur :88-102), second and third cell in the
+    // action's direction (move_step).  Unconditional reads at an index clamped into the staged span; whether a cell
+    // is frame follows from one coordinate.  The decision only asks "== 0 / > 0 / frame": saturated bytes answer it.
     int c6[6];
     {
+        const int lo_cell = row_lo * 20, hi_cell = row_hi * 20 + 19;
         const int dstep = dr * 20 + dc, sgn = dr + dc;
         const int coord = (dir < 2 ? e.pc : e.pr) - 3;
-        auto at = [&](int i) { return (int)ge[min(max(i, 0), CELLS3D - 1)]; };
+        auto at = [&](int i) { return (int)g[min(max(i, lo_cell), hi_cell)]; };
         const int vl = at(o - 1), vr = at(o + 1), vu = at(o + 20), vd = at(o - 20);
         const int v2 = at(o + 2 * dstep), v3 = at(o + 3 * dstep);
         c6[0] = (e.pc > D2_LO) ? vl : -1;
@@ -93,11 +163,11 @@ __global__ void __launch_bounds__(WPB_STEP * 32) k3d_step_rows(const DmpState st
         c6[5] = ((unsigned)(coord + 3 * sgn) < 20u) ? v3 : -1;
     }
     const bool boxed = (c6[0] != 0) && (c6[1] != 0) && (c6[2] != 0) && (c6[3] != 0);     // check_sur
-    const int nsel = (dir == 0) ? c6[0] : (dir == 1) ? c6[1] : (dir == 2) ? c6[2] : c6[3];
+    int nsel = (dir == 0) ? c6[0] : (dir == 1) ? c6[1] : (dir == 2) ? c6[2] : c6[3];
 
     bool done = false, tail = true;
     bool built = false, boxed_penalty = false;
-    int newh = 0, pplan = 0, ti = 0;
+    int newh = 0;
     if (a <= 3) {
         // (a) move_step (:104-134): consecutive empty cells, at most s
         int nstep = 0;
@@ -108,11 +178,10 @@ __global__ void __launch_bounds__(WPB_STEP * 32) k3d_step_rows(const DmpState st
         // (b) build on neighbour a-4 unless it is frame
         bool open_after = (c6[0] == 0) || (c6[1] == 0) || (c6[2] == 0) || (c6[3] == 0);
         if (a <= 7 && nsel != -1) {
+            if (nsel == 255) nsel = (int)__ldcg(ge + ti);             // saturated byte (tall envs only): the true height
             built = true;
             newh = nsel + 1;
-            ti = o + dr * 20 + dc;
             e.cb += 1;
-            pplan = __ldg(plans + e.plan_idx * CELLS3D + ti);
             open_after = ((dir != 0) && c6[0] == 0) || ((dir != 1) && c6[1] == 0) ||
                          ((dir != 2) && c6[2] == 0) || ((dir != 3) && c6[3] == 0);
         }
@@ -126,41 +195,98 @@ __global__ void __launch_bounds__(WPB_STEP * 32) k3d_step_rows(const DmpState st
         }
     }
     if (tail) done = (e.cs >= st.total_step) || (!dynamic && boxed);
-
-    // ---- stage the rows under the window at the new position: interior rows [pr-6, pr] clipped to the map ----
-    const int row_lo = max(e.pr - 6, 0), row_hi = min(e.pr, 19);
-    const int b_lo = (row_lo * 40) & ~15, b_hi = ((row_hi + 1) * 40 + 15) & ~15;      // 16 B granules, <= 304 B
-    __syncwarp();                                                                       // mbarrier init visible
-    if (live) {
-        mbar_arrive_expect_tx(bar, (uint32_t)(b_hi - b_lo));
-        bulk_g2s(slot + 16, reinterpret_cast<const uint8_t*>(ge) + b_lo, (uint32_t)(b_hi - b_lo), bar);
-    } else {
-        mbar_arrive(bar);
-    }
-    // virtual map base: cell (r, c) of the staged rows lives at g[r * 20 + c]
-    uint16_t* g = reinterpret_cast<uint16_t*>(slot + 16 - b_lo);
-    mbar_wait(bar, 0);
     if (built) {
-        g[ti] = (uint16_t)newh;                          // the copy has landed: patch the staged rows ...
-        if (live) ge[ti] = (uint16_t)newh;               // ... and write the brick through to HBM
+        g[ti] = sat_u8(newh);                            // patch the staged rows ...
+        if (live) {
+            be[ti] = sat_u8(newh);                       // ... and write the brick through to the byte map
+            if (tall) {
+                ge[ti] = (uint16_t)newh;                 // a tall env keeps its wide map exact
+            } else if (newh >= TALL3) {                  // the bytes stop being exact: the env turns tall and its
+                widen_env(ge, be, ti, newh);             // wide map is made current
+                tall = true;
+            }
+        }
     }
 
-    // ---- (c) observation --------------------------------------------------------------------
-    if (io.obs) {
-        observe_tile<ObsT>(g, e, tile + lane * D3_OBS, normalise, total_brick, st.total_step);
-        __syncwarp();
-        ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + env0 * D3_OBS;
-        if (nvalid == 32) warp_tile_store_full<ObsT, 32 * D3_OBS>(dst, tile, lane);
-        else warp_tile_store<ObsT>(dst, tile, nvalid * D3_OBS, lane);
-    }
-
-    // ---- (d) reward (reward_check :232-239) -----------------------------------------------------
+    // ---- (d) reward (reward_check :232-239): the plan byte is consumed after the window has been formatted; a record
+    // row carries the reward, so it is closed after (d), observation rows leave first
     float reward = 0.f;
-    if (built) {
-        if (newh <= pplan) e.cross += 1;
-        if (!tail && !done) reward = (newh > pplan) ? -1.f : (newh == pplan ? 10.f : 1.f);
+    auto reward_now = [&]() {
+        if (built) {
+            if (newh <= pplan) e.cross += 1;
+            if (!tail && !done) reward = (newh > pplan) ? -1.f : (newh == pplan ? 10.f : 1.f);
+        }
+        if (boxed_penalty) reward = -100.f;
+    };
+
+    // ---- (c) observation: window -> registers, then the warp's [32][51] tile over the drained slots ----------
+    bool bulk_pending = false;
+    if (io.obs) {
+        // the seven window rows as 2 words of biased bytes each (height + 1, 0 = frame)
+        uint32_t u0[7], u1[7];
+        {
+            const uint32_t cv = (COLVALID >> (e.pc - 3)) & 0x7Fu;     // window column j lies inside the plan area
+            const uint64_t one = spread7(cv);                          // 0x01 per valid byte
+            const uint32_t b0 = (uint32_t)one, b1 = (uint32_t)(one >> 32);
+            const uint32_t m0 = b0 * 0xFFu, m1 = b1 * 0xFFu;           // 0xFF per valid byte (no carries)
+            const int c0 = e.pc - 6;                                    // interior column of window column 0 (may be < 0)
+            const int shb = (c0 & 3) * 8;                               // the same for every row: rows are 5 words apart
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const int ir = e.pr - 6 + k;                            // interior row of window row k
+                const bool rowvalid = (unsigned)ir < 20u;
+                const int irc = min(max(ir, row_lo), row_hi);           // rows outside the map re-read a staged row, masked
+                const uint32_t* rw = reinterpret_cast<const uint32_t*>(g + ((irc * 20 + c0) & ~3));
+                const uint32_t x0 = rw[0], x1 = rw[1], x2 = rw[2];     // over-reads stay inside the 16 B guards
+                const uint32_t q0 = __funnelshift_r(x0, x1, shb) & m0, q1 = __funnelshift_r(x1, x2, shb) & m1;
+                u0[k] = rowvalid ? (q0 + b0) : 0u;
+                u1[k] = rowvalid ? (q1 + b1) : 0u;
+            }
+        }
+        __syncwarp();                                    // every lane has read its slot
+        ObsT* row = tile + lane * ROW;
+        if constexpr (REC) {                             // one packed record per env; it carries reward and done
+            uint64_t c[7];
+            if (!tall) {
+#pragma unroll
+                for (int k = 0; k < 7; ++k) c[k] = (uint64_t)u0[k] | ((uint64_t)u1[k] << 32);
+            } else {
+                window_u16_bytes(ge, e.pr, e.pc, c);     // tall env: the wide map, this step's brick included
+            }
+            uint32_t w[13];
+            pack49(c, w);
+            reward_now();
+            rec56_store(row, w, e.cb, e.cs, reward, done, tall);
+        } else {
+            if (!tall) {
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    ObsT* o7 = row + k * 7;
+                    o7[0] = obs_from_biased<ObsT, 0>(u0[k]);
+                    o7[1] = obs_from_biased<ObsT, 1>(u0[k]);
+                    o7[2] = obs_from_biased<ObsT, 2>(u0[k]);
+                    o7[3] = obs_from_biased<ObsT, 3>(u0[k]);
+                    o7[4] = obs_from_biased<ObsT, 0>(u1[k]);
+                    o7[5] = obs_from_biased<ObsT, 1>(u1[k]);
+                    o7[6] = obs_from_biased<ObsT, 2>(u1[k]);
+                }
+            } else {
+                observe_u16<ObsT>(ge, e.pr, e.pc, row);  // tall env: the wide map, this step's brick included
+            }
+            obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, st.total_step, row[49], row[50]);
+        }
+        ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + env0 * ROW;
+        if (!(io.flags & DMP_F_TILE_LDST) && nvalid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            warp_tile_bulk_store(dst, tile, 32 * ROW * sizeof(ObsT), lane);             // one bulk async copy per warp
+            bulk_pending = true;
+        } else {
+            __syncwarp();
+            tile_rows_store<ObsT, D3_OBS>(dst, tile, nvalid, lane);
+        }
+        if constexpr (!REC) reward_now();
+    } else {
+        reward_now();
     }
-    if (boxed_penalty) reward = -100.f;
     e.ret += reward;
     if (live) {
         if (io.reward) io.reward[idx] = reward;
@@ -169,7 +295,9 @@ __global__ void __launch_bounds__(WPB_STEP * 32) k3d_step_rows(const DmpState st
 
     // ---- (e) finished episodes: IoU = cross / (total_brick + count_brick - cross) (:257-276) ---------------
     const bool fin = done && autoreset && live;
+    const bool fin_wide = fin && tall;                      // a tall env's wide map is cleared with it
     if (fin) {
+        tall = false;
         const int den = total_brick + e.cb - e.cross;
         const double iou = (e.cross == 0 && den != 0) ? 0.0 : __ddiv_rn((double)e.cross, (double)den);
         atomicAdd(st.ep_cnt + env, 1u);                 // fire-and-forget REDs
@@ -187,47 +315,63 @@ __global__ void __launch_bounds__(WPB_STEP * 32) k3d_step_rows(const DmpState st
         e.pr = e.pc = D2_LO; e.cb = e.cs = 0; e.ret = 0.f; e.cross = 0;
     }
     unsigned dm = __ballot_sync(FULL, fin);
+    const unsigned dmw = __ballot_sync(FULL, fin_wide);
     while (dm) {                                            // the warp clears each finished env's map in HBM
         const int src = __ffs(dm) - 1;
         dm &= dm - 1;
         if (lane < 25) {
-            uint4* gg = reinterpret_cast<uint4*>(gwarp + src * CELLS3D) + 2 * lane;
             const uint4 z = make_uint4(0, 0, 0, 0);
-            gg[0] = z; gg[1] = z;
+            reinterpret_cast<uint4*>(bwarp + src * CELLS3D)[lane] = z;
+            if ((dmw >> src) & 1u) {
+                uint4* gg = reinterpret_cast<uint4*>(gwarp + src * CELLS3D) + 2 * lane;
+                gg[0] = z; gg[1] = z;
+            }
         }
     }
     if (live) {
-        aux[env] = make_uint4((uint32_t)e.pr | ((uint32_t)e.pc << 8) | ((uint32_t)e.plan_idx << 16),
-                              (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16), __float_as_uint(e.ret), (uint32_t)e.cross);
+        if ((e.cb | e.cs) > 0xFFFF) {                                 // 16-bit packed counters (include/dmp.h)
+            errbits |= DMP_ERR_OVERFLOW;
+            e.cb = min(e.cb, 0xFFFF); e.cs = min(e.cs, 0xFFFF);
+        }
+        stg_keep(aux + env, make_uint4((uint32_t)e.pr | (tall ? AUX3_TALL : 0u) | ((uint32_t)e.pc << 8) | ((uint32_t)e.plan_idx << 16),
+                                       (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16), __float_as_uint(e.ret), (uint32_t)e.cross), keep);
         if (errbits) atomicOr(st.err, errbits);
         if (st.t_dev && env == 0) st.t_dev[tslot ^ 1] = t + 1;
     }
+    if (bulk_pending) warp_tile_bulk_wait(lane);                        // the tile must outlive the copy that reads it
 }
 
+// Launch shape: two-warp blocks of 240 B slots fit 14 blocks = 28 warps per SM (the driver reserves 1 KB per block, so
+// single-warp blocks stop at 27): 8 192 warps (BASELINE's 262 144 envs) are 1.98 waves.  Measured 12.2 G env-steps/s
+// against 12.0 G with single-warp blocks.  (Per-lane cp.async copies of the rows instead of the per-lane bulk copy:
+// 10.9 G, MIO-throttled -- removed.)
 template <typename ObsT>
-int launch_step(const DmpState& st, const DmpIO& io, cudaStream_t s) {
-    const size_t smem = (size_t)WPB_STEP * 32 * (SLOT_B + D3_OBS * sizeof(ObsT)) + WPB_STEP * 8 + 16;
-    static bool attr_done = false;
+int launch_bytes(const DmpState& st, const DmpIO& io, cudaStream_t s) {
+    static_assert(warp_area_bytes<ObsT>() % 16 == 0, "warp areas and the mbarriers behind them must stay 16 B aligned");
+    constexpr int wpb = 2;
+    const size_t smem = (size_t)wpb * warp_area_bytes<ObsT>() + (size_t)wpb * 8 + 16;
+    static bool attr_done = false;                           // per instantiation
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k3d_step_rows<ObsT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k3d_step_bytes<ObsT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return dmp_set_error(e);
-        e = cudaFuncSetAttribute(k3d_step_rows<ObsT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        e = cudaFuncSetAttribute(k3d_step_bytes<ObsT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return dmp_set_error(e);
         attr_done = true;
     }
     const int64_t warps = (st.n_envs + 31) / 32;
-    const unsigned blocks = (unsigned)((warps + WPB_STEP - 1) / WPB_STEP);
-    k3d_step_rows<ObsT><<<blocks, WPB_STEP * 32, smem, s>>>(st, io);
-    return dmp_set_error(cudaGetLastError());
+    const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
+    return dmp_set_error(dmp_launch_pdl(!(io.flags & DMP_F_NO_PDL), k3d_step_bytes<ObsT>, blocks, (unsigned)(wpb * 32), smem,
+                                        s, st, io));
 }
 
 }  // namespace
 
-int dmp3d_step_rows(const DmpState& st, const DmpIO& io, cudaStream_t s) {
+int dmp3d_step_bytes(const DmpState& st, const DmpIO& io, cudaStream_t s) {
     switch (io.obs_kind) {
-        case DMP_OBS_F32: return launch_step<float>(st, io, s);
-        case DMP_OBS_F64: return launch_step<double>(st, io, s);
-        case DMP_OBS_I16: return launch_step<int16_t>(st, io, s);
+        case DMP_OBS_F32: return launch_bytes<float>(st, io, s);
+        case DMP_OBS_F64: return launch_bytes<double>(st, io, s);
+        case DMP_OBS_I16: return launch_bytes<int16_t>(st, io, s);
+        case DMP_OBS_REC: return launch_bytes<Rec56>(st, io, s);
     }
     return DMP_EINVAL;
 }

@@ -1,15 +1,9 @@
 // dmp_api.cu -- the C ABI of libdmp.so (include/dmp.h): argument checks, per-dimension dispatch,
 // plan generators / dataset packing (init path) and the episode-statistics reduction.
 #include <math.h>
-#include <stdlib.h>
 #include "dmp_common.cuh"
 
 static int g_last_cuda_error = 0;
-
-bool dmp_pdl_enabled() {
-    static const bool on = !(getenv("DMP_PDL") && getenv("DMP_PDL")[0] == '0');
-    return on;
-}
 
 int dmp_set_error(cudaError_t e) {
     if (e == cudaSuccess) return DMP_OK;
@@ -227,13 +221,14 @@ int dmp_layout(int dim, int64_t n, DmpLayout* out) {
     if (!out || n < 1) return DMP_EINVAL;
     switch (dim) {
         case 1:
-            *out = DmpLayout{64 * n, 8 * n, PLAN1D_BYTES, D1_OBS, D1_ACT, 1, 34, 750, 750};
+            *out = DmpLayout{64 * n, 8 * n, PLAN1D_BYTES, D1_OBS, D1_ACT, 1, 34, 750, 750, (int32_t)sizeof(Rec16), 0};
             return DMP_OK;
         case 2:
-            *out = DmpLayout{64 * n, 0, PLAN2D_WORDS * 4, D2_OBS, D2_ACT, 26, 26, 600, 600};
+            *out = DmpLayout{64 * n, 0, PLAN2D_WORDS * 4, D2_OBS, D2_ACT, 26, 26, 600, 600, (int32_t)sizeof(Rec56), 0};
             return DMP_OK;
         case 3:
-            *out = DmpLayout{(800 + 400) * n, 16 * n, CELLS3D, D3_OBS, D3_ACT, 26, 26, 1300, 1000};   // u16 maps + byte shadow
+            *out = DmpLayout{(800 + 400) * n, 16 * n, CELLS3D, D3_OBS, D3_ACT, 26, 26, 1300, 1000,    // u16 maps + byte maps
+                             (int32_t)sizeof(Rec56), 0};
             return DMP_OK;
     }
     return DMP_EINVAL;
@@ -264,8 +259,8 @@ int dmp_reset(const DmpState* st, const uint8_t* mask, const int32_t* plan_idx, 
 
 int dmp_rollout(const DmpState* st, const DmpIO* io, int K, void* stream) {
     if (!state_ok(st) || !io || K < 1) return DMP_EINVAL;
-    if (io->obs_kind < DMP_OBS_F32 || io->obs_kind > DMP_OBS_I16) return DMP_EINVAL;
-    if ((io->flags & DMP_F_NORMALISE) && io->obs_kind == DMP_OBS_I16) return DMP_EINVAL;
+    if (io->obs_kind < DMP_OBS_F32 || io->obs_kind > DMP_OBS_REC) return DMP_EINVAL;
+    if ((io->flags & DMP_F_NORMALISE) && (io->obs_kind == DMP_OBS_I16 || io->obs_kind == DMP_OBS_REC)) return DMP_EINVAL;
     if ((io->flags & DMP_F_AUTORESET) && (!st->ep_cnt || !st->ep_len || !st->ep_ret || !st->ep_iou)) return DMP_EINVAL;
     switch (st->dim) {
         case 1: return dmp1d_rollout(*st, *io, K, as_stream(stream));

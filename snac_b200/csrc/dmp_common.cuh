@@ -133,6 +133,41 @@ __device__ __forceinline__ void obs_counters(bool normalise, int cb, int cs, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// DMP_OBS_REC: packed step records (include/dmp.h).  A record type stands in for ObsT in the kernel templates; a
+// "row" of the warp tile is then ONE record instead of D observation values.
+//   Rec56 (2D / 3D): bytes 0..48 window value + 1, 49 flags, 50-51 count_brick, 52-53 count_step, 54 reward (i8), 55 done
+//   Rec16 (1D)     : 5 x i16 raw window, u16 count_brick, u16 count_step, i8 reward, u8 done
+// ---------------------------------------------------------------------------------------------
+struct Rec56 { uint32_t w[14]; };
+struct Rec16 { uint32_t w[4]; };
+template <typename T> struct is_rec { static constexpr bool value = false; };
+template <> struct is_rec<Rec56> { static constexpr bool value = true; };
+template <> struct is_rec<Rec16> { static constexpr bool value = true; };
+// elements of ObsT per env in an observation buffer / warp tile
+template <typename ObsT, int D> __host__ __device__ constexpr int row_elems() { return is_rec<ObsT>::value ? 1 : D; }
+
+// seven window rows of seven biased bytes each (bits 0..55 of c[k]) -> the 49-byte stream in 13 words (byte 48 is the low
+// byte of w[12]).  Every shift is a compile-time constant: funnel shifts / PRMTs.
+__device__ __forceinline__ void pack49(const uint64_t (&c)[7], uint32_t (&w)[13]) {
+#pragma unroll
+    for (int j = 0; j < 13; ++j) {
+        const int k = (4 * j) / 7, o = (4 * j) % 7;        // row and byte offset of the word's first stream byte
+        uint64_t v = c[k] >> (8 * o);
+        if (7 - o < 4 && k + 1 < 7) v |= c[k + 1] << (8 * (7 - o));
+        w[j] = (uint32_t)v;
+    }
+}
+__device__ __forceinline__ void rec56_store(Rec56* row, const uint32_t (&w)[13], int cb, int cs, float reward, bool done,
+                                            bool saturated) {
+    const uint32_t flags = (done ? (uint32_t)DMP_REC_DONE : 0u) | (saturated ? (uint32_t)DMP_REC_SATURATED : 0u);
+    uint2* d = reinterpret_cast<uint2*>(row);              // records are 8 B aligned (56 = 7 x 8)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) d[j] = make_uint2(w[2 * j], w[2 * j + 1]);
+    d[6] = make_uint2((w[12] & 0xFFu) | (flags << 8) | ((uint32_t)(cb & 0xFFFF) << 16),
+                      (uint32_t)(cs & 0xFFFF) | (((uint32_t)(int)reward & 0xFFu) << 16) | (done ? 1u << 24 : 0u));
+}
+
+// ---------------------------------------------------------------------------------------------
 // warp-tile copy-out: a warp has staged `n_elems` contiguous T elements in shared memory at
 // `tile`; stream them to `dst` (global) with 128-bit stores where the alignment allows.
 // ---------------------------------------------------------------------------------------------
@@ -167,6 +202,41 @@ __device__ __forceinline__ void warp_tile_store_full(T* __restrict__ dst, const 
 #pragma unroll
     for (int i = 0; i < (N16 + 31) / 32; ++i)
         if (i * 32 + 31 < N16 || i * 32 + lane < N16) __stcs(d4 + i * 32 + lane, v[i]);
+}
+
+// the same when the caller has already established that `dst` is 16 B aligned (no fallback path in the loop)
+template <typename T, int N_ELEMS>
+__device__ __forceinline__ void warp_tile_store_aligned(T* __restrict__ dst, const T* tile, int lane) {
+    constexpr int PER16 = 16 / (int)sizeof(T);
+    static_assert(N_ELEMS % PER16 == 0, "tile must be a whole number of 16 B vectors");
+    constexpr int N16 = N_ELEMS / PER16;
+    const uint4* s4 = reinterpret_cast<const uint4*>(tile);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    uint4 v[(N16 + 31) / 32];
+#pragma unroll
+    for (int i = 0; i < (N16 + 31) / 32; ++i)
+        if (i * 32 + 31 < N16 || i * 32 + lane < N16) v[i] = s4[i * 32 + lane];
+#pragma unroll
+    for (int i = 0; i < (N16 + 31) / 32; ++i)
+        if (i * 32 + 31 < N16 || i * 32 + lane < N16) __stcs(d4 + i * 32 + lane, v[i]);
+}
+
+// tile rows (D observation values, or one record) of `nrows` envs / of a full warp through the load/store path
+template <typename ObsT, int D>
+__device__ __forceinline__ void tile_rows_store(ObsT* __restrict__ dst, const ObsT* tile, int nrows, int lane) {
+    if constexpr (is_rec<ObsT>::value)
+        warp_tile_store<uint32_t>(reinterpret_cast<uint32_t*>(dst), reinterpret_cast<const uint32_t*>(tile),
+                                  nrows * (int)(sizeof(ObsT) / 4), lane);
+    else
+        warp_tile_store<ObsT>(dst, tile, nrows * D, lane);
+}
+template <typename ObsT, int D>
+__device__ __forceinline__ void tile_rows_store_full(ObsT* __restrict__ dst, const ObsT* tile, int lane) {
+    if constexpr (is_rec<ObsT>::value)
+        warp_tile_store_full<uint32_t, 32 * (int)(sizeof(ObsT) / 4)>(reinterpret_cast<uint32_t*>(dst),
+                                                                     reinterpret_cast<const uint32_t*>(tile), lane);
+    else
+        warp_tile_store_full<ObsT, 32 * D>(dst, tile, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -221,17 +291,15 @@ __device__ __forceinline__ void stg_keep(uint4* p, const uint4& v, uint64_t pol)
 // latency after the previous grid has drained.  The hot kernels therefore (1) signal `launch_dependents` as soon as
 // they start, so the next step's grid is scheduled while this one runs, and (2) touch no global memory before
 // `griddepcontrol.wait`, which returns once the previous grid has completed and its writes are visible.  Both
-// instructions are no-ops when a kernel is launched without the attribute (DMP_PDL=0).
+// instructions are no-ops when a kernel is launched without the attribute (DmpIO.flags & DMP_F_NO_PDL).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // host-side helpers ---------------------------------------------------------------------------
-bool dmp_pdl_enabled();             // DMP_PDL environment switch (default on), dmp_api.cu
-
 template <typename... KArgs, typename... Args>
-inline cudaError_t dmp_launch_pdl(void (*kern)(KArgs...), unsigned blocks, unsigned threads, size_t smem, cudaStream_t s,
-                                  Args&&... args) {
+inline cudaError_t dmp_launch_pdl(bool pdl, void (*kern)(KArgs...), unsigned blocks, unsigned threads, size_t smem,
+                                  cudaStream_t s, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(blocks, 1, 1);
     cfg.blockDim = dim3(threads, 1, 1);
@@ -241,7 +309,7 @@ inline cudaError_t dmp_launch_pdl(void (*kern)(KArgs...), unsigned blocks, unsig
     attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &attr;
-    cfg.numAttrs = dmp_pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
@@ -255,8 +323,8 @@ int dmp_set_error(cudaError_t e);   // records e, returns DMP_OK / DMP_ECUDA
 // env-steps/s, single steps 8.3 -> 12.2 G, profiles/README.md).
 //   dmp3d_widen(st, clear_flags) : wide map := bytes for every env that is not tall; optionally drops all flags
 //   dmp3d_sync_bytes(st)         : bytes := min(wide, 255) and flag := any(wide >= TALL3), for every env
-// The cross-check kernels, the stage kernels and import only know the wide maps: widen(clear) runs before them and
-// sync_bytes after; export / iou read the wide maps after widen(keep).
+// The stage kernels and import only know the wide maps: widen(clear) runs before them and sync_bytes after;
+// export / iou read the wide maps after widen(keep).
 constexpr int TALL3 = 254;                   // bytes of a non-tall env are <= 253: the +1 bias of the observation path fits
 constexpr uint32_t AUX3_TALL = 0x80u;        // aux.x bit 7 (pos_row is 3..22)
 __host__ __device__ inline uint8_t* bmap3(const DmpState& st) {
@@ -271,11 +339,8 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 int dmp1d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);
 int dmp2d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);
 int dmp3d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);
-int dmp3d_tile_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);
-int dmp3d_cache_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);
-int dmp3d_step_rows(const DmpState& st, const DmpIO& io, cudaStream_t s);
-int dmp3d_step_span(const DmpState& st, const DmpIO& io, cudaStream_t s);
-int dmp3d_step_bytes(const DmpState& st, const DmpIO& io, cudaStream_t s);
+int dmp3d_cache_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s);      // dmp_3d_roll.cu
+int dmp3d_step_bytes(const DmpState& st, const DmpIO& io, cudaStream_t s);                // dmp_3d_step.cu
 int dmp1d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs, int obs_kind, cudaStream_t s);
 int dmp2d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs, int obs_kind, cudaStream_t s);
 int dmp3d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx, uint64_t t_draw, void* obs, int obs_kind, cudaStream_t s);

@@ -69,10 +69,26 @@ class EpsilonGreedy:
         return torch.where(explore, rnd, greedy).to(torch.uint8)
 
 
+def reset_observation(dim: int, dtype: torch.dtype, device) -> torch.Tensor:
+    """The observation every reset() returns (raw or normalised counters: both are 0): the window at the start position
+    over an empty grid -- 1D [-1, -1, 0, 0, 0 | 0, 0] (Env/1D/DMP_Env_1D_static.py:81-83), 2D/3D rows and columns 0..2 of
+    the 7x7 window on the -1 frame (Env/2D/DMP_Env_2D_static.py:60-76)."""
+    if dim == 1:
+        o = torch.tensor([-1, -1, 0, 0, 0, 0, 0])
+    else:
+        w = torch.zeros((7, 7), dtype=torch.int64)
+        w[:3, :] = -1
+        w[:, :3] = -1
+        o = torch.cat([w.reshape(-1), torch.zeros(2, dtype=torch.int64)])
+    return o.to(device=device, dtype=dtype)
+
+
 class DeviceRollout:
     """T steps of ``obs -> policy -> dmp_step`` for every env, captured in one CUDA graph.
 
-    env        a BatchedDMPEnv that has been reset (auto_reset=True keeps finished envs going)
+    env        a BatchedDMPEnv that has been reset (auto_reset=True keeps finished envs going: ``next_obs[t]`` then holds
+               the terminal observation of an episode that ended in step t and ``obs[t + 1]`` the reset observation the
+               next episode starts from)
     policy     callable obs [N, D] -> uint8 actions [N] (see above); None = the kernels' own Philox actions
     horizon    steps per collect() (rounded up to an even number: the device step counter alternates two slots)
     graph      False runs the same loop eagerly (debugging / policies that cannot be captured)
@@ -83,8 +99,15 @@ class DeviceRollout:
             raise RuntimeError("reset() the env before building a DeviceRollout")
         self.env, self.policy = env, policy
         self.T = int(horizon) + (int(horizon) & 1)
+        if env.records:
+            raise ValueError("DeviceRollout feeds observations to a torch policy: build the env with a numeric obs_dtype")
         n, D, dev = env.num_envs, env.obs_dim, env.device
         self.obs = torch.zeros((self.T + 1, n, D), dtype=env.obs_dtype, device=dev)      # obs[t] is the input of step t
+        # what step t returned.  With auto_reset the kernel returns the TERMINAL observation of a finished episode and
+        # resets the env in the same launch; the next policy input of that env is then the reset observation, like
+        # ``state = env.reset()`` in the reference's loops (script/DQN/2d/DQN_2d_static.py:186-206)
+        self.next_obs = torch.zeros((self.T, n, D), dtype=env.obs_dtype, device=dev) if env.auto_reset else self.obs[1:]
+        self.reset_obs = reset_observation(env.dim, env.obs_dtype, dev)                  # constant [D] row
         self._cur = torch.zeros((n, D), dtype=env.obs_dtype, device=dev)                 # observation carried between collects
         self.actions = torch.zeros((self.T, n), dtype=torch.uint8, device=dev)
         self.reward = torch.zeros((self.T, n), dtype=torch.float32, device=dev)
@@ -107,8 +130,10 @@ class DeviceRollout:
             if self.policy is not None:
                 self.actions[t].copy_(self.policy(self.obs[t]))
                 a = self.actions[t:t + 1]
-            env.rollout(1, actions=a, out=(self.obs[t + 1:t + 2], self.reward[t:t + 1], self.done[t:t + 1]),
+            env.rollout(1, actions=a, out=(self.next_obs[t:t + 1], self.reward[t:t + 1], self.done[t:t + 1]),
                         use_device_t=True, t_slot=t & 1)
+            if env.auto_reset:                               # envs reset in this launch continue from the reset observation
+                torch.where(self.done[t].view(torch.bool)[:, None], self.reset_obs, self.next_obs[t], out=self.obs[t + 1])
         self._cur.copy_(self.obs[self.T])                    # next collect() continues from the last observation
 
     def collect(self) -> dict:
@@ -141,5 +166,5 @@ class DeviceRollout:
                 self._body()
         cur.wait_stream(self._stream)
         env._st.t = env._st.t + self.T
-        return dict(obs=self.obs[:self.T], next_obs=self.obs[1:], actions=self.actions, reward=self.reward,
+        return dict(obs=self.obs[:self.T], next_obs=self.next_obs, actions=self.actions, reward=self.reward,
                     done=self.done.view(torch.bool))

@@ -17,7 +17,35 @@ import torch
 
 from . import _lib as L
 
-_TORCH_OBS = {torch.float32: L.OBS_F32, torch.float64: L.OBS_F64, torch.int16: L.OBS_I16}
+_TORCH_OBS = {torch.float32: L.OBS_F32, torch.float64: L.OBS_F64, torch.int16: L.OBS_I16, torch.uint8: L.OBS_REC}
+RECORD = "record"      # obs_dtype=RECORD: packed step records (DMP_OBS_REC, include/dmp.h), uint8 [..., rec_bytes]
+
+
+def record_dtype(dim: int) -> np.dtype:
+    """numpy structured dtype of one DMP_OBS_REC step record (include/dmp.h): view a uint8 [..., rec_bytes] buffer with it.
+    2D / 3D (56 B): ``win`` u8[49] = window value + 1 (0 is the -1 frame), ``flags``, ``count_brick``, ``count_step``,
+    ``reward`` (i8), ``done`` (bool).  1D (16 B): ``win`` i16[5] raw heights, ``count_brick``, ``count_step``, ``reward``,
+    ``done``."""
+    if dim == 1:
+        return np.dtype({"names": ["win", "count_brick", "count_step", "reward", "done"],
+                         "formats": [("<i2", (5,)), "<u2", "<u2", "i1", "?"], "offsets": [0, 10, 12, 14, 15], "itemsize": 16})
+    return np.dtype({"names": ["win", "flags", "count_brick", "count_step", "reward", "done"],
+                     "formats": [("u1", (49,)), "u1", "<u2", "<u2", "i1", "?"], "offsets": [0, 49, 50, 52, 54, 55],
+                     "itemsize": 56})
+
+
+def unpack_records(rec, dim: int, dtype=np.float64):
+    """Step records -> (obs [..., D], reward float32 [...], done bool [...], saturated bool [...]) numpy arrays in the
+    layout of the other observation kinds (raw counters).  ``rec``: uint8 array [..., rec_bytes] (numpy or torch) or an
+    array of record_dtype(dim)."""
+    if torch.is_tensor(rec):
+        rec = rec.cpu().numpy()
+    r = rec if rec.dtype.names else np.ascontiguousarray(rec).view(record_dtype(dim))[..., 0]
+    win = r["win"].astype(dtype) - (0 if dim == 1 else 1)
+    obs = np.concatenate([win, r["count_brick"][..., None].astype(dtype), r["count_step"][..., None].astype(dtype)], axis=-1)
+    sat = np.zeros(r.shape, bool) if dim == 1 else (r["flags"] & L.REC_SATURATED) != 0
+    return obs, r["reward"].astype(np.float32), r["done"].copy(), sat
+
 
 # reference constants exposed as attributes (Env/*/…__init__)
 _SPEC = {
@@ -110,9 +138,14 @@ class BatchedDMPEnv:
     n_plans           size of the generated plan table (plans="generate" only; at most 65 535)
     random_choose_paln  (sic, reference spelling) True: random plan per reset; False: sequential with wrap
     auto_reset        fold finished episodes into the per-env statistics and reset them inside step()
-    obs_dtype         torch.float32 (default), torch.float64 (the reference's dtype) or torch.int16
+    obs_dtype         torch.float32 (default), torch.float64 (the reference's dtype), torch.int16, or "record": packed step
+                      records (window + counters + reward + done in one uint8 [N, rec_bytes] buffer: the compact
+                      host-facing kind, see record_dtype() / unpack_records())
     normalise         emit the dynamic classes' normalised counter columns (default: False = raw counters)
     env_base          global index of env 0 (multi-GPU sharding; keeps Philox streams shard-independent)
+    tuning            names of kernel tuning switches (snac_b200._lib.TUNING_FLAGS: "no_pdl", "tile_ldst", "generic",
+                      "rollout_k1", "no_l2_hint"), decided once here and passed to the library as DmpIO.flags bits;
+                      default: the SNAC_B200_TUNING environment variable (comma separated), read at construction
     dynamic_rules     3D only: use the dataset classes' termination rules (re-check after placement, -100 when
                       boxed in) independently of where the plan comes from -- the static *_Lnet class does that
                       (Env/3D/DMP_simulator_3d_static_circle_Lnet.py:210-236).  Default: same as `dynamic`.
@@ -124,20 +157,34 @@ class BatchedDMPEnv:
                  obs_dtype: torch.dtype = torch.float32, normalise: bool = False,
                  seed: int = L.SEED_DEFAULT, env_base: int = 0, action_dist: str = "uniform",
                  total_step: Optional[int] = None, dynamic_rules: Optional[bool] = None, n_plans: int = 4096,
-                 plan_id_base: int = 0):
+                 plan_id_base: int = 0, tuning: Optional[Sequence[str]] = None):
         if dim not in (1, 2, 3):
             raise ValueError("dim must be 1, 2 or 3")
-        if obs_dtype not in _TORCH_OBS:
-            raise ValueError("obs_dtype must be float32, float64 or int16")
-        if normalise and obs_dtype == torch.int16:
+        self.records = isinstance(obs_dtype, str) and obs_dtype == RECORD
+        if self.records:
+            obs_dtype = torch.uint8
+        elif obs_dtype not in (torch.float32, torch.float64, torch.int16):
+            raise ValueError('obs_dtype must be float32, float64, int16 or "record"')
+        if normalise and obs_dtype in (torch.int16, torch.uint8):
             raise ValueError("normalised counters need a floating obs_dtype")
+        if tuning is None:
+            tuning = [x for x in os.environ.get("SNAC_B200_TUNING", "").split(",") if x]
+        if os.environ.get("SNAC_B200_L2_HINTS", "1") == "0":
+            tuning = list(tuning) + ["no_l2_hint"]
+        unknown = [x for x in tuning if x not in L.TUNING_FLAGS]
+        if unknown:
+            raise ValueError("unknown tuning switches %s (known: %s)" % (unknown, sorted(L.TUNING_FLAGS)))
+        self.tuning = tuple(tuning)
+        self._tuning_flags = 0
+        for x in self.tuning:
+            self._tuning_flags |= L.TUNING_FLAGS[x]
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("snac_b200 has no CPU path; device must be a CUDA device")
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.dim, self.dynamic = dim, bool(dynamic)
-        self.l2_hints = os.environ.get("SNAC_B200_L2_HINTS", "1") != "0"
+        self.l2_hints = not (self._tuning_flags & L.F_NO_L2_HINT)
         self.num_envs = int(num_envs)
         self.auto_reset = bool(auto_reset)
         self.obs_dtype, self.normalise = obs_dtype, bool(normalise)
@@ -199,7 +246,7 @@ class BatchedDMPEnv:
                 L.check(rc, "dmp_plan_static")
                 self._plans_raw = None
             # ---- output buffers (reused by step(); rollout() allocates [K,...] on demand) -----
-            D = lay.obs_dim
+            D = lay.rec_bytes if self.records else lay.obs_dim
             self._obs = torch.zeros((n, D), dtype=obs_dtype, device=dev)
             self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
             self._done = torch.zeros(n, dtype=torch.uint8, device=dev)
@@ -223,6 +270,8 @@ class BatchedDMPEnv:
         self._st = st
         self.random_choose_paln = bool(random_choose_paln)
         self._needs_initial_reset = True
+        import torch.cuda.nvtx as _nvtx
+        self._nvtx = _nvtx
 
     # ------------------------------------------------------------------------------------------
     def _stream(self) -> int:
@@ -231,6 +280,11 @@ class BatchedDMPEnv:
     @property
     def obs_dim(self) -> int:
         return self._lay.obs_dim
+
+    @property
+    def obs_row(self) -> int:
+        """Elements of obs_dtype per env in an observation buffer: obs_dim, or the record size in bytes."""
+        return self._lay.rec_bytes if self.records else self._lay.obs_dim
 
     @property
     def t(self) -> int:
@@ -243,7 +297,7 @@ class BatchedDMPEnv:
         # fractional evict_last / evict_first policies that keep a half or a quarter of the lines were slower still).
         hint = self.l2_hints and (K > 1 or self._cells.numel() <= 40 * 1024 * 1024)
         return ((L.F_AUTORESET if self.auto_reset else 0) | (L.F_NORMALISE if self.normalise else 0)
-                | (0 if hint else L.F_NO_L2_HINT))
+                | (self._tuning_flags & ~L.F_NO_L2_HINT) | (0 if hint else L.F_NO_L2_HINT))
 
     def _u8(self, x, shape, what) -> torch.Tensor:
         if not torch.is_tensor(x):
@@ -270,16 +324,16 @@ class BatchedDMPEnv:
         (rows of envs that were not reset keep their previous content).
         Dynamic envs: ``plan_idx`` (int32 [N]) injects the reference's ``index_random`` draw
         (Env/2D/DMP_Env_2D_dynamic_usedata_plan.py:36); default is a Philox draw, or -- with
-        random_choose_paln=False -- plan 0 on the first reset and +1 (wrapping) afterwards."""
+        random_choose_paln=False -- plan 0 on an env's first reset and +1 (wrapping) afterwards (in the kernel)."""
         n = self.num_envs
         m = None if mask is None else self._u8(mask, (n,), "mask")
         p = None if plan_idx is None else self._i32(plan_idx, (n,), "plan_idx")
-        if p is None and self._needs_initial_reset and self.dynamic and not self.random_choose_paln:
-            p = torch.zeros(n, dtype=torch.int32, device=self.device)      # index_for_non_random = 0
         obs = self._obs if out is None else out
+        self._nvtx.range_push("dmp_reset")
         with torch.cuda.device(self.device):
             L.check(L.lib.dmp_reset(C.byref(self._st), _ptr(m), _ptr(p), C.c_uint64(L.T_INIT - self._st.t),
                                     obs.data_ptr(), _TORCH_OBS[obs.dtype], self._stream()), "dmp_reset")
+        self._nvtx.range_pop()
         if mask is None:
             self._needs_initial_reset = False
         self._keep = (m, p)
@@ -295,8 +349,8 @@ class BatchedDMPEnv:
         """One step of every env.  ``actions`` uint8 [N] (None: Philox synthetic actions).
         ``step_sizes`` uint8 [N] in {1,2,3} injects the reference's ``np.random.randint(1, 4)``
         draw (the *_hindsight_replay ``step(action, step_size)`` form); None = Philox.
-        Returns (obs [N,D], reward f32 [N], done bool [N]) -- views of internal buffers that the
-        next call overwrites."""
+        Returns (obs [N,D] (records: uint8 [N, rec_bytes]), reward f32 [N], done bool [N]) -- views of internal
+        buffers that the next call overwrites."""
         obs, rew, done = self.rollout(1, actions=None if actions is None else self._u8(actions, (self.num_envs,), "actions")[None],
                                       step_sizes=None if step_sizes is None else self._u8(step_sizes, (self.num_envs,), "step_sizes")[None],
                                       next_plan=None if next_plan is None else self._i32(next_plan, (self.num_envs,), "next_plan")[None],
@@ -307,7 +361,7 @@ class BatchedDMPEnv:
                 materialise_obs: bool = True, use_device_t: bool = False, t_slot: int = 0):
         """Advance every env K steps in ONE kernel launch (state stays on chip between steps).
         actions / step_sizes: uint8 [K,N] or None (Philox).  Returns (obs [K,N,D], reward [K,N], done [K,N])."""
-        n, D = self.num_envs, self._lay.obs_dim
+        n, D = self.num_envs, self.obs_row
         if self._needs_initial_reset:
             raise RuntimeError("call reset() before step()/rollout()")
         a = None if actions is None else self._u8(actions, (K, n), "actions")
@@ -325,8 +379,10 @@ class BatchedDMPEnv:
         io.obs_kind = _TORCH_OBS[self.obs_dtype if obs is None else obs.dtype]
         io.flags = self._flags(K) | (L.F_TSLOT1 if (use_device_t and t_slot) else 0)
         self._st.t_dev = self._t_dev.data_ptr() if use_device_t else None
+        self._nvtx.range_push("dmp_step" if K == 1 else "dmp_rollout")
         with torch.cuda.device(self.device):
             L.check(L.lib.dmp_rollout(C.byref(self._st), C.byref(io), int(K), self._stream()), "dmp_rollout")
+        self._nvtx.range_pop()
         if not use_device_t:
             self._st.t = self._st.t + K
         self._keep_io = (a, s, p)
@@ -402,6 +458,9 @@ class BatchedDMPEnv:
         if e & L.ERR_ACTION:
             raise UnboundLocalError("an action outside the env's action set was stepped "
                                     "(the reference leaves 'position' unbound, Env/1D/DMP_Env_1D_static.py:130-133)")
+        if e & L.ERR_OVERFLOW:
+            raise OverflowError("count_step or count_brick of an env passed 65 535 (envs stepped on after done without a "
+                                "reset): the packed counters hold 16 bits and have saturated")
         if e:
             raise ValueError("libdmp latched error bits 0x%x" % e)
 

@@ -50,7 +50,7 @@ def test_struct_sizes_match_header():
     from snac_b200 import _lib as L
     assert ctypes.sizeof(L.DmpIO) == 6 * 8 + 8
     assert ctypes.sizeof(L.DmpState) == 6 * 4 + 5 * 8 + 9 * 8
-    assert ctypes.sizeof(L.DmpLayout) == 3 * 8 + 6 * 4
+    assert ctypes.sizeof(L.DmpLayout) == 3 * 8 + 8 * 4
 
 
 def test_product_package_never_imports_oracle():

@@ -2,8 +2,6 @@
 Bit-exact: grids, positions, counters, observations, done flags, rewards (small integers in f32).
 IoU / normalised counters: IEEE fp64 division on both sides -> compared exactly, with a 1e-6
 relative fallback stated in BASELINE.json's north_star."""
-import os
-
 import numpy as np
 import pytest
 import torch
@@ -290,55 +288,52 @@ def test_get_set_state_and_functional_transition():
 
 
 # ------------------------------------------------------------------------------------------------
-# 7. the three 3D kernels (warp per env / u16 tile / byte cache) are interchangeable, and the byte-cache
-#    kernel's "tall env" path (a height >= 254 somewhere: the env runs from HBM) is exact
+# 7. the two 3D kernels (rollout: whole byte maps cached in shared memory; single step: only the rows a step can look at)
+#    and their tuning variants are interchangeable and equal the oracle; the "tall env" path (a height >= 254 somewhere:
+#    the env runs from its wide map in HBM) is exact
 # ------------------------------------------------------------------------------------------------
-def _with_kernel(kind, fn):
-    old = os.environ.get("DMP_3D_KERNEL")
-    os.environ["DMP_3D_KERNEL"] = kind
-    try:
-        return fn()
-    finally:
-        if old is None:
-            del os.environ["DMP_3D_KERNEL"]
-        else:
-            os.environ["DMP_3D_KERNEL"] = old
-
-
 @pytest.mark.parametrize("dynamic", [False, True])
 @pytest.mark.parametrize("K", [1, 37])
 def test_3d_kernels_agree(dynamic, K):
     plans = load_plans(3, "dense", "train") if dynamic else None
     n = 333                                                   # ragged last warp
     outs = {}
-    # "d": the default dispatch (byte cache for K > 1, byte-row kernel for K = 1); "s" / "r": second- / first-generation
-    # single-step kernels over the wide (u16) maps.
-    for kind in "wtcdsr":
+    # "d": the default dispatch (rollout kernel for K > 1, single-step kernel for K = 1); "c": the rollout kernel for
+    # every K; "l": load/store copy-out of the observation tile instead of the bulk async copy; "p": no programmatic
+    # dependent launch
+    variants = {"d": (), "c": ("rollout_k1",), "l": ("tile_ldst",), "p": ("no_pdl",), "cl": ("rollout_k1", "tile_ldst")}
+    reps = 120 // K + 1
+    for kind, tuning in variants.items():
         env = make_gpu(3, dynamic, n, 0, plans, auto_reset=True, env_base=99, seed=SEED, normalise=dynamic,
-                       obs_dtype=torch.float64 if dynamic else torch.float32)
+                       obs_dtype=torch.float64 if dynamic else torch.float32, tuning=tuning)
         env.reset()
-
-        def run():
-            res = [[x.clone() for x in env.rollout(K)] for _ in range(120 // K + 1)]
-            torch.cuda.synchronize()
-            return res
-        res = _with_kernel(kind, run)
+        res = [[x.clone() for x in env.rollout(K)] for _ in range(reps)]
+        torch.cuda.synchronize()
         st = env.get_state()
         # heights as exported, the byte maps behind the wide maps (the wide map of an env that is not tall is scratch),
         # scalar state incl. the tall flags
         outs[kind] = (res, torch.cat([env.export_state()["grid"].reshape(-1), st["cells"][n * 800:].to(torch.int32)]),
                       st["aux"].clone(), [x.clone() for x in env.episode_stats()])
         env.check_errors()
-    for kind in "tcdsr":
-        for a, b in zip(outs["w"][0], outs[kind][0]):
+    for kind in variants:
+        if kind == "d":
+            continue
+        for a, b in zip(outs["d"][0], outs[kind][0]):
             for x, y in zip(a, b):
                 assert torch.equal(x, y), kind
-        assert torch.equal(outs["w"][1], outs[kind][1]) and torch.equal(outs["w"][2], outs[kind][2]), kind
-        for x, y in zip(outs["w"][3], outs[kind][3]):
+        assert torch.equal(outs["d"][1], outs[kind][1]) and torch.equal(outs["d"][2], outs[kind][2]), kind
+        for x, y in zip(outs["d"][3], outs[kind][3]):
             assert torch.equal(x, y), kind
+    ob = OracleBatch(3, dynamic, n, 0, plans)
+    ob.reset(philox.reset_draw(SEED, np.arange(99, 99 + n), 0, ob.n_plans) if dynamic else None)
+    r_obs, r_rew, r_done, _, _ = philox_rollout(ob, reps * K, SEED, 99, 0, 8, normalise=dynamic)
+    obs = torch.cat([r[0] for r in outs["d"][0]]).cpu().numpy().astype(np.float64)
+    assert np.array_equal(obs, r_obs)
+    assert np.array_equal(torch.cat([r[1] for r in outs["d"][0]]).cpu().numpy(), r_rew)
+    assert np.array_equal(torch.cat([r[2] for r in outs["d"][0]]).cpu().numpy(), r_done)
 
 
-@pytest.mark.parametrize("kind", ["c", "t", "d1", "s1", "r1"])
+@pytest.mark.parametrize("kind", ["c", "d1", "c1", "cr", "d1r"])
 @pytest.mark.parametrize("dynamic", [False, True])
 def test_3d_tall_columns_match_oracle(kind, dynamic):
     """Heights around the byte paths' thresholds and far beyond the byte range (126..129, 252..256, 300, 40000) next to
@@ -346,7 +341,11 @@ def test_3d_tall_columns_match_oracle(kind, dynamic):
     plans = load_plans(3, "dense", "train") if dynamic else None
     n, K = 70, 48
     rng = np.random.RandomState(11)
-    env = make_gpu(3, dynamic, n, 0, plans, auto_reset=False, seed=SEED, obs_dtype=torch.float32)
+    # "c": one rollout launch; "d1": step by step through the single-step kernel; "c1": step by step through the rollout
+    # kernel; a trailing "r": packed step records (window bytes saturate at 255 and the record says so)
+    records = kind.endswith("r")
+    env = make_gpu(3, dynamic, n, 0, plans, auto_reset=False, seed=SEED, obs_dtype="record" if records else torch.float32,
+                   tuning=("rollout_k1",) if kind.startswith("c1") else ())
     ob = OracleBatch(3, dynamic, n, 0, plans)
     p0 = rng.randint(ob.n_plans, size=n).astype(np.int32) if dynamic else None
     env.reset(plan_idx=p0)
@@ -367,17 +366,22 @@ def test_3d_tall_columns_match_oracle(kind, dynamic):
     sizes = rng.randint(1, 4, size=(K, n)).astype(np.uint8)
     r_obs, r_rew, r_done, _, _ = philox_rollout(ob, K, SEED, 0, 0, 8, auto_reset=False, actions=acts, step_sizes=sizes)
 
-    def run():
-        ta, ts = torch.as_tensor(acts, device=env.device), torch.as_tensor(sizes, device=env.device)
-        if kind in ("d1", "s1", "r1"):                        # step by step through a single-step kernel
-            outs = [[x.clone() for x in env.step(ta[k], ts[k])] for k in range(K)]
-            out = [torch.stack([o[i] for o in outs]) for i in range(3)]
-        else:
-            out = env.rollout(K, actions=ta, step_sizes=ts)
-        torch.cuda.synchronize()
-        return out
-    obs, rew, done = _with_kernel(kind[0], run)
-    assert np.array_equal(obs.cpu().numpy().astype(np.float64), r_obs)
+    ta, ts = torch.as_tensor(acts, device=env.device), torch.as_tensor(sizes, device=env.device)
+    if kind[:2] in ("d1", "c1"):                              # step by step
+        outs = [[x.clone() for x in env.step(ta[k], ts[k])] for k in range(K)]
+        obs, rew, done = [torch.stack([o[i] for o in outs]) for i in range(3)]
+    else:
+        obs, rew, done = env.rollout(K, actions=ta, step_sizes=ts)
+    torch.cuda.synchronize()
+    if records:
+        from snac_b200.vecenv import unpack_records
+        o, r, d, sat = unpack_records(obs, 3)
+        # exact wherever the window holds nothing above 253; saturated bytes read 254 and the record is flagged
+        assert np.array_equal(o[..., :49], np.minimum(r_obs[..., :49], 254)) and np.array_equal(o[..., 49:], r_obs[..., 49:])
+        assert (sat | (r_obs[..., :49].max(axis=-1) < 254)).all() and sat.any()
+        assert np.array_equal(r, r_rew) and np.array_equal(d, r_done)
+    else:
+        assert np.array_equal(obs.cpu().numpy().astype(np.float64), r_obs)
     assert np.array_equal(rew.cpu().numpy(), r_rew)
     assert np.array_equal(done.cpu().numpy(), r_done)
     g_ref, sc_ref = ob.export()
@@ -398,7 +402,7 @@ def test_3d_tall_columns_match_oracle(kind, dynamic):
 
 # ------------------------------------------------------------------------------------------------
 # 8. 2D single steps leave through a bulk (TMA) copy of the warp tile: equal to the oracle, to the load/store copy-out
-#    (DMP_TILE_COPY=l) and independent of the alignment of the caller's observation buffer
+#    (tuning switch "tile_ldst") and independent of the alignment of the caller's observation buffer
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dynamic", [False, True])
 def test_2d_bulk_copy_out_step_mode(dynamic):
@@ -408,7 +412,7 @@ def test_2d_bulk_copy_out_step_mode(dynamic):
     envs = {}
     for kind in ("float", "unaligned", "tma"):
         envs[kind] = make_gpu(2, dynamic, n, 0, plans, auto_reset=True, env_base=3, seed=SEED, obs_dtype=torch.float32,
-                              total_step=35)
+                              total_step=35, tuning=("tile_ldst",) if kind == "float" else ())
     for e in ob.envs:
         e.total_step = 35
     p0 = philox.reset_draw(SEED, np.arange(3, 3 + n), 0, ob.n_plans) if dynamic else None
@@ -419,18 +423,8 @@ def test_2d_bulk_copy_out_step_mode(dynamic):
     raw = torch.zeros(n * 51 + 1, dtype=torch.float32, device="cuda")
     odd = raw[1:].view(1, n, 51)                              # 4 B aligned only
     for k in range(K):
-        def with_tile(mode, fn):
-            old = os.environ.get("DMP_TILE_COPY")
-            os.environ["DMP_TILE_COPY"] = mode
-            try:
-                return fn()
-            finally:
-                if old is None:
-                    del os.environ["DMP_TILE_COPY"]
-                else:
-                    os.environ["DMP_TILE_COPY"] = old
-        o1, r1, d1 = with_tile("b", lambda: envs["tma"].step(None))
-        o2, r2, d2 = with_tile("l", lambda: envs["float"].step(None))
+        o1, r1, d1 = envs["tma"].step(None)
+        o2, r2, d2 = envs["float"].step(None)
         e3 = envs["unaligned"]
         o3, r3, d3 = e3.rollout(1, out=(odd, e3._reward[None], e3._done[None]))           # default mode, 4 B aligned buffer
         assert np.array_equal(o1.cpu().numpy().astype(np.float64), r_obs[k]), k
@@ -443,8 +437,8 @@ def test_2d_bulk_copy_out_step_mode(dynamic):
 
 
 # ------------------------------------------------------------------------------------------------
-# 9. 1D rollouts: ragged last warp, both block shapes (32 / 128 envs per block), every observation dtype, load/store and
-#    bulk (TMA) copy-out of the observation tile -- equal to the oracle and independent of how a rollout is cut into launches
+# 9. 1D rollouts: ragged last warp, both block shapes (32 / 128 envs per block), every observation dtype -- equal to the
+#    oracle and independent of how a rollout is cut into launches
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dynamic,n", [(False, 32 * 37 + 20), (True, 128 * 148 * 4 + 64)])
 def test_1d_rollout_shapes_and_cuts(dynamic, n):
@@ -459,24 +453,12 @@ def test_1d_rollout_shapes_and_cuts(dynamic, n):
         ref = philox_rollout(ob, K, SEED, 5, 0, 3)
     outs = {}
     for dt in (torch.float32, torch.int16, torch.float64):
-        # "b": one launch; "t": one launch with the bulk (TMA) copy-out of the tile (DMP_TILE_COPY=b, off by default);
-        # "l": the same steps cut into launches of 1, 3, 7, ...
-        for mode in ("b", "t", "l"):
+        # "b": one launch; "l": the same steps cut into launches of 1, 3, 7, ...
+        for mode in ("b", "l"):
             env = make_gpu(1, dynamic, n, 2, plans, auto_reset=True, env_base=5, seed=SEED, obs_dtype=dt, total_step=30)
             env.reset()
             if mode == "b":
                 o, r, d = env.rollout(K)
-            elif mode == "t":
-                old = os.environ.get("DMP_TILE_COPY")
-                os.environ["DMP_TILE_COPY"] = "b"
-                try:
-                    o, r, d = env.rollout(K)
-                    torch.cuda.synchronize()
-                finally:
-                    if old is None:
-                        del os.environ["DMP_TILE_COPY"]
-                    else:
-                        os.environ["DMP_TILE_COPY"] = old
             else:
                 parts, left, c = [], K, 1
                 while left:
@@ -490,7 +472,7 @@ def test_1d_rollout_shapes_and_cuts(dynamic, n):
             env.check_errors()
             outs[(dt, mode)] = (o, r, d, o2, r2, d2, env.export_state())
         a = outs[(dt, "b")]
-        for other in ("t", "l"):
+        for other in ("l",):
             b = outs[(dt, other)]
             for x, y in zip(a[:6], b[:6]):
                 assert torch.equal(x, y), (dt, other)
@@ -498,3 +480,40 @@ def test_1d_rollout_shapes_and_cuts(dynamic, n):
         if ref is not None:
             assert np.array_equal(a[0].cpu().numpy().astype(np.float64), ref[0]), dt
             assert np.array_equal(a[1].cpu().numpy(), ref[1]) and np.array_equal(a[2].cpu().numpy(), ref[2])
+
+
+# ------------------------------------------------------------------------------------------------
+# 10. the 1D kernel's FAST instantiation (launch-uniform branches folded: Philox draws, everything materialised,
+#     auto-reset, raw counters, full blocks) against the generic one (tuning switch "generic") and the oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dynamic,n", [(False, 32 * 64), (True, 32 * 33), (False, 128 * 600), (True, 128 * 592)])
+def test_1d_fast_path_equals_generic(dynamic, n):
+    plans = load_plans(1, "dense", "train") if dynamic else None
+    K = 75
+    outs = {}
+    for dt in (torch.float32, torch.int16, torch.float64, "record"):
+        for fast in ("1", "0"):
+            env = make_gpu(1, dynamic, n, 1, plans, auto_reset=True, env_base=9, seed=SEED, obs_dtype=dt, total_step=40,
+                           tuning=() if fast == "1" else ("generic",))
+            env.reset()
+            o, r, d = env.rollout(K)
+            o2, r2, d2 = env.rollout(2)
+            torch.cuda.synchronize()
+            env.check_errors()
+            outs[(dt, fast)] = (o, r, d, o2, r2, d2, env.export_state(), [x.clone() for x in env.episode_stats()])
+        a, b = outs[(dt, "1")], outs[(dt, "0")]
+        for x, y in zip(a[:6], b[:6]):
+            assert torch.equal(x, y), dt
+        assert torch.equal(a[6]["grid"], b[6]["grid"]) and torch.equal(a[6]["scalars"], b[6]["scalars"])
+        for x, y in zip(a[7], b[7]):
+            assert torch.equal(x, y)
+        assert int(a[7][0].sum()) > 0                         # episodes did finish (auto-reset path exercised)
+    if n < 4000:
+        ob = OracleBatch(1, dynamic, n, 1, plans)
+        for e in ob.envs:
+            e.total_step = 40
+        ob.reset(philox.reset_draw(SEED, np.arange(9, 9 + n), 0, ob.n_plans) if dynamic else None)
+        ref = philox_rollout(ob, K, SEED, 9, 0, 3)
+        a = outs[(torch.float32, "1")]
+        assert np.array_equal(a[0].cpu().numpy().astype(np.float64), ref[0])
+        assert np.array_equal(a[1].cpu().numpy(), ref[1]) and np.array_equal(a[2].cpu().numpy(), ref[2])

@@ -31,8 +31,11 @@ def test_loop_matches_oracle(dim, graph):
     o = env.reset()
     cur = ob.reset()
     assert np.array_equal(o.cpu().numpy().astype(np.float64), cur)
+    reset_row = cur[0].copy()                                 # reset() returns the same row for every env
+    assert (cur == reset_row).all()
     loop = DeviceRollout(env, int_policy(A), horizon=T, graph=graph)
-    t = 0
+    assert np.array_equal(loop.reset_obs.cpu().numpy().astype(np.float64), reset_row)
+    t, n_done = 0, 0
     for rep in range(3):                                     # replays continue where the previous one stopped
         traj = loop.collect()
         torch.cuda.synchronize()
@@ -42,14 +45,16 @@ def test_loop_matches_oracle(dim, graph):
             assert np.array_equal(traj["obs"][k].cpu().numpy().astype(np.float64), cur), (rep, k)
             assert np.array_equal(traj["actions"][k].cpu().numpy(), a), (rep, k)
             nxt, r, d = ob.step(a, s)
-            # on done the oracle batch resets the env: the NEXT policy input is the terminal observation the step
-            # returned (the kernel does the same: auto-reset returns the terminal observation)
+            # next_obs is the terminal observation the step returned; on done the oracle batch has reset the env, and the
+            # NEXT policy input of that env is the reset observation -- ``state = env.reset()`` in the reference's loops
             assert np.array_equal(traj["next_obs"][k].cpu().numpy().astype(np.float64), nxt), (rep, k)
             assert np.array_equal(traj["reward"][k].cpu().numpy(), r)
             assert np.array_equal(traj["done"][k].cpu().numpy(), d)
-            cur = nxt
+            cur = np.where(d[:, None], reset_row[None, :], nxt)
+            n_done += int(d.sum())
             t += 1
     assert env.t == 3 * T
+    assert n_done > 0 or dim != 3                            # 3D episodes end within 90 steps: the reset rows were exercised
     g_ref, sc_ref = ob.export()
     st = env.export_state()
     assert np.array_equal(st["grid"].cpu().numpy().reshape(g_ref.shape), g_ref)
