@@ -68,9 +68,15 @@ class HostStepper:
     * ``obs_dtype="record"`` envs: ``step(actions) -> records``, a structured array (``record_dtype``) whose fields ``win``,
       ``count_brick``, ``count_step``, ``reward``, ``done`` are views into the one buffer that was copied -- 56 B per env
       instead of 209 B: the PCIe link carries 3.7x fewer bytes per step.
-    """
 
-    def __init__(self, env: BatchedDMPEnv, buffers: int = 2):
+    ``mapped=True`` drops both copies: the pinned host buffers are mapped into the device's address space (unified
+    addressing), the kernel reads the actions from host memory and writes its results straight into the pinned result
+    buffer -- one launch and one synchronisation per step, and the transfer overlaps the kernel.  Default: mapped for
+    small batches (a step is then bound by call latency, not bytes), staged copies otherwise.
+    """
+    MAPPED_MAX_BYTES = 1 << 18       # default switch-over: results of at most 256 KB per step go through mapped memory
+
+    def __init__(self, env: BatchedDMPEnv, buffers: int = 2, mapped: Optional[bool] = None):
         self.env = env
         n, row = env.num_envs, env.obs_row
         dev = env.device
@@ -84,14 +90,12 @@ class HostStepper:
             self._off_done = self._off_rew + _align16(4 * n)
             total = self._off_done + n
         self._total = total
-        self._res_dev = torch.empty(total, dtype=torch.uint8, device=dev)
-        self._obs_dev = self._res_dev[:self._obs_bytes].view(env.obs_dtype).view(1, n, row)
-        self._rew_dev = self._done_dev = None
-        if not env.records:
-            self._rew_dev = self._res_dev[self._off_rew:self._off_rew + 4 * n].view(torch.float32).view(1, n)
-            self._done_dev = self._res_dev[self._off_done:self._off_done + n].view(1, n)
+        self.mapped = (total <= self.MAPPED_MAX_BYTES) if mapped is None else bool(mapped)
         self._res_pin = [torch.empty(total, dtype=torch.uint8, pin_memory=True) for _ in range(max(1, int(buffers)))]
         self._views = [self._host_views(b.numpy()) for b in self._res_pin]
+        # what the kernel writes: the device result buffer, or (mapped) each pinned buffer itself
+        self._res_dev = None if self.mapped else torch.empty(total, dtype=torch.uint8, device=dev)
+        self._outs = [self._out_tensors(b) for b in ((self._res_pin) if self.mapped else [self._res_dev])]
         self._in_pin = torch.empty(2 * n, dtype=torch.uint8, pin_memory=True)          # [actions | step sizes]
         self._in_dev = torch.empty(2 * n, dtype=torch.uint8, device=dev)
         self._in_np = self._in_pin.numpy()
@@ -100,6 +104,14 @@ class HostStepper:
         self._i = 0
         self.h2d_bytes = n                                  # 2 n when step sizes are injected
         self.d2h_bytes = total
+
+    def _out_tensors(self, buf: torch.Tensor):
+        env, n = self.env, self.env.num_envs
+        obs = buf[:self._obs_bytes].view(env.obs_dtype).view(1, n, env.obs_row)
+        if env.records:
+            return obs, None, None
+        return (obs, buf[self._off_rew:self._off_rew + 4 * n].view(torch.float32).view(1, n),
+                buf[self._off_done:self._off_done + n].view(1, n))
 
     def _host_views(self, buf: np.ndarray):
         env, n = self.env, self.env.num_envs
@@ -118,15 +130,19 @@ class HostStepper:
         if step_sizes is not None and step_sizes is not self.step_sizes_buffer:
             self.step_sizes_buffer[:] = step_sizes
         nin = n if step_sizes is None else 2 * n
-        pin = self._res_pin[self._i]
-        out = self._views[self._i]
-        self._i = (self._i + 1) % len(self._res_pin)
+        j = self._i
+        pin, out = self._res_pin[j], self._views[j]
+        self._i = (j + 1) % len(self._res_pin)
         with torch.cuda.device(env.device):
-            self._in_dev[:nin].copy_(self._in_pin[:nin], non_blocking=True)
-            env.rollout(1, actions=self._in_dev[:n].view(1, n),
-                        step_sizes=None if step_sizes is None else self._in_dev[n:].view(1, n),
-                        out=(self._obs_dev, self._rew_dev, self._done_dev))
-            pin.copy_(self._res_dev, non_blocking=True)
+            if self.mapped:                                 # the kernel reads / writes the pinned host buffers themselves
+                env.rollout(1, actions=self._in_pin[:n].view(1, n),
+                            step_sizes=None if step_sizes is None else self._in_pin[n:].view(1, n),
+                            out=self._outs[j])
+            else:
+                self._in_dev[:nin].copy_(self._in_pin[:nin], non_blocking=True)
+                env.rollout(1, actions=self._in_dev[:n].view(1, n),
+                            step_sizes=None if step_sizes is None else self._in_dev[n:].view(1, n), out=self._outs[0])
+                pin.copy_(self._res_dev, non_blocking=True)
             torch.cuda.current_stream(env.device).synchronize()
         return out
 
@@ -708,7 +724,7 @@ class VectorizedEnvWrapper:
     the step after next; copy what must live longer).  Rewards are converted to float64 on the device."""
 
     def __init__(self, env_: _ScalarDMP, num_envs: int = 1, obs_dtype=torch.float64, auto_reset: bool = False,
-                 step_size_rng: str = "numpy"):
+                 step_size_rng: str = "numpy", mapped: Optional[bool] = None):
         if step_size_rng not in ("numpy", "philox"):
             raise ValueError('step_size_rng must be "numpy" or "philox"')
         self.env = env_
@@ -748,6 +764,14 @@ class VectorizedEnvWrapper:
         self._i = 0
         self.h2d_bytes = 2 * n if step_size_rng == "numpy" else n
         self.d2h_bytes = total
+        # small batches (the reference's own --num_envs 3 / 5): no staging copies at all -- the kernel reads the actions from
+        # and writes its results into mapped pinned host memory; a step is one launch and one synchronisation
+        self.mapped = (total <= HostStepper.MAPPED_MAX_BYTES) if mapped is None else bool(mapped)
+        if self.mapped:
+            self._rew32_pin = torch.empty((1, n), dtype=torch.float32, pin_memory=True)
+            self._rew32_np = self._rew32_pin.numpy()[0]
+            self._outs = [(b[:self._obs_bytes].view(obs_dtype).view(1, n, D), self._rew32_pin, b[self._off_done:].view(1, n))
+                          for b in self._res_pin]
 
     def _draw_plans(self, n):
         if not self._proto._dynamic:
@@ -778,8 +802,16 @@ class VectorizedEnvWrapper:
             self._in_np[n:] = np.random.randint(1, 4, size=n)
         self._in_np[:n] = actions
         nin = 2 * n if numpy_rng else n
-        pin, out = self._res_pin[self._i], self._views[self._i]
+        j = self._i
+        pin, out = self._res_pin[j], self._views[j]
         self._i ^= 1
+        if self.mapped:
+            with torch.cuda.device(vec.device):
+                vec.rollout(1, actions=self._in_pin[:n].view(1, n),
+                            step_sizes=self._in_pin[n:].view(1, n) if numpy_rng else None, out=self._outs[j])
+                torch.cuda.current_stream(vec.device).synchronize()
+            out[1][:] = self._rew32_np                          # float64 rewards like the reference's np.asarray(...)
+            return out
         with torch.cuda.device(vec.device):
             self._in_dev[:nin].copy_(self._in_pin[:nin], non_blocking=True)
             vec.rollout(1, actions=self._in_dev[:n].view(1, n),

@@ -14,9 +14,12 @@
 
 namespace {
 
-constexpr int B2 = 128;                 // threads (= envs) per block
-constexpr int S2_WORDS = 18;            // smem words per env: 2 zero | 13 grid | 3 zero
-constexpr int S2_G0 = 2;                // first grid word
+// Threads (= envs) per block is a template parameter BT.  Shared memory per env: 13 grid words + the 51-word row of the warp
+// tile = 256 B, so an SM holds 6 blocks of 128 threads (80 registers) or 4 blocks of 224 threads (72 registers; 4 x (224 x 256
+// + 1 KB reserved) is exactly the SM's 228 KB): 768 or 896 resident envs per SM.  The launcher picks the shape that covers
+// the shard in ONE wave where the other needs two -- BASELINE's 1 048 576 envs over 8 GPUs are 131 072 per GPU: 1.15 waves
+// of 128-thread blocks, 0.99 of 224-thread blocks (wide_blocks2 below has the measurements).
+constexpr int S2_WORDS = GRID2D_WORDS;  // smem words per env: the 13 grid words, [word][thread]
 constexpr uint32_t COLVALID = 0x7FFFF8u;  // padded columns 3..22 are inside the plan area
 
 struct Env2 {
@@ -53,28 +56,30 @@ __device__ __forceinline__ void stage_move2(Env2& e, int a, int s) {
 // stage (b): brick deposition into the bit grid (g = this thread's smem column).  Returns the
 // previous occupancy of the cell (nonzero = was already occupied); :120-125, :129-130, :143-144
 // (increment then clip to 1 == OR of one bit).
+template <int BT>
 __device__ __forceinline__ uint32_t stage_deposit2(uint32_t* g, const Env2& e, int& word, uint32_t& bit) {
     const int b = (e.pr - D2_HW) * D2_W + (e.pc - D2_HW);
     word = b >> 5;
     bit = 1u << (b & 31);
-    const uint32_t old = g[(S2_G0 + word) * B2];
-    g[(S2_G0 + word) * B2] = old | bit;
+    const uint32_t old = g[word * BT];
+    g[word * BT] = old | bit;
     return old & bit;
 }
 
 // stage (c): observation window -> this thread's row of the warp tile.  observation_ :78-82 + hstack.
 // For a record row (Rec56) the seven row codes ARE the window bytes; reward and done ride along.
-template <typename ObsT>
+template <typename ObsT, int BT>
 __device__ __forceinline__ void stage_observe2(const uint32_t* g, const Env2& e, ObsT* row,
                                                bool normalise, int total_brick, int total_step,
                                                float reward = 0.f, bool done = false) {
-    // rows pr-3 .. pr+3 of the padded grid are interior rows pr-6 .. pr; the grid words are stored
-    // behind 64 zero bits so that the 143-bit span [B0, B0+143) is always in range.  Starting 3 bits
-    // early puts interior column c of every row at bit c+3 = its padded column.
-    const int B0 = 64 + (e.pr - 2 * D2_HW) * D2_W - D2_HW;
-    const int w0 = B0 >> 5, off = B0 & 31;
-    const uint32_t x0 = g[(w0 + 0) * B2], x1 = g[(w0 + 1) * B2], x2 = g[(w0 + 2) * B2];
-    const uint32_t x3 = g[(w0 + 3) * B2], x4 = g[(w0 + 4) * B2], x5 = g[(w0 + 5) * B2];
+    // rows pr-3 .. pr+3 of the padded grid are interior rows pr-6 .. pr: a 143-bit span [B0, B0+143) of the bit grid that
+    // starts up to 63 bits before it and ends up to 124 bits behind it.  Starting 3 bits early puts interior column c of
+    // every row at bit c+3 = its padded column.  Words outside the grid are read at a clamped index: whatever they hold
+    // only reaches rows that are masked as frame below (a valid row's 20 bits always lie inside words 0..12).
+    const int B0 = (e.pr - 2 * D2_HW) * D2_W - D2_HW;                  // -63 .. 317
+    const int w0 = B0 >> 5, off = B0 & 31;                               // arithmetic shift: floor for negative B0
+    auto gw = [&](int j) { return g[min(max(w0 + j, 0), GRID2D_WORDS - 1) * BT]; };
+    const uint32_t x0 = gw(0), x1 = gw(1), x2 = gw(2), x3 = gw(3), x4 = gw(4), x5 = gw(5);
     const uint32_t q0 = __funnelshift_r(x0, x1, off), q1 = __funnelshift_r(x1, x2, off);
     const uint32_t q2 = __funnelshift_r(x2, x3, off), q3 = __funnelshift_r(x3, x4, off);
     const uint32_t q4 = __funnelshift_r(x4, x5, off);
@@ -122,11 +127,12 @@ __device__ __forceinline__ void stage_observe2(const uint32_t* g, const Env2& e,
 }
 
 // stage (d) helper: IoU = |G & P| / |G | P| over the interior (render :169-175) with warp-free popc.
+template <int BT>
 __device__ __forceinline__ double iou2(const uint32_t* g, const uint32_t* __restrict__ plan) {
     int inter = 0, uni = 0;
 #pragma unroll
     for (int w = 0; w < GRID2D_WORDS; ++w) {
-        const uint32_t gw = g[(S2_G0 + w) * B2], pw = __ldg(plan + w);
+        const uint32_t gw = g[w * BT], pw = __ldg(plan + w);
         inter += __popc(gw & pw);
         uni += __popc(gw | pw);
     }
@@ -136,12 +142,13 @@ __device__ __forceinline__ double iou2(const uint32_t* g, const uint32_t* __rest
 // TMA = true: the warp tile leaves through one bulk async copy (dmp_common.cuh: warp_tile_bulk_store) instead of 13 x
 // (LDS.128 + STG.128) per lane: the L1 data pipe was the busiest unit of this kernel (ncu: 69 %).
 // ObsT = float / double / int16_t: [n][51] observation rows; ObsT = Rec56: one packed 56 B step record per env.
-template <typename ObsT, bool TMA>
-__global__ void __launch_bounds__(B2, TMA ? 6 : 7) k2d_rollout(const DmpState st, const DmpIO io, const int K) {
+template <typename ObsT, bool TMA, int BT>
+__global__ void __launch_bounds__(BT, BT == 128 ? 6 : 4) k2d_rollout(const DmpState st, const DmpIO io, const int K) {
     constexpr int ROW = row_elems<ObsT, D2_OBS>();                       // tile elements per env (51 values or 1 record)
+    constexpr int B2 = BT;
     extern __shared__ uint4 smem_raw[];
-    uint32_t* G = reinterpret_cast<uint32_t*>(smem_raw);                 // [S2_WORDS][B2]
-    ObsT* tiles = reinterpret_cast<ObsT*>(G + S2_WORDS * B2);            // [B2/32][32*ROW]
+    uint32_t* G = reinterpret_cast<uint32_t*>(smem_raw);                 // [S2_WORDS][BT]
+    ObsT* tiles = reinterpret_cast<ObsT*>(G + S2_WORDS * B2);            // [BT/32][32*ROW]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t n = st.n_envs;
     const int64_t env = (int64_t)blockIdx.x * B2 + tid;
@@ -168,12 +175,10 @@ __global__ void __launch_bounds__(B2, TMA ? 6 : 7) k2d_rollout(const DmpState st
             v0 = cells[env]; v1 = cells[n + env]; v2 = cells[2 * n + env]; v3 = cells[3 * n + env];
         }
     }
-    g[0] = 0; g[B2] = 0;
-    g[2 * B2] = v0.x;  g[3 * B2] = v0.y;  g[4 * B2] = v0.z;  g[5 * B2] = v0.w;
-    g[6 * B2] = v1.x;  g[7 * B2] = v1.y;  g[8 * B2] = v1.z;  g[9 * B2] = v1.w;
-    g[10 * B2] = v2.x; g[11 * B2] = v2.y; g[12 * B2] = v2.z; g[13 * B2] = v2.w;
-    g[14 * B2] = v3.x;
-    g[15 * B2] = 0; g[16 * B2] = 0; g[17 * B2] = 0;
+    g[0 * B2] = v0.x;  g[1 * B2] = v0.y;  g[2 * B2] = v0.z;  g[3 * B2] = v0.w;
+    g[4 * B2] = v1.x;  g[5 * B2] = v1.y;  g[6 * B2] = v1.z;  g[7 * B2] = v1.w;
+    g[8 * B2] = v2.x;  g[9 * B2] = v2.y;  g[10 * B2] = v2.z; g[11 * B2] = v2.w;
+    g[12 * B2] = v3.x;
     Env2 e;
     unpack2(v3, e);
     if (!live) { e.pr = e.pc = D2_LO; e.plan_idx = 0; }
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__(B2, TMA ? 6 : 7) k2d_rollout(const DmpState st
         } else if (a == 4) {                                // (b) drop + (d) reward
             e.cb += 1;
             int word; uint32_t bit;
-            const uint32_t was = stage_deposit2(g, e, word, bit);
+            const uint32_t was = stage_deposit2<BT>(g, e, word, bit);
             dirty |= 1u << (word >> 2);
             if (e.cb >= total_brick) {                      // :127-135 budget exhausted: reward 0.0
                 done = true;
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(B2, TMA ? 6 : 7) k2d_rollout(const DmpState st
             ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * ROW;
             if constexpr (TMA) {
                 if (k > 0) warp_tile_bulk_wait(lane);               // the previous step's copy has drained the tile
-                stage_observe2<ObsT>(g, e, tile + lane * ROW, normalise, total_brick, st.total_step, reward, done);
+                stage_observe2<ObsT, BT>(g, e, tile + lane * ROW, normalise, total_brick, st.total_step, reward, done);
                 if (nvalid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
                     warp_tile_bulk_store(dst, tile, 32 * ROW * sizeof(ObsT), lane);
                 } else {
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(B2, TMA ? 6 : 7) k2d_rollout(const DmpState st
                     if (nvalid > 0) tile_rows_store<ObsT, D2_OBS>(dst, tile, nvalid, lane);
                 }
             } else {
-                stage_observe2<ObsT>(g, e, tile + lane * ROW, normalise, total_brick, st.total_step, reward, done);
+                stage_observe2<ObsT, BT>(g, e, tile + lane * ROW, normalise, total_brick, st.total_step, reward, done);
                 __syncwarp();
                 if (nvalid == 32) tile_rows_store_full<ObsT, D2_OBS>(dst, tile, lane);
                 else if (nvalid > 0) tile_rows_store<ObsT, D2_OBS>(dst, tile, nvalid, lane);
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(B2, TMA ? 6 : 7) k2d_rollout(const DmpState st
 
         // ---- (e) done / auto-reset ------------------------------------------------------------
         if (done && autoreset && live) {
-            const double iou = iou2(g, plans + e.plan_idx * PLAN2D_WORDS);
+            const double iou = iou2<BT>(g, plans + e.plan_idx * PLAN2D_WORDS);
             atomicAdd(st.ep_cnt + env, 1u);                 // fire-and-forget REDs: no read-modify-write stall
             atomicAdd(st.ep_len + env, (uint32_t)e.cs);
             atomicAdd(st.ep_ret + env, (double)e.ret);
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(B2, TMA ? 6 : 7) k2d_rollout(const DmpState st
             }
             total_brick = __ldg(st.plan_total + e.plan_idx);
 #pragma unroll
-            for (int w = 0; w < GRID2D_WORDS; ++w) g[(S2_G0 + w) * B2] = 0;
+            for (int w = 0; w < GRID2D_WORDS; ++w) g[w * B2] = 0;
             e.pr = e.pc = D2_LO;
             e.cb = e.cs = 0;
             e.ret = 0.f;
@@ -279,16 +284,16 @@ __global__ void __launch_bounds__(B2, TMA ? 6 : 7) k2d_rollout(const DmpState st
             errbits |= DMP_ERR_OVERFLOW;
             e.cb = min(e.cb, 0xFFFF); e.cs = min(e.cs, 0xFFFF);
         }
-        pack2(e, g[14 * B2], v3);
+        pack2(e, g[12 * B2], v3);
         if (hint) {
-            if (dirty & 1u) stg_keep(cells + env, make_uint4(g[2 * B2], g[3 * B2], g[4 * B2], g[5 * B2]), keep);
-            if (dirty & 2u) stg_keep(cells + n + env, make_uint4(g[6 * B2], g[7 * B2], g[8 * B2], g[9 * B2]), keep);
-            if (dirty & 4u) stg_keep(cells + 2 * n + env, make_uint4(g[10 * B2], g[11 * B2], g[12 * B2], g[13 * B2]), keep);
+            if (dirty & 1u) stg_keep(cells + env, make_uint4(g[0 * B2], g[1 * B2], g[2 * B2], g[3 * B2]), keep);
+            if (dirty & 2u) stg_keep(cells + n + env, make_uint4(g[4 * B2], g[5 * B2], g[6 * B2], g[7 * B2]), keep);
+            if (dirty & 4u) stg_keep(cells + 2 * n + env, make_uint4(g[8 * B2], g[9 * B2], g[10 * B2], g[11 * B2]), keep);
             stg_keep(cells + 3 * n + env, v3, keep);
         } else {
-            if (dirty & 1u) cells[env] = make_uint4(g[2 * B2], g[3 * B2], g[4 * B2], g[5 * B2]);
-            if (dirty & 2u) cells[n + env] = make_uint4(g[6 * B2], g[7 * B2], g[8 * B2], g[9 * B2]);
-            if (dirty & 4u) cells[2 * n + env] = make_uint4(g[10 * B2], g[11 * B2], g[12 * B2], g[13 * B2]);
+            if (dirty & 1u) cells[env] = make_uint4(g[0 * B2], g[1 * B2], g[2 * B2], g[3 * B2]);
+            if (dirty & 2u) cells[n + env] = make_uint4(g[4 * B2], g[5 * B2], g[6 * B2], g[7 * B2]);
+            if (dirty & 4u) cells[2 * n + env] = make_uint4(g[8 * B2], g[9 * B2], g[10 * B2], g[11 * B2]);
             cells[3 * n + env] = v3;
         }
         if (errbits) atomicOr(st.err, errbits);
@@ -410,18 +415,40 @@ __global__ void k2d_import(const DmpState st, const int32_t* __restrict__ grid, 
     if (ret) wref(15) = __float_as_uint(ret[env]);
 }
 
-template <typename ObsT, bool TMA>
-int launch_rollout2_t(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
-    const size_t smem = (size_t)S2_WORDS * B2 * 4 + (size_t)(B2 / 32) * 32 * row_elems<ObsT, D2_OBS>() * sizeof(ObsT);
+template <typename ObsT, bool TMA, int BT>
+int launch_rollout2_b(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    const size_t smem = (size_t)S2_WORDS * BT * 4 + (size_t)(BT / 32) * 32 * row_elems<ObsT, D2_OBS>() * sizeof(ObsT);
     static bool attr_done = false;           // per instantiation
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k2d_rollout<ObsT, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k2d_rollout<ObsT, TMA, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return dmp_set_error(e);
+        e = cudaFuncSetAttribute(k2d_rollout<ObsT, TMA, BT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return dmp_set_error(e);
         attr_done = true;
     }
-    const unsigned blocks = (unsigned)((st.n_envs + B2 - 1) / B2);
-    return dmp_set_error(dmp_launch_pdl(!(io.flags & DMP_F_NO_PDL), k2d_rollout<ObsT, TMA>, blocks, (unsigned)B2, smem, s,
+    const unsigned blocks = (unsigned)((st.n_envs + BT - 1) / BT);
+    return dmp_set_error(dmp_launch_pdl(!(io.flags & DMP_F_NO_PDL), k2d_rollout<ObsT, TMA, BT>, blocks, (unsigned)BT, smem, s,
                                         st, io, K));
+}
+
+// Launch shape by shard size: 128-thread blocks hold 768 envs per SM, 224-thread blocks 896 (see the top of the file).
+// Measured at 20 steps per launch (f32 observations, G env-steps/s, narrow / wide): 1 048 576 envs 30.4 / 29.3, 524 288
+// 30.2 / 28.9, 262 144 29.6 / 27.7 -- but 131 072 envs (BASELINE's batch over 8 GPUs) 22.7 / 26.5: there the narrow shape
+// needs a second, nearly empty wave whose blocks run latency-bound while the wide shape holds every env at once.  So the
+// wide shape is taken exactly when it turns two waves into one.  DMP_F_GENERIC keeps 128-thread blocks.
+constexpr int B2_NARROW = 128, B2_WIDE = 224, SMS = 148;
+inline bool wide_blocks2(int64_t n, uint32_t flags) {
+    if (flags & DMP_F_GENERIC) return false;
+    const int64_t cap_n = (int64_t)SMS * 6 * B2_NARROW, cap_w = (int64_t)SMS * 4 * B2_WIDE;     // 113 664 / 132 608 envs
+    return n > cap_n && n <= cap_w;
+}
+
+template <typename ObsT, bool TMA>
+int launch_rollout2_t(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    // (the residency figures above hold for tile rows of at most 204 B; float64 observations keep the narrow shape)
+    if (row_elems<ObsT, D2_OBS>() * sizeof(ObsT) <= 204 && wide_blocks2(st.n_envs, io.flags))
+        return launch_rollout2_b<ObsT, TMA, B2_WIDE>(st, io, K, s);
+    return launch_rollout2_b<ObsT, TMA, B2_NARROW>(st, io, K, s);
 }
 
 // the observation tile leaves through one bulk async copy per warp and step unless DMP_F_TILE_LDST asks for load/store pairs

@@ -302,8 +302,8 @@ class BatchedDMPEnv:
     def _u8(self, x, shape, what) -> torch.Tensor:
         if not torch.is_tensor(x):
             x = torch.as_tensor(np.asarray(x), device=self.device)
-        if x.device != self.device:
-            x = x.to(self.device, non_blocking=True)
+        if x.device != self.device and not (x.device.type == "cpu" and x.is_pinned()):
+            x = x.to(self.device, non_blocking=True)        # pinned host tensors are mapped: the kernel reads them in place
         if x.dtype != torch.uint8:
             x = x.to(torch.uint8)
         if tuple(x.shape) != tuple(shape):

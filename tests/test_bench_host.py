@@ -12,12 +12,13 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
-@pytest.mark.parametrize("K,KL,G", [(16384, 16, 16), (8192, 1, 32), (100, 16, 16), (3, 16, 16), (1, 1, 32), (4097, 64, 16),
-                                    (6000, 16, 16), (7500, 64, 16)])
-def test_launch_plan_times_exactly_k_steps(K, KL, G):
-    n_replay, n_tail, rem = bench.plan_launches(K, KL, G)
-    assert n_replay * G * KL + n_tail * KL + rem == K
-    assert 0 <= n_tail < G and 0 <= rem < KL
+@pytest.mark.parametrize("K,KL", [(20, 64), (20, 16), (8192, 1), (100, 16), (3, 16), (1, 1), (4097, 64), (64, 64), (65, 64)])
+def test_launch_plan_times_exactly_k_steps(K, KL):
+    launches = bench.plan_launches(K, KL)
+    assert sum(launches) == K and all(0 < k <= KL for k in launches)
+    assert len(launches) == -(-K // KL) and all(k == KL for k in launches[:-1])
+    if K <= KL:
+        assert launches == [K]                       # the driver's --steps 20: ONE dmp_rollout launch per timed region
 
 
 def test_workload_table_matches_baseline_configs():
@@ -33,18 +34,21 @@ def test_workload_table_matches_baseline_configs():
 
 
 def test_reference_arm_prints_one_contract_line():
-    """`bench.py --impl reference` (the oracle port on the host cores) on a tiny sample: one JSON line with the
-    contract's keys; non-zero ranks print nothing."""
+    """`bench.py --impl reference` (the staged reference classes -- the oracle port where nothing is staged -- on the
+    host cores) on a tiny sample: one JSON line with the contract's keys; non-zero ranks print nothing."""
     env = dict(os.environ, RANK="0", WORLD_SIZE="1")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "30", "--warmup", "3",
-                          "--workload", "2d_static_dense"], capture_output=True, text=True, env=env, timeout=600)
+                          "--workload", "2d_static_dense", "--ref-envs-per-proc", "8"], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "env-steps/sec" and d["higher_is_better"] is True
     assert d["steps"] == 30 and d["value"] > 0 and d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    if d["cpu_baseline"]["kind"] == "reference":
+        assert "UNMODIFIED reference classes" in d["cpu_baseline"]["sample"] and d["cpu_baseline_port"]["value"] > 0
+    assert d["config"]["workload"] == "2d_static_dense" and d["config"]["total_envs"] == 1048576
     assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     env["RANK"] = "1"
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "30", "--warmup", "3"],

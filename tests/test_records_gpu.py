@@ -89,7 +89,8 @@ def test_records_reject_normalised_counters_and_stage_kernels():
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dim,kind", [(1, torch.float32), (2, torch.float32), (2, torch.int16), (3, torch.float64),
                                       (1, "record"), (2, "record"), (3, "record")])
-def test_host_stepper_returns_what_a_device_step_returns(dim, kind):
+@pytest.mark.parametrize("mapped", [False, True], ids=["staged", "mapped"])
+def test_host_stepper_returns_what_a_device_step_returns(dim, kind, mapped):
     from snac_b200.compat import HostStepper
     from snac_b200.vecenv import unpack_records
     n, T = 300, 60
@@ -97,7 +98,8 @@ def test_host_stepper_returns_what_a_device_step_returns(dim, kind):
     env = make_gpu(dim, False, n, 0, auto_reset=True, seed=SEED, obs_dtype=kind)
     ref = make_gpu(dim, False, n, 0, auto_reset=True, seed=SEED, obs_dtype=torch.float64)
     env.reset(), ref.reset()
-    hs = HostStepper(env)
+    assert HostStepper(env).mapped == (HostStepper(env)._total <= HostStepper.MAPPED_MAX_BYTES)     # default: by result size
+    hs = HostStepper(env, mapped=mapped)                     # mapped: the kernel reads / writes pinned host memory itself
     assert hs.d2h_bytes == (n * env.obs_row if kind == "record" else
                             hs._off_done + n) and hs.h2d_bytes == n
     rng = np.random.RandomState(1)
@@ -122,12 +124,14 @@ def test_host_stepper_returns_what_a_device_step_returns(dim, kind):
     env.check_errors()
 
 
-def test_vectorized_wrapper_philox_mode_and_views():
+@pytest.mark.parametrize("mapped", [False, True], ids=["staged", "mapped"])
+def test_vectorized_wrapper_philox_mode_and_views(mapped):
     """step_size_rng="philox": no host draws; results equal a BatchedDMPEnv stepped with the same actions; the returned
-    arrays are float64 / float64 / bool views that survive one more step."""
+    arrays are float64 / float64 / bool views that survive one more step.  Staged copies and mapped host buffers."""
     import snac_b200 as S
     n = 64
-    w = S.VectorizedEnvWrapper(S.deep_mobile_printing_2d1r(plan_choose=0), num_envs=n, step_size_rng="philox")
+    w = S.VectorizedEnvWrapper(S.deep_mobile_printing_2d1r(plan_choose=0), num_envs=n, step_size_rng="philox", mapped=mapped)
+    assert w.mapped == mapped
     ref = make_gpu(2, False, n, 0, obs_dtype=torch.float64)
     o = w.reset()
     assert np.array_equal(o[:, 0, :], ref.reset().cpu().numpy())
