@@ -556,15 +556,16 @@ class Bench:
 
     @staticmethod
     def b_layout(dim, b_alg_step, D, KL, philox_actions, mean_len=None):
-        """The same formula with the bytes of THIS repo's 3D layout (byte maps: window 49 x 1 B + 1 B brick, 400 B maps,
-        E = 800/L): what a kernel on this layout has to move at least.  1D/2D: identical to b_alg."""
+        """The same formula with the bytes of THIS repo's 3D layout (nibble maps: window 49 x 0.5 B + the 1 B store that
+        carries the brick instead of 49 x 2 + 2, 208 B maps instead of 800 B, E = 416/L): what a kernel on this layout has
+        to move at least.  1D/2D: identical to b_alg."""
         if dim != 3:
             return Bench.b_alg(dim, b_alg_step, D, KL, philox_actions, mean_len)
         act = 0 if philox_actions else 1
-        E = (800.0 / mean_len) if mean_len else 0.0
+        E = (416.0 / mean_len) if mean_len else 0.0
         if KL == 1:
-            return b_alg_step - 50 - 1 + act + E
-        return act + D * 4 + 5 + (2 * 6 + 8 + 2 * 400) / KL + E
+            return b_alg_step - 100 + 25.5 - 1 + act + E
+        return act + D * 4 + 5 + (2 * 6 + 8 + 2 * 208) / KL + E
 
     def kernel_result(self, wl, total_envs, env, r, KL_eff, philox_actions, mean_len):
         """value / roofline of one time_regions() result (KL_eff: steps per launch the byte formula is evaluated at)."""
@@ -728,7 +729,7 @@ class Bench:
         line = {"metric": METRIC, "value": kr["value"], "unit": "env-steps/s", "n_gpus": self.world, "steps": K, "warmup": W,
                 "ms_per_step": kr["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "u32 bit-grid / i32 counters, f32 observations" if dim == 2 else
-                         ("u16 heights / i32 counters, f32 observations" if dim == 1 else "u8 heights (u16 escape) / i32 counters, f32 observations"),
+                         ("u16 heights / i32 counters, f32 observations" if dim == 1 else "u4 heights (u16 escape) / i32 counters, f32 observations"),
                 "data": "synthetic", "repeats": main["repeats"],
                 "region_ms": {"median": main["ms"], "min": main["ms_min"], "max": main["ms_max"], "mean": main["ms_mean"]},
                 "config": {"workload": wl, "total_envs": total_envs, "envs_per_gpu": n,
@@ -753,7 +754,7 @@ class Bench:
                                         "k%dd%s_rollout<float> (K=%d)" % (dim, "_cache" if dim == 3 else "", KL_eff)),
                              "bytes_per_env_step": kr["bytes_per_env_step"], "envs_per_launch": n,
                              "bytes_per_env_step_this_layout": kr["bytes_per_env_step_this_layout"], "frac_this_layout": kr["frac_this_layout"],
-                             "layout_note": None if dim != 3 else "frac uses SURVEY 8(d)'s canonical u16 maps (800 B, window 98 B, E = 1600/L); this repo's 3D state is byte maps (400 B, window 49 B, E = 800/L): frac_this_layout is the fraction by those bytes"},
+                             "layout_note": None if dim != 3 else "frac uses SURVEY 8(d)'s canonical u16 maps (800 B, window 98 B, E = 1600/L); this repo's 3D state is nibble maps (208 B, window 24.5 B, E = 416/L): frac_this_layout is the fraction by those bytes"},
                 "episode_stats": {"mean_episode_length": mean_len, "mean_iou": (float(stats[1] / stats[2]) if stats[2] > 0 else None),
                                   "mean_return": (float(stats[0] / stats[2]) if stats[2] > 0 else None),
                                   "sum_return": float(stats[0]), "sum_iou": float(stats[1]), "episodes": float(stats[2]),

@@ -21,10 +21,12 @@
  *                              20x20 interior), word 13 = pos_row | pos_col << 8 | plan_idx << 16,
  *                              word 14 = count_brick | count_step << 16, word 15 = episode return (f32)
  *       aux   : unused (NULL)
- *   3D  cells : two areas.  At byte offset 800 n: the BYTE maps u8 [n][400], per-env contiguous 20x20 (row-major, 400 B,
- *               16 B aligned), byte = min(height, 255) -- what single steps and rollouts read and write.  At offset 0:
- *               the WIDE maps u16 [n][400] (800 B per env), exact and maintained only for envs whose tall flag is set
- *               (a height >= 254 somewhere); for every other env the wide map is scratch (the bytes ARE the heights).
+ *   3D  cells : two areas.  At byte offset 800 n: the NIBBLE maps u8 [n][208], per env the 20x20 interior row-major with two
+ *               cells per byte (cell i = nibble i & 1 of byte i >> 1, low nibble first; bytes 200..207 are zero padding
+ *               that keeps every env 16 B aligned), nibble = min(height, 15) -- what single steps and rollouts read and
+ *               write.  At offset 0: the WIDE maps u16 [n][400] (800 B per env), exact and maintained only for envs whose
+ *               tall flag is set (a height >= 15 somewhere); for every other env the wide map is scratch (the nibbles ARE
+ *               the heights: the reference's plans are 6 high).
  *               dmp_export_state / dmp_iou / dmp_import_state convert as needed; callers never see the difference.
  *       aux   : uint4 [n]      .x = pos_row | tall flag << 7 | pos_col << 8 | plan_idx << 16 ;
  *                              .y = count_brick | count_step << 16 ;
@@ -71,7 +73,7 @@ extern "C" {
                             Every reward of the six classes (-100, -1, 0, 1, 5, 10) fits the i8.  DmpIO.reward / DmpIO.done
                             are still written when they are not NULL. */
 #define DMP_REC_DONE       1
-#define DMP_REC_SATURATED  2   /* 3D only: the env holds a height >= 254 ("tall"), so a window byte may have saturated
+#define DMP_REC_SATURATED  2   /* 3D only: the env holds a height >= 15 ("tall"); its window bytes are exact up to 253 and saturate
                                   at 255; read that env's exact observation through another obs kind / dmp_export_state */
 
 /* DmpIO.flags */

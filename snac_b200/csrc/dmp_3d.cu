@@ -1,6 +1,6 @@
 // dmp_3d.cu -- 3D (2.5-D height map) mobile-construction envs: 20x20 heights, 7x7 window,
 // 8 actions (4 collision-checked moves, 4 adjacent builds).  This file holds the dispatch of dmp_rollout for 3D and the
-// warp-per-env utility kernels (reset, IoU, export, import, wide <-> byte map passes); the hot kernels are
+// warp-per-env utility kernels (reset, IoU, export, import, wide <-> nibble map passes); the hot kernels are
 // dmp_3d_roll.cu (K steps per launch) and dmp_3d_step.cu (single steps).
 //
 // Reference semantics: Env/3D/DMP_simulator_3d_static_circle.py:67-276 (static, T=1300) and
@@ -91,7 +91,7 @@ __global__ void k3d_reset(const DmpState st, const uint8_t* __restrict__ mask, c
     const uint4 z = make_uint4(0, 0, 0, 0);
     g4[lane] = z;
     if (lane < 18) g4[lane + 32] = z;
-    if (lane < 25) reinterpret_cast<uint4*>(bmap3(st) + env * CELLS3D)[lane] = z;       // byte shadow
+    if (lane < NIB3_STRIDE / 16) reinterpret_cast<uint4*>(nmap3(st) + env * NIB3_STRIDE)[lane] = z;      // nibble map
     if (lane == 0) aux[env] = pack3(Env3{D2_LO, D2_LO, p, 0, 0, 0.f, 0});
     if (obs) {
         if constexpr (is_rec<ObsT>::value) {
@@ -163,24 +163,26 @@ __global__ void k3d_import(const DmpState st, const int32_t* __restrict__ grid, 
     if (lane == 0) aux[env] = pack3(e);
 }
 
-// bytes := min(wide, 255) and flag := any(wide >= TALL3) for every env; one warp per env
+// nibbles := min(wide, 15) and flag := any(wide >= TALL3) for every env; one warp per env
 __global__ void k3d_sync_bytes(const DmpState st) {
     const int lane = threadIdx.x & 31;
     const int64_t env = (int64_t)blockIdx.x * WPB3 + (threadIdx.x >> 5);
     if (env >= st.n_envs) return;
     bool tall = false;
-    if (lane < 25) {                                     // 16 cells per lane
+    if (lane < 25) {                                     // 16 cells per lane: 32 B of heights -> 8 B of nibbles
         const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(st.cells) + env * CELLS3D) + 2 * lane;
         const uint4 a = src[0], b = src[1];
         const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        uint32_t o[4];
+        uint32_t o[2] = {0u, 0u};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t h0 = w[2 * q] & 0xFFFFu, h1 = w[2 * q] >> 16, h2 = w[2 * q + 1] & 0xFFFFu, h3 = w[2 * q + 1] >> 16;
-            tall |= max(max(h0, h1), max(h2, h3)) >= (uint32_t)TALL3;
-            o[q] = min(h0, 255u) | (min(h1, 255u) << 8) | (min(h2, 255u) << 16) | (min(h3, 255u) << 24);
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t h0 = w[q] & 0xFFFFu, h1 = w[q] >> 16;
+            tall |= max(h0, h1) >= (uint32_t)TALL3;
+            o[q >> 2] |= (min(h0, 15u) | (min(h1, 15u) << 4)) << (8 * (q & 3));
         }
-        reinterpret_cast<uint4*>(bmap3(st) + env * CELLS3D)[lane] = make_uint4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<uint2*>(nmap3(st) + env * NIB3_STRIDE)[lane] = make_uint2(o[0], o[1]);
+    } else if (lane == 25) {
+        reinterpret_cast<uint2*>(nmap3(st) + env * NIB3_STRIDE)[25] = make_uint2(0u, 0u);      // pad bytes 200..207
     }
     const bool any = __any_sync(FULL, tall);
     if (lane == 0) {
@@ -189,7 +191,7 @@ __global__ void k3d_sync_bytes(const DmpState st) {
     }
 }
 
-// wide := bytes for every env that is not tall (whose bytes are exact); optionally drops all flags afterwards
+// wide := nibbles for every env that is not tall (whose nibbles are exact); optionally drops all flags afterwards
 __global__ void k3d_widen(const DmpState st, const int clear_flags) {
     const int lane = threadIdx.x & 31;
     const int64_t env = (int64_t)blockIdx.x * WPB3 + (threadIdx.x >> 5);
@@ -197,13 +199,13 @@ __global__ void k3d_widen(const DmpState st, const int clear_flags) {
     uint32_t* ax = reinterpret_cast<uint32_t*>(reinterpret_cast<uint4*>(st.aux) + env);
     const uint32_t x = *ax;
     if (!(x & AUX3_TALL) && lane < 25) {
-        const uint4 b = reinterpret_cast<const uint4*>(bmap3(st) + env * CELLS3D)[lane];
-        const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+        const uint2 b = reinterpret_cast<const uint2*>(nmap3(st) + env * NIB3_STRIDE)[lane];
+        const uint32_t w[2] = {b.x, b.y};
         uint32_t o[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            o[2 * q] = (w[q] & 0xFFu) | ((w[q] & 0xFF00u) << 8);
-            o[2 * q + 1] = ((w[q] >> 16) & 0xFFu) | ((w[q] >> 24) << 16);
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t by = (w[q >> 2] >> (8 * (q & 3))) & 0xFFu;       // cells 2q, 2q+1 of this lane's 16
+            o[q] = (by & 0xFu) | ((by >> 4) << 16);
         }
         uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(st.cells) + env * CELLS3D) + 2 * lane;
         dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -227,7 +229,7 @@ int dmp3d_widen(const DmpState& st, bool clear_flags, cudaStream_t s) {
 }
 
 int dmp3d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
-    // rollouts (K > 1) stage whole byte maps in shared memory; a single step fetches only the rows it can look at
+    // rollouts (K > 1) stage whole maps in shared memory; a single step fetches only the rows it can look at
     if (K > 1 || (io.flags & DMP_F_ROLLOUT_K1)) return dmp3d_cache_rollout(st, io, K, s);
     return dmp3d_step_bytes(st, io, s);
 }

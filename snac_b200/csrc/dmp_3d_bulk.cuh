@@ -42,4 +42,49 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ---- an env turns tall (a height has just reached 15: every nibble, the new one included, is still exact): the warp
+// writes its wide map out, 16 cells per lane.  Rare per env, but among 262 144 random-policy envs it happens in every few
+// launches, and a serial loop over 400 cells held the whole grid up for ~70 us: hence cooperative, one round trip.
+__device__ __forceinline__ void warp_widen_words(uint16_t* wide, uint32_t w0, uint32_t w1, int lane) {
+    const uint32_t w[2] = {w0, w1};                       // this lane's 16 nibbles (cells 16 lane .. 16 lane + 15)
+    uint32_t o[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const uint32_t by = (w[q >> 2] >> (8 * (q & 3))) & 0xFFu;
+        o[q] = (by & 0xFu) | ((by >> 4) << 16);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(wide) + 2 * lane;
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// ---- tall envs (dmp_common.cuh): a nibble that reads 15 stands for "15 or more".  The window of a tall env is formatted
+// from its nibbles like any other; only when a saturated nibble lies inside the window are those cells re-read from the
+// env's exact wide map.  u0 / u1: the seven rows of biased bytes (nibble + 1, 0 = frame): a saturated cell reads 16.
+__device__ __forceinline__ bool window_saturated(const uint32_t (&u0)[7], const uint32_t (&u1)[7]) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) m |= u0[k] | u1[k];
+    return (m & 0x10101010u) != 0u;
+}
+// out of line, practically never: observation values of the saturated cells from the wide map
+template <typename ObsT>
+__device__ __noinline__ void fix_saturated_row(const uint16_t* ge, int pr, int pc, const uint32_t* u0, const uint32_t* u1, ObsT* row) {
+    for (int k = 0; k < 7; ++k) {
+        const uint64_t c = (uint64_t)u0[k] | ((uint64_t)u1[k] << 32);
+        for (int j = 0; j < 7; ++j)
+            if (((c >> (8 * j)) & 0xFFu) == 16u)
+                row[k * 7 + j] = obs_from_int<ObsT>((int)__ldcg(ge + (pr - 6 + k) * 20 + (pc - 6 + j)));
+    }
+}
+// the same for record rows: window bytes = min(height + 1, 255), patched in the packed row codes
+static __device__ __noinline__ void fix_saturated_codes(const uint16_t* ge, int pr, int pc, uint64_t* c) {
+    for (int k = 0; k < 7; ++k)
+        for (int j = 0; j < 7; ++j)
+            if (((c[k] >> (8 * j)) & 0xFFu) == 16u) {
+                const uint64_t h = (uint64_t)min((int)__ldcg(ge + (pr - 6 + k) * 20 + (pc - 6 + j)) + 1, 255);
+                c[k] = (c[k] & ~(0xFFull << (8 * j))) | (h << (8 * j));
+            }
+}
+
 }  // namespace d3

@@ -1,21 +1,21 @@
 // dmp_3d_roll.cu -- 3D envs, rollout kernel (K steps per launch): one env per lane, the warp's 32 height
-// maps cached in shared memory as BYTES.
+// maps cached in shared memory as NIBBLES.
 //
-// Why a byte cache: the step logic only asks "is this cell -1 / 0 / > 0" and the observation wants the raw
+// Why a nibble cache: the step logic only asks "is this cell -1 / 0 / > 0" and the observation wants the raw
 // height, which for every reachable state of the reference's plans is tiny (plan height 6; an env would have
-// to stack 254 bricks on one cell to leave the byte range).  Halving the cache (404 B instead of 816 B per env)
-// lifts the number of resident warps per SM from 7 to 11 (f32 observations; 14 with i16), which is what this
-// latency-bound kernel needs, and an odd word stride (101) makes same-offset accesses of the 32 lanes
-// bank-conflict free.  HBM keeps the same bytes (dmp_common.cuh); every brick is written through.
-//   * state in : the warp's 32 byte maps are one contiguous 12 800 B span (include/dmp.h): 25 coalesced 128-bit
-//                loads per lane in one round trip, four 32-bit shared stores per 16 B.  An env whose tall flag is set
-//                (a height >= 254 somewhere) runs entirely from its wide u16 map in HBM (exact, slow, practically
-//                never); an env that reaches that height inside the launch writes its wide map out and carries on
-//                like that.  Bricks of all other envs are written through to the byte map only.
-//   * step     : neighbours / walk cells / 7x7 window are shared-memory byte reads;
-//   * obs out  : window rows are cut out of the byte map with funnel shifts, biased by +1 (0 = frame), each byte
+// to stack 15 bricks on one cell to leave the nibble range).  204 B per env (instead of 816 B of u16, or 404 B of bytes)
+// lets 16 warps share an SM instead of 7 (11 with bytes), which is what this latency-bound kernel needs, and an odd word
+// stride (51) makes same-offset accesses of the 32 lanes bank-conflict free.  HBM keeps the same nibbles
+// (dmp_common.cuh); every brick is written through.
+//   * state in : the warp's 32 nibble maps are one contiguous 6 656 B span (include/dmp.h): 13 coalesced 128-bit
+//                loads per lane in one round trip.  An env whose tall flag is set (a height >= 15 somewhere) keeps its
+//                wide u16 map in HBM exact as well and reads it only where a nibble says "15 or more" (a build on such
+//                a cell, window cells that read 15); an env that reaches that height inside the launch writes its
+//                wide map out and carries on like that.
+//   * step     : neighbours / walk cells are nibble reads, the 7x7 window is 2 word reads + 1 funnel shift per row;
+//   * obs out  : a row's seven nibbles are spread to bytes (2 LOP + 2 PRMT), biased by +1 (0 = frame), each byte
 //                is dropped into the mantissa of 2^23 (PRMT) and turned into -1/0/h by one FADD; the warp's
-//                [32][51] tile is streamed out as one contiguous span of 128-bit stores;
+//                [32][51] tile leaves as one contiguous span (one bulk async copy per step);
 //   * done     : IoU needs no scan (`cross` is maintained by every build); the warp clears a finished env's
 //                map cooperatively in shared memory and in HBM.
 // Semantics: Env/3D/DMP_simulator_3d_static_circle.py:67-276 and
@@ -26,10 +26,10 @@ namespace {
 
 using namespace d3;
 
-constexpr int MAP_B = 404;                    // bytes per env in the cache: 400 cells + 4 pad = 101 words (odd)
-constexpr int FRONT = 80;                     // guard in front of env 0 of a warp: unclamped reads reach 64 B back
-constexpr int WARP_MAP_B = FRONT + 32 * MAP_B;  // 13 008 (multiple of 16); reads past the end land in the next
-                                              // warp's guard or in the tiles
+constexpr int MAP_W = 51;                     // words per env in the cache: 400 nibbles = 50 words + 1 pad (odd stride)
+constexpr int MAP_B = MAP_W * 4;              // 204 B
+constexpr int FRONT = 32;                     // guard in front of env 0 of a warp: unclamped reads reach 63 nibbles back
+constexpr int WARP_MAP_B = FRONT + 32 * MAP_B;  // 6 560 (multiple of 16); reads past the end (<= 32 B) land in the tile
 constexpr size_t SMEM_MAX = 232448;           // 227 KB opt-in limit per block
 
 struct EnvR {
@@ -38,59 +38,35 @@ struct EnvR {
     int cross;      // running sum(min(height, plan)): +1 per brick laid at or below the plan height
 };
 
-// environment_memory[r][c] (padded coordinates) from HBM (tall envs only); -1 on the frame (:72-75).
-// .cg: other lanes of the warp clear maps with plain stores.
-__device__ __forceinline__ int cell_g(const uint16_t* ge, int r, int c) {
-    const unsigned ir = (unsigned)(r - 3), ic = (unsigned)(c - 3);
-    return (ir < 20u && ic < 20u) ? (int)__ldcg(ge + ir * 20u + ic) : -1;
-}
+// cell i of a cached nibble map (i may run into the guards: the caller masks what it reads there)
+__device__ __forceinline__ int nib_at(const uint32_t* gw, int i) { return (int)((gw[i >> 3] >> ((i & 7) * 4)) & 0xFu); }
 
-// an env turns tall: its wide map in HBM := the (still exact) byte cache.  Out of line, practically never.
-__device__ __noinline__ void widen_from_cache(uint16_t* ge, const uint8_t* gb) {
-    for (int i = 0; i < CELLS3D; ++i) ge[i] = gb[i];
-}
-
-// out-of-line copy for the tall-env path (keeps the hot loop small)
-__device__ __noinline__ int cell_tall(const uint16_t* ge, int r, int c) { return cell_g(ge, r, c); }
-
-template <typename ObsT>
-__device__ __noinline__ void observe_tall(const uint16_t* ge, int pr, int pc, ObsT* row) {
-    for (int k = 0; k < 7; ++k)
-        for (int j = 0; j < 7; ++j) row[k * 7 + j] = obs_from_int<ObsT>(cell_g(ge, pr - 3 + k, pc - 3 + j));
-}
-// the same as record bytes (value + 1, saturating at 255; the record carries DMP_REC_SATURATED)
-__device__ __noinline__ void window_tall_bytes(const uint16_t* ge, int pr, int pc, uint64_t (&c)[7]) {
-    for (int k = 0; k < 7; ++k) {
-        uint64_t v = 0;
-        for (int j = 0; j < 7; ++j) v |= (uint64_t)min(cell_g(ge, pr - 3 + k, pc - 3 + j) + 1, 255) << (8 * j);
-        c[k] = v;
-    }
-}
-
-// stage (c): 7x7 window of this lane's env (byte cache) -> its row of the warp tile.  The seven rows are
-// read at fixed word offsets from one base (rows outside the map land in the guards / the neighbouring
-// env and are masked), so no per-row clamping or address arithmetic is needed.
-__device__ __forceinline__ void window_cache(const uint8_t* gb, int pr, int pc, uint32_t (&u0)[7], uint32_t (&u1)[7]) {
+// stage (c): 7x7 window of this lane's env (nibble cache) -> seven rows of biased bytes (height + 1, 0 = frame), two
+// words per row.  Row k starts 20 k nibbles after row 0: two word reads and one funnel shift cut its seven nibbles out
+// (rows outside the map land in the guards / the neighbouring env and are masked), 2 LOP + 2 PRMT spread them to bytes.
+__device__ __forceinline__ void window_cache(const uint32_t* gw, int pr, int pc, uint32_t (&u0)[7], uint32_t (&u1)[7]) {
     const uint32_t cv = (COLVALID >> (pc - 3)) & 0x7Fu;           // window column j lies inside the plan area
     const uint64_t one = spread7(cv);                              // 0x01 per valid byte
     const uint32_t b0 = (uint32_t)one, b1 = (uint32_t)(one >> 32);
     const uint32_t m0 = b0 * 0xFFu, m1 = b1 * 0xFFu;               // 0xFF per valid byte (no carries)
-    const int o0 = (pr - 6) * 20 + (pc - 6);                       // byte offset of window cell (0,0): -63 .. 336
-    const uint32_t* rw = reinterpret_cast<const uint32_t*>(gb + (o0 & ~3));
-    const int shb = (o0 & 3) * 8;                                  // the same for every row: 20 B = 5 words apart
+    const int o0 = (pr - 6) * 20 + (pc - 6);                       // nibble offset of window cell (0,0): -63 .. 336
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
         const bool rowvalid = (unsigned)(pr - 6 + k) < 20u;        // interior row of window row k
-        const uint32_t x0 = rw[5 * k], x1 = rw[5 * k + 1], x2 = rw[5 * k + 2];
-        const uint32_t q0 = __funnelshift_r(x0, x1, shb), q1 = __funnelshift_r(x1, x2, shb);
+        const int ok = o0 + 20 * k;
+        const uint32_t* rw = gw + (ok >> 3);
+        const uint32_t q = __funnelshift_r(rw[0], rw[1], (ok & 7) * 4);
+        uint32_t q0, q1;
+        nib8_to_bytes(q, q0, q1);
         u0[k] = rowvalid ? ((q0 & m0) + b0) : 0u;                  // biased bytes: height + 1, 0 = frame
         u1[k] = rowvalid ? ((q1 & m1) + b1) : 0u;
     }
 }
 template <typename ObsT>
-__device__ __forceinline__ void observe_cache(const uint8_t* gb, int pr, int pc, ObsT* row) {
+__device__ __forceinline__ void observe_cache(const uint32_t* gw, const uint16_t* ge, bool tall, int pr, int pc, ObsT* row) {
     uint32_t u0[7], u1[7];
-    window_cache(gb, pr, pc, u0, u1);
+    window_cache(gw, pr, pc, u0, u1);
+    const bool fix = tall && window_saturated(u0, u1);            // a cell of 15 or more in a tall env's window
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
         ObsT* o7 = row + k * 7;
@@ -102,9 +78,10 @@ __device__ __forceinline__ void observe_cache(const uint8_t* gb, int pr, int pc,
         o7[5] = obs_from_biased<ObsT, 1>(u1[k]);
         o7[6] = obs_from_biased<ObsT, 2>(u1[k]);
     }
+    if (fix) fix_saturated_row<ObsT>(ge, pr, pc, u0, u1, row);    // exact heights from the wide map
 }
 
-// shared memory: [WPB][WARP_MAP_B] byte maps | [WPB][32*51] ObsT tiles
+// shared memory: [WPB][WARP_MAP_B] nibble maps | [WPB][32*51] ObsT tiles
 template <typename ObsT>
 __host__ __device__ constexpr size_t warp_smem_bytes() { return (size_t)WARP_MAP_B + 32 * row_elems<ObsT, D3_OBS>() * sizeof(ObsT); }
 
@@ -125,13 +102,13 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
     uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw);
     uint8_t* wmap = base + (size_t)warp * WARP_MAP_B + FRONT;
     ObsT* tile = reinterpret_cast<ObsT*>(base + (size_t)wpb * WARP_MAP_B) + warp * (32 * ROW);
-    uint8_t* gb = wmap + lane * MAP_B;                                // this lane's byte map
+    uint32_t* gw = reinterpret_cast<uint32_t*>(wmap + lane * MAP_B);  // this lane's nibble map (51 words)
 
     uint16_t* cells = reinterpret_cast<uint16_t*>(st.cells);
     uint16_t* gwarp = cells + env0 * CELLS3D;                         // the warp's 32 WIDE maps in HBM (tall envs only)
     uint16_t* ge = cells + env * CELLS3D;                             // this lane's wide map in HBM
-    uint8_t* bwarp = bmap3(st) + env0 * CELLS3D;                      // the warp's 32 byte maps in HBM (contiguous)
-    uint8_t* be = bmap3(st) + env * CELLS3D;
+    uint8_t* nwarp = nmap3(st) + env0 * NIB3_STRIDE;                  // the warp's 32 nibble maps in HBM (contiguous)
+    uint8_t* ne = nmap3(st) + env * NIB3_STRIDE;
     uint4* aux = reinterpret_cast<uint4*>(st.aux);
     const uint8_t* __restrict__ plans = reinterpret_cast<const uint8_t*>(st.plans);
     const bool autoreset = io.flags & DMP_F_AUTORESET;
@@ -144,11 +121,12 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
     bool tall = false;
     double acc_iou = 0.0;                                             // this env's sum of episode IoUs (sequential, exact)
     {
-        // the warp's 32 byte maps are one contiguous 12 800 B span of the byte shadow: 25 coalesced 128-bit loads per
-        // lane, all in flight at once (ONE DRAM round trip per launch), four 32-bit shared stores per vector
-        const uint4* src = reinterpret_cast<const uint4*>(bwarp);
-        const int nvec = nvalid * (CELLS3D / 16);                     // 25 vectors of 16 cells per env
-        constexpr int U = CELLS3D / 16;
+        // the warp's 32 nibble maps are one contiguous 6 656 B span: 13 coalesced 128-bit loads per lane, all in flight at
+        // once (ONE DRAM round trip per launch); env el's 13 vectors land in its 51-word slot (the last one carries the
+        // 8 pad bytes of the 208 B record: only three of its words are stored)
+        const uint4* src = reinterpret_cast<const uint4*>(nwarp);
+        constexpr int U = NIB3_STRIDE / 16;                           // 13 vectors per env
+        const int nvec = nvalid * U;
         uint4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -169,7 +147,8 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
             const int idx = u * 32 + lane;
             const int el = idx / U, j = idx - el * U;
             uint32_t* dst = reinterpret_cast<uint32_t*>(wmap + el * MAP_B + j * 16);
-            dst[0] = v[u].x; dst[1] = v[u].y; dst[2] = v[u].z; dst[3] = v[u].w;   // lanes beyond nvec write zeros into their own slots
+            dst[0] = v[u].x; dst[1] = v[u].y; dst[2] = v[u].z;       // lanes beyond nvec write zeros into their own slots
+            if (j < U - 1) dst[3] = v[u].w;                           // (word 51 would be the next env's first word)
         }
     }
     int total_brick = __ldg(st.plan_total + e.plan_idx);
@@ -204,28 +183,23 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
         const int dir = a & 3, dr = dir_dr(dir), dc = dir_dc(dir);
         const int o = (e.pr - 3) * 20 + (e.pc - 3);
         int c6[6];
-        if (!tall) {
+        {
             const int dstep = dr * 20 + dc, sgn = dr + dc;
             const int coord = (dir < 2 ? e.pc : e.pr) - 3;
-            const int vl = gb[o - 1], vr = gb[o + 1], vu = gb[o + 20], vd = gb[o - 20];
-            const int v2 = gb[o + 2 * dstep], v3 = gb[o + 3 * dstep];
+            const int vl = nib_at(gw, o - 1), vr = nib_at(gw, o + 1), vu = nib_at(gw, o + 20), vd = nib_at(gw, o - 20);
+            const int v2 = nib_at(gw, o + 2 * dstep), v3 = nib_at(gw, o + 3 * dstep);
             c6[0] = (e.pc > D2_LO) ? vl : -1;
             c6[1] = (e.pc < D2_HI) ? vr : -1;
             c6[2] = (e.pr < D2_HI) ? vu : -1;
             c6[3] = (e.pr > D2_LO) ? vd : -1;
             c6[4] = ((unsigned)(coord + 2 * sgn) < 20u) ? v2 : -1;
             c6[5] = ((unsigned)(coord + 3 * sgn) < 20u) ? v3 : -1;
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) c6[q] = cell_tall(ge, e.pr + dir_dr(q), e.pc + dir_dc(q));
-            c6[4] = cell_tall(ge, e.pr + 2 * dr, e.pc + 2 * dc);
-            c6[5] = cell_tall(ge, e.pr + 3 * dr, e.pc + 3 * dc);
         }
         const bool boxed = (c6[0] != 0) && (c6[1] != 0) && (c6[2] != 0) && (c6[3] != 0);     // check_sur
-        const int nsel = (dir == 0) ? c6[0] : (dir == 1) ? c6[1] : (dir == 2) ? c6[2] : c6[3];
+        int nsel = (dir == 0) ? c6[0] : (dir == 1) ? c6[1] : (dir == 2) ? c6[2] : c6[3];
 
         bool done = false, tail = true;
-        bool built = false, boxed_penalty = false;
+        bool built = false, boxed_penalty = false, turns_tall = false;
         int newh = 0, pplan = 0;
         if (a <= 3) {
             // (a) move_step (:104-134): consecutive empty cells, at most s
@@ -237,20 +211,23 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
             // (b) build on neighbour a-4 unless it is frame
             bool open_after = (c6[0] == 0) || (c6[1] == 0) || (c6[2] == 0) || (c6[3] == 0);   // some neighbour still empty
             if (a <= 7 && nsel != -1) {
+                const int ti = o + dr * 20 + dc;
+                if (nsel == 15) nsel = (int)__ldcg(ge + ti);                   // saturated nibble (tall envs only): true height
                 built = true;
                 newh = nsel + 1;
-                const int ti = o + dr * 20 + dc;
                 e.cb += 1;
                 pplan = ldg_u8(plans + e.plan_idx * CELLS3D + ti);             // consumed after the observation
-                if (!tall) gb[ti] = (uint8_t)newh;
+                uint32_t* wp = gw + (ti >> 3);
+                const int sh = (ti & 7) * 4;
+                const uint32_t x = (*wp & ~(0xFu << sh)) | ((uint32_t)sat_nib(newh) << sh);
+                *wp = x;                                                       // the cache stays current for tall envs too
                 if (live) {
-                    be[ti] = sat_u8(newh);                                     // write-through to the byte map
+                    ne[ti >> 1] = (uint8_t)(x >> (((ti >> 1) & 3) * 8));         // write-through: the byte holding the nibble
                     if (tall) {
                         ge[ti] = (uint16_t)newh;                               // a tall env keeps its wide map exact
-                    } else if (newh >= TALL3) {                                // the bytes stop being exact: the env turns
-                        widen_from_cache(ge, gb);                              // tall, its wide map is made current
-                        tall = true;
-                    }
+                    } else if (newh >= TALL3) {                                // the nibbles stop being exact after this brick:
+                        turns_tall = tall = true;                              // the env turns tall, its wide map is made
+                    }                                                          // current below (by the warp)
                 }
                 // neighbours after placement: only neighbour `dir` changed, and it is now > 0
                 open_after = ((dir != 0) && c6[0] == 0) || ((dir != 1) && c6[1] == 0) ||
@@ -266,6 +243,15 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
             }
         }
         if (tail) done = (e.cs >= st.total_step) || (!dynamic && boxed);
+        if (__any_sync(FULL, turns_tall)) {                 // wide map := the (still exact) nibble cache, 16 cells per lane
+            __syncwarp();
+            for (unsigned tw = __ballot_sync(FULL, turns_tall); tw; tw &= tw - 1) {
+                const int src = __ffs(tw) - 1;
+                const uint32_t* cw = reinterpret_cast<const uint32_t*>(wmap + src * MAP_B);
+                if (lane < 25) warp_widen_words(gwarp + src * CELLS3D, cw[2 * lane], cw[2 * lane + 1], lane);
+            }
+            __syncwarp();
+        }
 
         // ---- (c) observation; (d) reward (reward_check :232-239) -------------------------------------------
         // The plan byte requested at build time is consumed only after the window has been formatted, which hides its
@@ -283,21 +269,17 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
             ObsT* row = tile + lane * ROW;
             if constexpr (REC) {
                 uint64_t c[7];
-                if (!tall) {
-                    uint32_t u0[7], u1[7];
-                    window_cache(gb, e.pr, e.pc, u0, u1);
+                uint32_t u0[7], u1[7];
+                window_cache(gw, e.pr, e.pc, u0, u1);
 #pragma unroll
-                    for (int k = 0; k < 7; ++k) c[k] = (uint64_t)u0[k] | ((uint64_t)u1[k] << 32);
-                } else {
-                    window_tall_bytes(ge, e.pr, e.pc, c);
-                }
+                for (int k = 0; k < 7; ++k) c[k] = (uint64_t)u0[k] | ((uint64_t)u1[k] << 32);
+                if (tall && window_saturated(u0, u1)) fix_saturated_codes(ge, e.pr, e.pc, c);
                 uint32_t w[13];
                 pack49(c, w);
                 reward_now();
                 rec56_store(row, w, e.cb, e.cs, reward, done, tall);
             } else {
-                if (!tall) observe_cache<ObsT>(gb, e.pr, e.pc, row);
-                else observe_tall<ObsT>(ge, e.pr, e.pc, row);
+                observe_cache<ObsT>(gw, ge, tall, e.pr, e.pc, row);
                 obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, st.total_step, row[49], row[50]);
             }
             ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * ROW;
@@ -347,15 +329,13 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
             const int src = __ffs(dm) - 1;
             dm &= dm - 1;
             uint32_t* sg = reinterpret_cast<uint32_t*>(wmap + src * MAP_B) + lane;
-            sg[0] = 0u; sg[32] = 0u; sg[64] = 0u;
-            if (lane < 4) sg[96] = 0u;
-            if (lane < 25) {
-                const uint4 z = make_uint4(0, 0, 0, 0);
-                reinterpret_cast<uint4*>(bwarp + src * CELLS3D)[lane] = z;
-                if ((dmw >> src) & 1u) {
-                    uint4* gg = reinterpret_cast<uint4*>(gwarp + src * CELLS3D) + 2 * lane;
-                    gg[0] = z; gg[1] = z;
-                }
+            sg[0] = 0u;
+            if (lane < MAP_W - 32) sg[32] = 0u;
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            if (lane < NIB3_STRIDE / 16) reinterpret_cast<uint4*>(nwarp + src * NIB3_STRIDE)[lane] = z;
+            if (lane < 25 && ((dmw >> src) & 1u)) {
+                uint4* gg = reinterpret_cast<uint4*>(gwarp + src * CELLS3D) + 2 * lane;
+                gg[0] = z; gg[1] = z;
             }
         }
         __syncwarp();
@@ -381,7 +361,7 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
 
 // Launch shape.  Every warp is an independent tile of 32 envs, so blocks are single warps: the block scheduler then refills
 // an SM warp by warp instead of waiting for the slowest warp of a big block (three-warp blocks: 16.6 vs 19.3 G env-steps/s).
-// Shared memory alone limits residency (11 warps per SM for f32 observations).
+// Shared memory limits residency to 16 warps per SM for f32 observations (6.6 KB of maps + 6.5 KB of tile per warp).
 template <typename ObsT, bool TMA>
 int launch_cache_t(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
     constexpr int wpb = 1;

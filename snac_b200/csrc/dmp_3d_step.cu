@@ -1,58 +1,35 @@
 // dmp_3d_step.cu -- 3D envs, single-step kernel (K = 1, dmp_step): the rows a step looks at are
-// staged from the BYTE maps (include/dmp.h: u8[n][400] behind the wide u16 maps, byte = min(h, 255)).
+// staged from the NIBBLE maps (include/dmp.h: u8[n][208] behind the wide u16 maps, nibble = min(h, 15)).
 //
-// A step touches bytes only.  (An earlier generation staged u16 rows and wrote every brick into a u16 map: 0.55 of the HBM
-// roofline -- a 2-byte store into a line that is not in L2 costs a 32 B read and a 32 B write of DRAM traffic, and clearing
-// an 800 B map per episode added 35 B per env-step.)  <= 224 B of byte rows per env land in a 240 B slot (15 granules of
-// 16 B: an odd count spreads same-offset words of the 32 lanes over 8 bank groups), 7.7 KB per warp, 28 resident warps
-// per SM; the window is cut out with 3 word reads + 2 funnel shifts per row; the brick goes to the byte map, whose line the
-// step has just read.  The action and the step size are known before anything is loaded, so ONE bulk async copy per env
-// (cp.async.bulk -> UBLKCP, completion on the warp's mbarrier) right after the scalar state fetches the 7 rows under the
-// old window plus `step_size` more rows in the direction of a vertical move; the six decision cells, the window at the new
-// position and the brick patch are served from that span; every lane pulls its window into registers, then the warp's
-// [32][51] observation tile is built over the drained slots and leaves through one bulk async copy.
-// Exactness (dmp_common.cuh): the bytes of an env ARE its heights until one reaches 254; from then on the env is
-// flagged tall, its wide u16 map is kept exact as well, a build on a saturated byte reads the true height there and the
-// observation row comes from there (out of line, practically never: plan height is 6).  Bricks of all other envs are
-// written through to the byte map only -- a 2-byte store into a cold u16 line costs 64 B of DRAM traffic.
+// A step is bound by what it must fetch from DRAM, and DRAM is read in 64 B pieces.  The 7..10 map rows under the window
+// were 140..200 B of byte rows in the previous generation (256 B of DRAM reads per env-step, 0.58 of the HBM roofline);
+// they are 70..100 B of nibble rows now (<= 128 B staged, ~160 B read).  (The generation before staged u16 rows and
+// wrote every brick into a u16 map: 0.55 -- a 2-byte store into a line that is not in L2 costs a 32 B read and a 32 B
+// write of DRAM traffic.)  <= 128 B of nibble rows per env land in a 144 B slot (9 granules of 16 B: an odd count spreads
+// same-offset words of the 32 lanes over 8 bank groups); the window is cut out with 2 word reads + 1 funnel shift per row
+// and spread to bytes with 2 LOP + 2 PRMT; the brick goes to the nibble map, whose line the step has just read.  The
+// action and the step size are known before anything is loaded, so ONE bulk async copy per env (cp.async.bulk -> UBLKCP,
+// completion on the warp's mbarrier) right after the scalar state fetches the 7 rows under the old window plus
+// `step_size` more rows in the direction of a vertical move; the six decision cells, the window at the new position and
+// the brick patch are served from that span; every lane pulls its window into registers, then the warp's [32][51]
+// observation tile is built over the drained slots and leaves through one bulk async copy.
+// Exactness (dmp_common.cuh): the nibbles of an env ARE its heights until one reaches 15; from then on the env is
+// flagged tall and its wide u16 map is kept exact as well: a build on a saturated nibble reads the true height there, and
+// so do the window cells that read 15 (out of line; plan height is 6, but among 262 144 random-policy envs a handful
+// are tall at any time, so the tall path must not be slow: everything else still comes from the nibbles).
 // Semantics: Env/3D/DMP_simulator_3d_static_circle.py:67-276 and
-// Env/3D/DMP_simulator_3d_dynamic_triangle_usedata.py:45-277 (see dmp_3d.cu for the line-by-line citations).
+// Env/3D/DMP_simulator_3d_dynamic_triangle_usedata.py:45-277 (see dmp_3d_roll.cu for the line-by-line citations).
 #include "dmp_3d_bulk.cuh"
 
 namespace {
 
 using namespace d3;
 
-constexpr int SLOT3_B = 240;                 // per-lane staging: 16 B guard | <= 224 B of byte rows.  Word reads of the window
-                                             // run up to 8 B past the rows: into the next lane's guard (masked columns)
+constexpr int SLOT3_B = 144;                 // per-lane staging: 16 B guard | <= 128 B of nibble rows.  Word reads of the window
+                                             // run up to 6 B past the rows: into the next lane's guard (masked columns)
 
-// an env turns tall: its wide map := its (still exact) byte map, with the brick just laid.  Out of line, practically never.
-__device__ __noinline__ void widen_env(uint16_t* ge, const uint8_t* be, int ti, int newh) {
-    for (int i = 0; i < CELLS3D; ++i) ge[i] = (i == ti) ? (uint16_t)newh : (uint16_t)__ldcg(be + i);
-}
-
-// a tall env's observation row straight from its wide map
-template <typename ObsT>
-__device__ __noinline__ void observe_u16(const uint16_t* ge, int pr, int pc, ObsT* row) {
-    for (int k = 0; k < 7; ++k)
-        for (int j = 0; j < 7; ++j) {
-            const unsigned ir = (unsigned)(pr - 6 + k), ic = (unsigned)(pc - 6 + j);
-            row[k * 7 + j] = obs_from_int<ObsT>((ir < 20u && ic < 20u) ? (int)__ldcg(ge + ir * 20u + ic) : -1);
-        }
-}
-
-// the same as record bytes (value + 1, saturating at 255; the record carries DMP_REC_SATURATED)
-__device__ __noinline__ void window_u16_bytes(const uint16_t* ge, int pr, int pc, uint64_t (&c)[7]) {
-    for (int k = 0; k < 7; ++k) {
-        uint64_t v = 0;
-        for (int j = 0; j < 7; ++j) {
-            const unsigned ir = (unsigned)(pr - 6 + k), ic = (unsigned)(pc - 6 + j);
-            const int h = (ir < 20u && ic < 20u) ? (int)__ldcg(ge + ir * 20u + ic) : -1;
-            v |= (uint64_t)min(h + 1, 255) << (8 * j);
-        }
-        c[k] = v;
-    }
-}
+// cell i of a nibble map addressed through its (virtual) word base
+__device__ __forceinline__ int nib_at(const uint32_t* gw, int i) { return (int)((gw[i >> 3] >> ((i & 7) * 4)) & 0xFu); }
 
 // per-warp shared memory: 32 slots, or the observation tile built over them when that is larger (f64)
 template <typename ObsT>
@@ -84,8 +61,8 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
     uint16_t* cells = reinterpret_cast<uint16_t*>(st.cells);
     uint16_t* gwarp = cells + env0 * CELLS3D;
     uint16_t* ge = cells + env * CELLS3D;                             // this lane's u16 map in HBM (canonical)
-    uint8_t* bwarp = bmap3(st) + env0 * CELLS3D;
-    uint8_t* be = bmap3(st) + env * CELLS3D;                          // ... and its byte shadow
+    uint8_t* nwarp = nmap3(st) + env0 * NIB3_STRIDE;
+    uint8_t* ne = nmap3(st) + env * NIB3_STRIDE;                      // ... and its nibble map
     uint4* aux = reinterpret_cast<uint4*>(st.aux);
     const uint8_t* __restrict__ plans = reinterpret_cast<const uint8_t*>(st.plans);
 
@@ -123,15 +100,15 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
     e.ret = __uint_as_float(ax.z);
     e.cross = (int)ax.w;
 
-    // ---- round trip 2: every map row this step can look at, one bulk copy of byte rows per env ----------------
+    // ---- round trip 2: every map row this step can look at, one bulk copy of nibble rows (10 B each) per env ------
     const int ext = min(max(s, 1), 3);                     // a move covers at most min(s, 3) cells (move_step :104-134)
     const int row_lo = max(e.pr - 6 - (a == 3 ? ext : 0), 0);
     const int row_hi = min(e.pr + (a == 2 ? ext : 0), 19);
-    const int b_lo = (row_lo * 20) & ~15, b_hi = ((row_hi + 1) * 20 + 15) & ~15;      // 16 B granules, <= 224 B
+    const int b_lo = (row_lo * 10) & ~15, b_hi = ((row_hi + 1) * 10 + 15) & ~15;      // 16 B granules, <= 128 B, <= 208
     __syncwarp();                                                                       // mbarrier init visible
     if (live) {
         mbar_arrive_expect_tx(bar, (uint32_t)(b_hi - b_lo));
-        bulk_g2s(slot + 16, be + b_lo, (uint32_t)(b_hi - b_lo), bar);
+        bulk_g2s(slot + 16, ne + b_lo, (uint32_t)(b_hi - b_lo), bar);
     } else {
         mbar_arrive(bar);
     }
@@ -140,19 +117,19 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
     const int ti = min(max(o + dr * 20 + dc, 0), CELLS3D - 1);        // build target (valid whenever a brick is laid)
     int pplan = 0;
     if (a >= 4) pplan = __ldg(plans + e.plan_idx * CELLS3D + ti);     // consumed after the observation
-    // virtual map base: cell (r, c) of the staged rows lives at g[r * 20 + c]; 16 B aligned like the slot
-    uint8_t* g = slot + 16 - b_lo;
+    // virtual map base: cell i of the staged rows is nibble i & 7 of g[i >> 3]; 16 B aligned like the slot
+    uint32_t* g = reinterpret_cast<uint32_t*>(slot + 16 - b_lo);
     mbar_wait(bar, 0);
 
     // ---- the six cells the decision reads: four neighbours (check_sur :88-102), second and third cell in the
     // action's direction (move_step).  Unconditional reads at an index clamped into the staged span; whether a cell
-    // is frame follows from one coordinate.  The decision only asks "== 0 / > 0 / frame": saturated bytes answer it.
+    // is frame follows from one coordinate.  The decision only asks "== 0 / > 0 / frame": saturated nibbles answer it.
     int c6[6];
     {
         const int lo_cell = row_lo * 20, hi_cell = row_hi * 20 + 19;
         const int dstep = dr * 20 + dc, sgn = dr + dc;
         const int coord = (dir < 2 ? e.pc : e.pr) - 3;
-        auto at = [&](int i) { return (int)g[min(max(i, lo_cell), hi_cell)]; };
+        auto at = [&](int i) { return nib_at(g, min(max(i, lo_cell), hi_cell)); };
         const int vl = at(o - 1), vr = at(o + 1), vu = at(o + 20), vd = at(o - 20);
         const int v2 = at(o + 2 * dstep), v3 = at(o + 3 * dstep);
         c6[0] = (e.pc > D2_LO) ? vl : -1;
@@ -178,7 +155,7 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
         // (b) build on neighbour a-4 unless it is frame
         bool open_after = (c6[0] == 0) || (c6[1] == 0) || (c6[2] == 0) || (c6[3] == 0);
         if (a <= 7 && nsel != -1) {
-            if (nsel == 255) nsel = (int)__ldcg(ge + ti);             // saturated byte (tall envs only): the true height
+            if (nsel == 15) nsel = (int)__ldcg(ge + ti);              // saturated nibble (tall envs only): the true height
             built = true;
             newh = nsel + 1;
             e.cb += 1;
@@ -195,17 +172,36 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
         }
     }
     if (tail) done = (e.cs >= st.total_step) || (!dynamic && boxed);
+    bool turns_tall = false;
+    uint32_t brick_byte = 0;                             // the nibble-map byte that holds the new brick
     if (built) {
-        g[ti] = sat_u8(newh);                            // patch the staged rows ...
+        uint32_t* wp = g + (ti >> 3);                    // patch the staged rows ...
+        const int sh = (ti & 7) * 4;
+        const uint32_t x = (*wp & ~(0xFu << sh)) | ((uint32_t)sat_nib(newh) << sh);
+        *wp = x;
+        brick_byte = (x >> (((ti >> 1) & 3) * 8)) & 0xFFu;
         if (live) {
-            be[ti] = sat_u8(newh);                       // ... and write the brick through to the byte map
+            ne[ti >> 1] = (uint8_t)brick_byte;           // ... and write the brick's byte through to the nibble map
             if (tall) {
                 ge[ti] = (uint16_t)newh;                 // a tall env keeps its wide map exact
-            } else if (newh >= TALL3) {                  // the bytes stop being exact: the env turns tall and its
-                widen_env(ge, be, ti, newh);             // wide map is made current
-                tall = true;
+            } else if (newh >= TALL3) {                  // the nibbles stop being exact after this brick: the env turns
+                turns_tall = tall = true;                // tall and its wide map is made current (below, by the warp)
             }
         }
+    }
+    for (unsigned tw = __ballot_sync(FULL, turns_tall); tw; tw &= tw - 1) {
+        const int src = __ffs(tw) - 1;
+        const int tib = __shfl_sync(FULL, ti >> 1, src);
+        const uint32_t nb = __shfl_sync(FULL, brick_byte, src);
+        if (lane < 25) {                                 // 16 cells per lane; the new brick's byte may not have landed yet
+            uint2 v = __ldcg(reinterpret_cast<const uint2*>(nwarp + src * NIB3_STRIDE) + lane);
+            if ((tib >> 3) == lane) {
+                const int bs = (tib & 3) * 8;
+                if (tib & 4) v.y = (v.y & ~(0xFFu << bs)) | (nb << bs); else v.x = (v.x & ~(0xFFu << bs)) | (nb << bs);
+            }
+            warp_widen_words(gwarp + src * CELLS3D, v.x, v.y, lane);
+        }
+        __syncwarp();                                    // the wide map is visible to its env's lane
     }
 
     // ---- (d) reward (reward_check :232-239): the plan byte is consumed after the window has been formatted; a record
@@ -230,49 +226,45 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
             const uint32_t b0 = (uint32_t)one, b1 = (uint32_t)(one >> 32);
             const uint32_t m0 = b0 * 0xFFu, m1 = b1 * 0xFFu;           // 0xFF per valid byte (no carries)
             const int c0 = e.pc - 6;                                    // interior column of window column 0 (may be < 0)
-            const int shb = (c0 & 3) * 8;                               // the same for every row: rows are 5 words apart
 #pragma unroll
             for (int k = 0; k < 7; ++k) {
                 const int ir = e.pr - 6 + k;                            // interior row of window row k
                 const bool rowvalid = (unsigned)ir < 20u;
                 const int irc = min(max(ir, row_lo), row_hi);           // rows outside the map re-read a staged row, masked
-                const uint32_t* rw = reinterpret_cast<const uint32_t*>(g + ((irc * 20 + c0) & ~3));
-                const uint32_t x0 = rw[0], x1 = rw[1], x2 = rw[2];     // over-reads stay inside the 16 B guards
-                const uint32_t q0 = __funnelshift_r(x0, x1, shb) & m0, q1 = __funnelshift_r(x1, x2, shb) & m1;
-                u0[k] = rowvalid ? (q0 + b0) : 0u;
-                u1[k] = rowvalid ? (q1 + b1) : 0u;
+                const int ok = irc * 20 + c0;                           // nibble offset of the row's first window cell
+                const uint32_t* rw = g + (ok >> 3);                     // over-reads stay inside the 16 B guards
+                const uint32_t q = __funnelshift_r(rw[0], rw[1], (ok & 7) * 4);
+                uint32_t q0, q1;
+                nib8_to_bytes(q, q0, q1);                               // seven nibbles -> seven bytes (the eighth is masked)
+                u0[k] = rowvalid ? ((q0 & m0) + b0) : 0u;
+                u1[k] = rowvalid ? ((q1 & m1) + b1) : 0u;
             }
         }
         __syncwarp();                                    // every lane has read its slot
         ObsT* row = tile + lane * ROW;
+        const bool fix = tall && window_saturated(u0, u1);      // a cell of 15 or more in a tall env's window: practically never
         if constexpr (REC) {                             // one packed record per env; it carries reward and done
             uint64_t c[7];
-            if (!tall) {
 #pragma unroll
-                for (int k = 0; k < 7; ++k) c[k] = (uint64_t)u0[k] | ((uint64_t)u1[k] << 32);
-            } else {
-                window_u16_bytes(ge, e.pr, e.pc, c);     // tall env: the wide map, this step's brick included
-            }
+            for (int k = 0; k < 7; ++k) c[k] = (uint64_t)u0[k] | ((uint64_t)u1[k] << 32);
+            if (fix) fix_saturated_codes(ge, e.pr, e.pc, c);     // exact heights from the wide map, this step's brick included
             uint32_t w[13];
             pack49(c, w);
             reward_now();
             rec56_store(row, w, e.cb, e.cs, reward, done, tall);
         } else {
-            if (!tall) {
 #pragma unroll
-                for (int k = 0; k < 7; ++k) {
-                    ObsT* o7 = row + k * 7;
-                    o7[0] = obs_from_biased<ObsT, 0>(u0[k]);
-                    o7[1] = obs_from_biased<ObsT, 1>(u0[k]);
-                    o7[2] = obs_from_biased<ObsT, 2>(u0[k]);
-                    o7[3] = obs_from_biased<ObsT, 3>(u0[k]);
-                    o7[4] = obs_from_biased<ObsT, 0>(u1[k]);
-                    o7[5] = obs_from_biased<ObsT, 1>(u1[k]);
-                    o7[6] = obs_from_biased<ObsT, 2>(u1[k]);
-                }
-            } else {
-                observe_u16<ObsT>(ge, e.pr, e.pc, row);  // tall env: the wide map, this step's brick included
+            for (int k = 0; k < 7; ++k) {
+                ObsT* o7 = row + k * 7;
+                o7[0] = obs_from_biased<ObsT, 0>(u0[k]);
+                o7[1] = obs_from_biased<ObsT, 1>(u0[k]);
+                o7[2] = obs_from_biased<ObsT, 2>(u0[k]);
+                o7[3] = obs_from_biased<ObsT, 3>(u0[k]);
+                o7[4] = obs_from_biased<ObsT, 0>(u1[k]);
+                o7[5] = obs_from_biased<ObsT, 1>(u1[k]);
+                o7[6] = obs_from_biased<ObsT, 2>(u1[k]);
             }
+            if (fix) fix_saturated_row<ObsT>(ge, e.pr, e.pc, u0, u1, row);      // exact heights from the wide map
             obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, st.total_step, row[49], row[50]);
         }
         ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + env0 * ROW;
@@ -319,13 +311,11 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
     while (dm) {                                            // the warp clears each finished env's map in HBM
         const int src = __ffs(dm) - 1;
         dm &= dm - 1;
-        if (lane < 25) {
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            reinterpret_cast<uint4*>(bwarp + src * CELLS3D)[lane] = z;
-            if ((dmw >> src) & 1u) {
-                uint4* gg = reinterpret_cast<uint4*>(gwarp + src * CELLS3D) + 2 * lane;
-                gg[0] = z; gg[1] = z;
-            }
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        if (lane < NIB3_STRIDE / 16) reinterpret_cast<uint4*>(nwarp + src * NIB3_STRIDE)[lane] = z;
+        if (lane < 25 && ((dmw >> src) & 1u)) {
+            uint4* gg = reinterpret_cast<uint4*>(gwarp + src * CELLS3D) + 2 * lane;
+            gg[0] = z; gg[1] = z;
         }
     }
     if (live) {
@@ -341,8 +331,7 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
     if (bulk_pending) warp_tile_bulk_wait(lane);                        // the tile must outlive the copy that reads it
 }
 
-// Launch shape: two-warp blocks of 240 B slots fit 14 blocks = 28 warps per SM (the driver reserves 1 KB per block, so
-// single-warp blocks stop at 27): 8 192 warps (BASELINE's 262 144 envs) are 1.98 waves.  Measured 12.2 G env-steps/s
+// Launch shape: two-warp blocks, 28 warps per SM by registers (72): 8 192 warps (BASELINE's 262 144 envs) are 1.98 waves.  Measured 12.2 G env-steps/s
 // against 12.0 G with single-warp blocks.  (Per-lane cp.async copies of the rows instead of the per-lane bulk copy:
 // 10.9 G, MIO-throttled -- removed.)
 template <typename ObsT>

@@ -227,7 +227,7 @@ int dmp_layout(int dim, int64_t n, DmpLayout* out) {
             *out = DmpLayout{64 * n, 0, PLAN2D_WORDS * 4, D2_OBS, D2_ACT, 26, 26, 600, 600, (int32_t)sizeof(Rec56), 0};
             return DMP_OK;
         case 3:
-            *out = DmpLayout{(800 + 400) * n, 16 * n, CELLS3D, D3_OBS, D3_ACT, 26, 26, 1300, 1000,    // u16 maps + byte maps
+            *out = DmpLayout{(800 + NIB3_STRIDE) * n, 16 * n, CELLS3D, D3_OBS, D3_ACT, 26, 26, 1300, 1000,    // u16 maps + nibble maps
                              (int32_t)sizeof(Rec56), 0};
             return DMP_OK;
     }

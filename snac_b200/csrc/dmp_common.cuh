@@ -315,22 +315,40 @@ inline cudaError_t dmp_launch_pdl(bool pdl, void (*kern)(KArgs...), unsigned blo
 
 int dmp_set_error(cudaError_t e);   // records e, returns DMP_OK / DMP_ECUDA
 
-// 3D height maps (include/dmp.h): the BYTE maps u8[n][400] behind the u16 area are what the hot kernels
-// (dmp_3d_roll.cu, dmp_3d_step3.cu) read and write.  An env is "tall" once a height reaches TALL3: its flag (bit 7 of the
-// position-row byte of aux.x) is set, its u16 "wide" map holds the exact heights and its bytes saturate at 255; the wide
-// map of every other env is stale scratch that nothing reads.  Not writing it is what the layout is for: a 2-byte store
-// into a line that is not in L2 costs a 32 B read and a 32 B write of DRAM traffic (measured: 3D rollouts 15.0 -> 19.8 G
-// env-steps/s, single steps 8.3 -> 12.2 G, profiles/README.md).
-//   dmp3d_widen(st, clear_flags) : wide map := bytes for every env that is not tall; optionally drops all flags
-//   dmp3d_sync_bytes(st)         : bytes := min(wide, 255) and flag := any(wide >= TALL3), for every env
+// 3D height maps (include/dmp.h): the NIBBLE maps u8[n][208] behind the u16 area are what the hot kernels
+// (dmp_3d_roll.cu, dmp_3d_step.cu) read and write: cell i of an env is nibble i (byte i >> 1, low nibble first) =
+// min(height, 15); bytes 200..207 pad the env to 13 granules of 16 B (bulk copies need 16 B alignment).  An env is "tall"
+// once a height reaches TALL3 = 15: its flag (bit 7 of the position-row byte of aux.x) is set, its u16 "wide" map holds
+// the exact heights and its nibbles saturate at 15; the wide map of every other env is stale scratch that nothing reads.
+// Why nibbles: every reachable state of the reference's plans is tiny (plan height 6), and a single step has to fetch the
+// 7..10 map rows under its window from DRAM, which is read in 64 B pieces -- 20 B byte rows cost 256 B per env-step for
+// 49 useful cells (the single-step kernel's bound), 10 B nibble rows 160 B; rollouts stage half the bytes per launch and
+// clear half per episode.  Not writing the wide map is the other half of the layout: a 2-byte store into a line that is
+// not in L2 costs a 32 B read and a 32 B write of DRAM traffic (profiles/README.md).
+//   dmp3d_widen(st, clear_flags) : wide map := nibbles for every env that is not tall; optionally drops all flags
+//   dmp3d_sync_bytes(st)         : nibbles := min(wide, 15) and flag := any(wide >= TALL3), for every env
 // The stage kernels and import only know the wide maps: widen(clear) runs before them and sync_bytes after;
 // export / iou read the wide maps after widen(keep).
-constexpr int TALL3 = 254;                   // bytes of a non-tall env are <= 253: the +1 bias of the observation path fits
+constexpr int TALL3 = 15;                    // nibbles of a non-tall env are <= 14: exact heights
+constexpr int NIB3_STRIDE = 208;             // bytes per env in the nibble area (200 used)
 constexpr uint32_t AUX3_TALL = 0x80u;        // aux.x bit 7 (pos_row is 3..22)
-__host__ __device__ inline uint8_t* bmap3(const DmpState& st) {
+__host__ __device__ inline uint8_t* nmap3(const DmpState& st) {
     return reinterpret_cast<uint8_t*>(st.cells) + (size_t)st.n_envs * (CELLS3D * 2);
 }
-__device__ __forceinline__ uint8_t sat_u8(int h) { return (uint8_t)min(h, 255); }
+__device__ __forceinline__ int sat_nib(int h) { return min(h, 15); }
+// eight nibbles (cells 8j .. 8j+7 of a map word) -> two words of four bytes each, cell order kept
+__device__ __forceinline__ void nib8_to_bytes(uint32_t x, uint32_t& b0, uint32_t& b1) {
+    const uint32_t lo = x & 0x0F0F0F0Fu, hi = (x >> 4) & 0x0F0F0F0Fu;    // even / odd cells as bytes
+    b0 = __byte_perm(lo, hi, 0x5140);                                    // cells 0 1 2 3
+    b1 = __byte_perm(lo, hi, 0x7362);                                    // cells 4 5 6 7
+}
+// the byte of a nibble map that holds cell i, rewritten with that cell := v (this thread is the env's only writer)
+__device__ __forceinline__ void nib_store_global(uint8_t* map, int i, int v) {
+    uint8_t* p = map + (i >> 1);
+    const int sh = (i & 1) * 4;
+    const uint32_t b = __ldcg(p);
+    *p = (uint8_t)((b & ~(0xFu << sh)) | ((uint32_t)v << sh));
+}
 int dmp3d_sync_bytes(const DmpState& st, cudaStream_t s);
 int dmp3d_widen(const DmpState& st, bool clear_flags, cudaStream_t s);
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

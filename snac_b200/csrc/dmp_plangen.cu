@@ -200,10 +200,13 @@ __global__ void k_plans_from_state(const DmpState st, void* plans_out, int32_t* 
             dst[q] = v;
         }
     } else {
-        const uint8_t* map = bmap3(st) + i * CELLS3D;        // the byte maps hold min(height, 255) for every env
+        // heights of an env that is not tall are its nibbles; a tall env's are in its wide map (plan rows are bytes)
+        const bool tall = (reinterpret_cast<const uint4*>(st.aux)[i].x & AUX3_TALL) != 0u;
+        const uint8_t* nib = nmap3(st) + i * NIB3_STRIDE;
+        const uint16_t* wide = reinterpret_cast<const uint16_t*>(st.cells) + i * CELLS3D;
         uint8_t* dst = reinterpret_cast<uint8_t*>(plans_out) + i * CELLS3D;
         for (int c = 0; c < CELLS3D; ++c) {
-            const int h = map[c];
+            const int h = tall ? min((int)wide[c], 255) : ((nib[c >> 1] >> ((c & 1) * 4)) & 0xF);
             total += h;
             dst[c] = (uint8_t)h;
         }

@@ -34,7 +34,7 @@ def test_layout_and_argument_checks_without_gpu():
     assert L.lib.dmp_layout(2, 10, ctypes.byref(lay)) == L.OK
     assert (lay.cells_bytes, lay.aux_bytes, lay.obs_dim, lay.n_actions) == (640, 0, 51, 5)
     assert L.lib.dmp_layout(3, 10, ctypes.byref(lay)) == L.OK
-    assert (lay.cells_bytes, lay.aux_bytes, lay.obs_dim, lay.n_actions) == (12000, 160, 51, 8)      # u16 maps + their byte shadow
+    assert (lay.cells_bytes, lay.aux_bytes, lay.obs_dim, lay.n_actions) == (10080, 160, 51, 8)      # u16 maps + the nibble maps (208 B per env)
     assert (lay.total_step_static, lay.total_step_dynamic) == (1300, 1000)
     assert L.lib.dmp_layout(4, 10, ctypes.byref(lay)) == L.EINVAL
     # argument validation happens before any CUDA call

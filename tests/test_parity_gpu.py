@@ -288,9 +288,9 @@ def test_get_set_state_and_functional_transition():
 
 
 # ------------------------------------------------------------------------------------------------
-# 7. the two 3D kernels (rollout: whole byte maps cached in shared memory; single step: only the rows a step can look at)
-#    and their tuning variants are interchangeable and equal the oracle; the "tall env" path (a height >= 254 somewhere:
-#    the env runs from its wide map in HBM) is exact
+# 7. the two 3D kernels (rollout: whole nibble maps cached in shared memory; single step: only the rows a step can look
+#    at) and their tuning variants are interchangeable and equal the oracle; the "tall env" path (a height >= 15
+#    somewhere: the env runs from its wide map in HBM) is exact
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dynamic", [False, True])
 @pytest.mark.parametrize("K", [1, 37])
@@ -310,7 +310,7 @@ def test_3d_kernels_agree(dynamic, K):
         res = [[x.clone() for x in env.rollout(K)] for _ in range(reps)]
         torch.cuda.synchronize()
         st = env.get_state()
-        # heights as exported, the byte maps behind the wide maps (the wide map of an env that is not tall is scratch),
+        # heights as exported, the nibble maps behind the wide maps (the wide map of an env that is not tall is scratch),
         # scalar state incl. the tall flags
         outs[kind] = (res, torch.cat([env.export_state()["grid"].reshape(-1), st["cells"][n * 800:].to(torch.int32)]),
                       st["aux"].clone(), [x.clone() for x in env.episode_stats()])
@@ -336,8 +336,9 @@ def test_3d_kernels_agree(dynamic, K):
 @pytest.mark.parametrize("kind", ["c", "d1", "c1", "cr", "d1r"])
 @pytest.mark.parametrize("dynamic", [False, True])
 def test_3d_tall_columns_match_oracle(kind, dynamic):
-    """Heights around the byte paths' thresholds and far beyond the byte range (126..129, 252..256, 300, 40000) next to
-    the agent: builds on top of them, walks blocked by them and windows over them must equal the oracle's."""
+    """Heights around the nibble paths' threshold (13..17: an env turns "tall" at 15), around the record bytes' (252..256)
+    and far beyond (300, 40000) next to the agent: builds on top of them -- including the brick that makes an env tall
+    inside a launch --, walks blocked by them and windows over them must equal the oracle's."""
     plans = load_plans(3, "dense", "train") if dynamic else None
     n, K = 70, 48
     rng = np.random.RandomState(11)
@@ -351,7 +352,7 @@ def test_3d_tall_columns_match_oracle(kind, dynamic):
     env.reset(plan_idx=p0)
     ob.reset(p0)
     g, sc = ob.export()
-    tall_values = [126, 127, 128, 129, 252, 253, 254, 255, 256, 300, 40000]
+    tall_values = [12, 13, 13, 14, 14, 14, 15, 16, 17, 127, 252, 253, 254, 255, 256, 300, 40000]
     for i, e in enumerate(ob.envs):
         r, c = int(rng.randint(5, 21)), int(rng.randint(5, 21))
         e.pos = [r, c]
@@ -388,15 +389,19 @@ def test_3d_tall_columns_match_oracle(kind, dynamic):
     st = env.export_state()
     assert np.array_equal(st["grid"].cpu().numpy().reshape(g_ref.shape), g_ref)
     assert np.array_equal(st["scalars"].cpu().numpy()[:, :4], sc_ref[:, :4])
-    # the byte maps behind the wide maps are min(height, 255) whichever kernel wrote them, and exactly the envs holding
-    # a height >= 254 carry the tall flag (bit 7 of aux.x)
+    # the nibble maps behind the wide maps (208 B per env, low nibble = even cell) are min(height, 15) whichever kernel
+    # wrote them, and exactly the envs holding a height >= 15 carry the tall flag (bit 7 of aux.x)
     raw = env.get_state()["cells"].cpu().numpy()
-    shadow = raw[n * 800:].reshape(n, 20, 20)
+    packed = raw[n * 800:].reshape(n, 208)
+    assert not packed[:, 200:].any()
+    shadow = np.stack([packed[:, :200] & 15, packed[:, :200] >> 4], axis=-1).reshape(n, 20, 20)
     interior = g_ref.reshape(n, 26, 26)[:, 3:23, 3:23]
-    assert np.array_equal(shadow, np.minimum(interior, 255).astype(np.uint8))
+    assert np.array_equal(shadow, np.minimum(interior, 15).astype(np.uint8))
     flags = (env.get_state()["aux"].cpu().numpy().view(np.uint32).reshape(n, 4)[:, 0] >> 7) & 1
-    assert np.array_equal(flags.astype(bool), interior.reshape(n, -1).max(axis=1) >= 254)
+    assert np.array_equal(flags.astype(bool), interior.reshape(n, -1).max(axis=1) >= 15)
     assert g_ref.max() > 40000 or g_ref.max() >= 254
+    # some env crossed the threshold INSIDE the run (started at <= 14 everywhere, ended tall)
+    assert ((g.reshape(n, -1).max(axis=1) <= 14) & flags.astype(bool)).any()
     assert np.array_equal(env.iou().cpu().numpy(), ob.iou(), equal_nan=True)
 
 
