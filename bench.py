@@ -609,6 +609,24 @@ class Bench:
             ts.append(self.max_over_ranks(time.perf_counter() - t0))
         return total_envs * Ke / statistics.median(ts)
 
+    def pcie_probe(self, mb=256, reps=4):
+        """Device-to-host copy bandwidth with ALL ranks copying at the same time (pinned host buffers): what the host-buffer
+        numbers are bound by.  Returns GB/s per GPU (slowest rank) and for the whole job."""
+        import torch
+        n = mb << 20
+        d = torch.empty(n, dtype=torch.uint8, device=self.dev)
+        h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        h.copy_(d, non_blocking=True)
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            h.copy_(d, non_blocking=True)
+        torch.cuda.synchronize()
+        t = self.max_over_ranks(time.perf_counter() - t0)
+        per = reps * n / t / 1e9
+        return {"d2h_gbs_per_gpu": per, "d2h_gbs_all_gpus": per * self.world,
+                "what": "%d ranks copy %d x %d MB device -> pinned host at the same time (slowest rank's time)" % (self.world, reps, mb)}
+
     def e2e_suite(self, wl, total_envs, K):
         """The reference-facing calls with HOST buffers: numpy actions in, numpy results out, H2D + D2H inside the timed
         region.  `record` = packed step records (56 B / 16 B per env: one buffer, one D2H copy, the compact host-facing
@@ -719,6 +737,8 @@ class Bench:
 
         e2e = self.e2e_suite(wl, total_envs, K)
 
+        pcie = self.pcie_probe()
+
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s|%d|K=%d" % (wl, n, KL_eff))
@@ -744,6 +764,7 @@ class Bench:
                 "clocks": main["clocks"],
                 "e2e": e2e["record"], "e2e_record_mapped": e2e.get("record_mapped"), "e2e_f32": e2e.get("f32"), "e2e_i16": e2e.get("i16"),
                 "e2e_wrapper": e2e.get("wrapper"), "e2e_wrapper_f32_philox": e2e.get("wrapper_f32_philox"),
+                "pcie": pcie,
                 "gpu_launches": main["launches_per_region"] * main["repeats"],
                 "gpu_launches_per_region": main["launches_per_region"],
                 "roofline": {"bound": "hbm", "achieved": kr["achieved_gbs"], "peak": self.peak, "unit": "GB/s", "frac": kr["frac"],

@@ -3,9 +3,9 @@
 //
 // Why a nibble cache: the step logic only asks "is this cell -1 / 0 / > 0" and the observation wants the raw
 // height, which for every reachable state of the reference's plans is tiny (plan height 6; an env would have
-// to stack 15 bricks on one cell to leave the nibble range).  204 B per env (instead of 816 B of u16, or 404 B of bytes)
+// to stack 15 bricks on one cell to leave the nibble range).  212 B per env (instead of 816 B of u16, or 404 B of bytes)
 // lets 16 warps share an SM instead of 7 (11 with bytes), which is what this latency-bound kernel needs, and an odd word
-// stride (51) makes same-offset accesses of the 32 lanes bank-conflict free.  HBM keeps the same nibbles
+// stride (53) makes same-offset accesses of the 32 lanes bank-conflict free.  HBM keeps the same nibbles
 // (dmp_common.cuh); every brick is written through.
 //   * state in : the warp's 32 nibble maps are one contiguous 6 656 B span (include/dmp.h): 13 coalesced 128-bit
 //                loads per lane in one round trip.  An env whose tall flag is set (a height >= 15 somewhere) keeps its
@@ -26,10 +26,14 @@ namespace {
 
 using namespace d3;
 
-constexpr int MAP_W = 51;                     // words per env in the cache: 400 nibbles = 50 words + 1 pad (odd stride)
-constexpr int MAP_B = MAP_W * 4;              // 204 B
-constexpr int FRONT = 32;                     // guard in front of env 0 of a warp: unclamped reads reach 63 nibbles back
-constexpr int WARP_MAP_B = FRONT + 32 * MAP_B;  // 6 560 (multiple of 16); reads past the end (<= 32 B) land in the tile
+// Cache slot of one env: 1 guard word | 50 words = 400 nibbles | 2 guard words = 53 words (odd stride: same-offset accesses
+// of the 32 lanes hit 32 banks).  Every read of a lane stays inside its own slot -- a window row that starts up to 3 cells
+// before row 0 / ends up to 4 cells behind row 19 reads the guards, rows outside the map re-read the agent's row and are
+// masked, frame cells are not read at all -- so no lane ever reads what another lane writes (racecheck-clean).
+constexpr int MAP_W = 53;
+constexpr int MAP_B = MAP_W * 4;              // 212 B
+constexpr int MAP_G0 = 1;                     // guard words in front of the data
+constexpr int WARP_MAP_B = 32 * MAP_B;        // 6 784 (multiple of 16)
 constexpr size_t SMEM_MAX = 232448;           // 227 KB opt-in limit per block
 
 struct EnvR {
@@ -43,7 +47,7 @@ __device__ __forceinline__ int nib_at(const uint32_t* gw, int i) { return (int)(
 
 // stage (c): 7x7 window of this lane's env (nibble cache) -> seven rows of biased bytes (height + 1, 0 = frame), two
 // words per row.  Row k starts 20 k nibbles after row 0: two word reads and one funnel shift cut its seven nibbles out
-// (rows outside the map land in the guards / the neighbouring env and are masked), 2 LOP + 2 PRMT spread them to bytes.
+// (a valid row reads at most one word before / behind the map: the slot's guards), 2 LOP + 2 PRMT spread them to bytes.
 __device__ __forceinline__ void window_cache(const uint32_t* gw, int pr, int pc, uint32_t (&u0)[7], uint32_t (&u1)[7]) {
     const uint32_t cv = (COLVALID >> (pc - 3)) & 0x7Fu;           // window column j lies inside the plan area
     const uint64_t one = spread7(cv);                              // 0x01 per valid byte
@@ -53,7 +57,7 @@ __device__ __forceinline__ void window_cache(const uint32_t* gw, int pr, int pc,
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
         const bool rowvalid = (unsigned)(pr - 6 + k) < 20u;        // interior row of window row k
-        const int ok = o0 + 20 * k;
+        const int ok = o0 + (rowvalid ? 20 * k : 60);              // a row outside the map re-reads the agent's row (masked)
         const uint32_t* rw = gw + (ok >> 3);
         const uint32_t q = __funnelshift_r(rw[0], rw[1], (ok & 7) * 4);
         uint32_t q0, q1;
@@ -100,9 +104,9 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
     const int64_t env = env0 + (live ? lane : 0);                     // idle lanes shadow env0 but never store
 
     uint8_t* base = reinterpret_cast<uint8_t*>(smem_raw);
-    uint8_t* wmap = base + (size_t)warp * WARP_MAP_B + FRONT;
+    uint8_t* wmap = base + (size_t)warp * WARP_MAP_B;
     ObsT* tile = reinterpret_cast<ObsT*>(base + (size_t)wpb * WARP_MAP_B) + warp * (32 * ROW);
-    uint32_t* gw = reinterpret_cast<uint32_t*>(wmap + lane * MAP_B);  // this lane's nibble map (51 words)
+    uint32_t* gw = reinterpret_cast<uint32_t*>(wmap + lane * MAP_B) + MAP_G0;   // this lane's nibble map (word 0 = cells 0..7)
 
     uint16_t* cells = reinterpret_cast<uint16_t*>(st.cells);
     uint16_t* gwarp = cells + env0 * CELLS3D;                         // the warp's 32 WIDE maps in HBM (tall envs only)
@@ -146,9 +150,9 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
         for (int u = 0; u < U; ++u) {
             const int idx = u * 32 + lane;
             const int el = idx / U, j = idx - el * U;
-            uint32_t* dst = reinterpret_cast<uint32_t*>(wmap + el * MAP_B + j * 16);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(wmap + el * MAP_B) + MAP_G0 + j * 4;
             dst[0] = v[u].x; dst[1] = v[u].y; dst[2] = v[u].z;       // lanes beyond nvec write zeros into their own slots
-            if (j < U - 1) dst[3] = v[u].w;                           // (word 51 would be the next env's first word)
+            if (j < U - 1) dst[3] = v[u].w;                           // (the last vector's fourth word would be the next slot's)
         }
     }
     int total_brick = __ldg(st.plan_total + e.plan_idx);
@@ -178,22 +182,21 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
 
         e.cs += 1;
         // ---- the six cells this step can depend on: the four neighbours (check_sur :88-102) and the second and
-        // third cell in the action's direction (move_step :104-134).  Byte-cache reads are unconditional (the
-        // guards absorb them); whether a cell is frame follows from ONE coordinate, the other is the agent's.
+        // third cell in the action's direction (move_step :104-134); whether a cell is frame follows from ONE
+        // coordinate, the other is the agent's.
         const int dir = a & 3, dr = dir_dr(dir), dc = dir_dc(dir);
         const int o = (e.pr - 3) * 20 + (e.pc - 3);
         int c6[6];
         {
             const int dstep = dr * 20 + dc, sgn = dr + dc;
             const int coord = (dir < 2 ? e.pc : e.pr) - 3;
-            const int vl = nib_at(gw, o - 1), vr = nib_at(gw, o + 1), vu = nib_at(gw, o + 20), vd = nib_at(gw, o - 20);
-            const int v2 = nib_at(gw, o + 2 * dstep), v3 = nib_at(gw, o + 3 * dstep);
-            c6[0] = (e.pc > D2_LO) ? vl : -1;
-            c6[1] = (e.pc < D2_HI) ? vr : -1;
-            c6[2] = (e.pr < D2_HI) ? vu : -1;
-            c6[3] = (e.pr > D2_LO) ? vd : -1;
-            c6[4] = ((unsigned)(coord + 2 * sgn) < 20u) ? v2 : -1;
-            c6[5] = ((unsigned)(coord + 3 * sgn) < 20u) ? v3 : -1;
+            // (predicated reads: a frame cell is not read, so every read stays inside the env's own map)
+            c6[0] = (e.pc > D2_LO) ? nib_at(gw, o - 1) : -1;
+            c6[1] = (e.pc < D2_HI) ? nib_at(gw, o + 1) : -1;
+            c6[2] = (e.pr < D2_HI) ? nib_at(gw, o + 20) : -1;
+            c6[3] = (e.pr > D2_LO) ? nib_at(gw, o - 20) : -1;
+            c6[4] = ((unsigned)(coord + 2 * sgn) < 20u) ? nib_at(gw, o + 2 * dstep) : -1;
+            c6[5] = ((unsigned)(coord + 3 * sgn) < 20u) ? nib_at(gw, o + 3 * dstep) : -1;
         }
         const bool boxed = (c6[0] != 0) && (c6[1] != 0) && (c6[2] != 0) && (c6[3] != 0);     // check_sur
         int nsel = (dir == 0) ? c6[0] : (dir == 1) ? c6[1] : (dir == 2) ? c6[2] : c6[3];
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
             __syncwarp();
             for (unsigned tw = __ballot_sync(FULL, turns_tall); tw; tw &= tw - 1) {
                 const int src = __ffs(tw) - 1;
-                const uint32_t* cw = reinterpret_cast<const uint32_t*>(wmap + src * MAP_B);
+                const uint32_t* cw = reinterpret_cast<const uint32_t*>(wmap + src * MAP_B) + MAP_G0;
                 if (lane < 25) warp_widen_words(gwarp + src * CELLS3D, cw[2 * lane], cw[2 * lane + 1], lane);
             }
             __syncwarp();
@@ -328,7 +331,7 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
         while (dm) {                                        // the warp clears each finished env's map
             const int src = __ffs(dm) - 1;
             dm &= dm - 1;
-            uint32_t* sg = reinterpret_cast<uint32_t*>(wmap + src * MAP_B) + lane;
+            uint32_t* sg = reinterpret_cast<uint32_t*>(wmap + src * MAP_B) + lane;      // the whole slot, guards included
             sg[0] = 0u;
             if (lane < MAP_W - 32) sg[32] = 0u;
             const uint4 z = make_uint4(0, 0, 0, 0);
