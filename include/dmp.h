@@ -90,6 +90,11 @@ extern "C" {
                                 configuration has one with its launch-uniform branches folded) */
 #define DMP_F_ROLLOUT_K1 128 /* tuning switch: 3D single steps run through the rollout kernel (whole maps staged) instead
                                 of the single-step kernel (only the rows a step can look at) */
+#define DMP_F_RESET_OBS  256 /* with DMP_F_AUTORESET: the observation written for an env whose episode ends in this step is
+                                the one its reset returns -- the next episode's first policy input, as in gym's vector
+                                envs; the terminal observation is not materialised.  reward / done are the finished
+                                episode's.  Acting loops (state = env.reset() after done, e.g.
+                                script/DQN/2d/DQN_2d_static.py:186-206) read their next input straight from the buffer */
 
 /* DmpState.plan_mode: which plan an env gets when it auto-resets and DmpIO.next_plan is NULL */
 #define DMP_PLAN_PHILOX      0   /* random_choose_paln=True : counter-based draw                */

@@ -14,6 +14,7 @@ OBS_F32, OBS_F64, OBS_I16, OBS_REC = 0, 1, 2, 3
 REC_DONE, REC_SATURATED = 1, 2
 F_AUTORESET, F_NORMALISE, F_TSLOT1, F_NO_L2_HINT = 1, 2, 4, 8
 F_NO_PDL, F_TILE_LDST, F_GENERIC, F_ROLLOUT_K1 = 16, 32, 64, 128
+F_RESET_OBS = 256
 # tuning switches by name (BatchedDMPEnv(tuning=...)); decided once on the host, passed as DmpIO.flags bits
 TUNING_FLAGS = {"no_l2_hint": F_NO_L2_HINT, "no_pdl": F_NO_PDL, "tile_ldst": F_TILE_LDST, "generic": F_GENERIC,
                 "rollout_k1": F_ROLLOUT_K1}

@@ -83,7 +83,9 @@ __device__ __forceinline__ double iou1_words(const uint32_t (&hw)[15], const uin
 // FAST = true: the throughput configuration with everything that is uniform over a launch folded at compile time --
 // in-kernel Philox draws, observations / rewards / done flags all materialised, auto-reset, raw counters, full warps
 // (n a multiple of the block size), 16 B aligned observation buffer.  The launcher checks those conditions.
-template <typename ObsT, int B1, bool FAST>
+// RF = true (DMP_F_RESET_OBS): a finished env is reset BEFORE its observation is cut (the row it writes is the next episode's
+// first policy input); a template parameter so that each instantiation carries one copy of the reset block.
+template <typename ObsT, int B1, bool FAST, bool RF>
 __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO io, const int K) {
     constexpr bool REC = is_rec<ObsT>::value;
     constexpr int ROW = row_elems<ObsT, D1_OBS>();
@@ -173,31 +175,9 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
             done = e.cs >= st.total_step;
         }
 
-        uint32_t q0 = 0, q1 = 0, q2 = 0;
-        if (want_obs) {
-            if constexpr (REC) {
-                window1<B1>(g, e, q0, q1, q2);                  // the record is assembled once the reward is known
-            } else {
-                stage_observe1<ObsT, B1>(g, e, tile + lane * D1_OBS, normalise, total_brick, st.total_step);
-                __syncwarp();
-                if constexpr (FAST) warp_tile_store_aligned<ObsT, 32 * D1_OBS>(dst, tile, lane);
-                else if (nvalid == 32) warp_tile_store_full<ObsT, 32 * D1_OBS>(dst, tile, lane);
-                else if (nvalid > 0) warp_tile_store<ObsT>(dst, tile, nvalid * D1_OBS, lane);
-                __syncwarp();
-            }
-        }
-        // (d) reward: -1 / 10 / 1 for a column above / at / below its plan height (:117-123)
-        const float reward = rewarded ? ((h > p) ? -1.f : (h == p ? 10.f : 1.f)) : 0.f;
-        e.ret += reward;
-        if (live) {
-            if constexpr (REC) {
-                if (want_obs) __stcs(reinterpret_cast<uint4*>(dst) + lane, make_rec16(q0, q1, q2, e.cb, e.cs, reward, done));
-            }
-            if (want_rew) io.reward[idx] = reward;
-            if (want_done) io.done[idx] = done ? 1 : 0;
-        }
-
-        if (done && autoreset && live) {
+        // (e) done / auto-reset: fold the episode into the statistics, clear the state, next plan
+        const bool fin = done && autoreset && live;
+        auto finish = [&]() {
             uint32_t hw[15];
 #pragma unroll
             for (int j = 0; j < 15; ++j) hw[j] = g[(j + 1) * B1];
@@ -219,7 +199,42 @@ __global__ void __launch_bounds__(B1) k1d_rollout(const DmpState st, const DmpIO
             for (int j = 1; j <= 15; ++j) g[j * B1] = 0;
             e.pos = D1_LO; e.cb = e.cs = 0; e.ret = 0.f;
             dirty = 0xFu;
+        };
+        // (d) reward: -1 / 10 / 1 for a column above / at / below its plan height (:117-123).  Normally evaluated after the
+        // observation (the plan byte's latency hides behind it); DMP_F_RESET_OBS needs it before the reset
+        float reward = 0.f;
+        if constexpr (RF) {
+            reward = rewarded ? ((h > p) ? -1.f : (h == p ? 10.f : 1.f)) : 0.f;
+            e.ret += reward;
+            if (fin) finish();                              // the observation below is the reset env's
         }
+
+        uint32_t q0 = 0, q1 = 0, q2 = 0;
+        if (want_obs) {
+            if constexpr (REC) {
+                window1<B1>(g, e, q0, q1, q2);                  // the record is assembled once the reward is known
+            } else {
+                stage_observe1<ObsT, B1>(g, e, tile + lane * D1_OBS, normalise, total_brick, st.total_step);
+                __syncwarp();
+                if constexpr (FAST) warp_tile_store_aligned<ObsT, 32 * D1_OBS>(dst, tile, lane);
+                else if (nvalid == 32) warp_tile_store_full<ObsT, 32 * D1_OBS>(dst, tile, lane);
+                else if (nvalid > 0) warp_tile_store<ObsT>(dst, tile, nvalid * D1_OBS, lane);
+                __syncwarp();
+            }
+        }
+        if constexpr (!RF) {
+            reward = rewarded ? ((h > p) ? -1.f : (h == p ? 10.f : 1.f)) : 0.f;
+            e.ret += reward;
+        }
+        if (live) {
+            if constexpr (REC) {
+                if (want_obs) __stcs(reinterpret_cast<uint4*>(dst) + lane, make_rec16(q0, q1, q2, e.cb, e.cs, reward, done));
+            }
+            if (want_rew) io.reward[idx] = reward;
+            if (want_done) io.done[idx] = done ? 1 : 0;
+        }
+
+        if constexpr (!RF) { if (fin) finish(); }
     }
 
     if (live) {
@@ -333,20 +348,26 @@ __global__ void k1d_import(const DmpState st, const int32_t* __restrict__ grid, 
     aux[env] = ax;
 }
 
-template <typename ObsT, int B1, bool FAST>
-int launch_rollout1_k(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+template <typename ObsT, int B1, bool FAST, bool RF>
+int launch_rollout1_r(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
     const size_t smem = (size_t)S1_WORDS * B1 * 4 + (is_rec<ObsT>::value ? 0 : (size_t)(B1 / 32) * 32 * D1_OBS * sizeof(ObsT));
     const unsigned blocks = (unsigned)((st.n_envs + B1 - 1) / B1);
     static bool attr_done = false;           // per instantiation
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k1d_rollout<ObsT, B1, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k1d_rollout<ObsT, B1, FAST, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return dmp_set_error(e);
         attr_done = true;
     }
     // plain stream-ordered launch: with programmatic dependent launch the next grid's single-warp blocks become
     // resident early and unbalance the SMs (measured: 47 vs 61 G env-steps/s at 65 536 envs, K = 16)
-    k1d_rollout<ObsT, B1, FAST><<<blocks, B1, smem, s>>>(st, io, K);
+    k1d_rollout<ObsT, B1, FAST, RF><<<blocks, B1, smem, s>>>(st, io, K);
     return dmp_set_error(cudaGetLastError());
+}
+
+template <typename ObsT, int B1, bool FAST>
+int launch_rollout1_k(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    if (io.flags & DMP_F_RESET_OBS) return launch_rollout1_r<ObsT, B1, FAST, true>(st, io, K, s);
+    return launch_rollout1_r<ObsT, B1, FAST, false>(st, io, K, s);
 }
 
 template <typename ObsT, int B1>

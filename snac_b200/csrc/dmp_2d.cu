@@ -142,7 +142,10 @@ __device__ __forceinline__ double iou2(const uint32_t* g, const uint32_t* __rest
 // TMA = true: the warp tile leaves through one bulk async copy (dmp_common.cuh: warp_tile_bulk_store) instead of 13 x
 // (LDS.128 + STG.128) per lane: the L1 data pipe was the busiest unit of this kernel (ncu: 69 %).
 // ObsT = float / double / int16_t: [n][51] observation rows; ObsT = Rec56: one packed 56 B step record per env.
-template <typename ObsT, bool TMA, int BT>
+// RF = true (DMP_F_RESET_OBS): a finished env is reset BEFORE its observation is cut, so the row it writes is the next
+// episode's first policy input.  A template parameter, not a run-time branch: two inlined copies of the reset block
+// cost the kernel registers it does not have (it sits at its 80-register cap).
+template <typename ObsT, bool TMA, int BT, bool RF>
 __global__ void __launch_bounds__(BT, BT == 128 ? 6 : 4) k2d_rollout(const DmpState st, const DmpIO io, const int K) {
     constexpr int ROW = row_elems<ObsT, D2_OBS>();                       // tile elements per env (51 values or 1 record)
     constexpr int B2 = BT;
@@ -229,6 +232,32 @@ __global__ void __launch_bounds__(BT, BT == 128 ? 6 : 4) k2d_rollout(const DmpSt
         }
         e.ret += reward;
 
+        // ---- (e) done / auto-reset: fold the episode into the statistics, clear the state, next plan -------------
+        const bool fin = done && autoreset && live;
+        auto finish = [&]() {
+            const double iou = iou2<BT>(g, plans + e.plan_idx * PLAN2D_WORDS);
+            atomicAdd(st.ep_cnt + env, 1u);                 // fire-and-forget REDs: no read-modify-write stall
+            atomicAdd(st.ep_len + env, (uint32_t)e.cs);
+            atomicAdd(st.ep_ret + env, (double)e.ret);
+            atomicAdd(st.ep_iou + env, iou);
+            if (io.next_plan) {
+                const int p = io.next_plan[idx];
+                if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
+            } else if (st.plan_mode == DMP_PLAN_PHILOX) {
+                e.plan_idx = draw_plan(plan_word(st.seed, (uint64_t)(st.env_base + env), t), st.n_plans);
+            } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
+                e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
+            }
+            total_brick = __ldg(st.plan_total + e.plan_idx);
+#pragma unroll
+            for (int w = 0; w < GRID2D_WORDS; ++w) g[w * B2] = 0;
+            e.pr = e.pc = D2_LO;
+            e.cb = e.cs = 0;
+            e.ret = 0.f;
+            dirty = 0xFu;
+        };
+        if constexpr (RF) { if (fin) finish(); }            // DMP_F_RESET_OBS: the observation below is the reset env's
+
         // ---- (c) observation ------------------------------------------------------------------
         if (io.obs) {
             ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * ROW;
@@ -254,29 +283,7 @@ __global__ void __launch_bounds__(BT, BT == 128 ? 6 : 4) k2d_rollout(const DmpSt
             if (io.done) io.done[idx] = done ? 1 : 0;
         }
 
-        // ---- (e) done / auto-reset ------------------------------------------------------------
-        if (done && autoreset && live) {
-            const double iou = iou2<BT>(g, plans + e.plan_idx * PLAN2D_WORDS);
-            atomicAdd(st.ep_cnt + env, 1u);                 // fire-and-forget REDs: no read-modify-write stall
-            atomicAdd(st.ep_len + env, (uint32_t)e.cs);
-            atomicAdd(st.ep_ret + env, (double)e.ret);
-            atomicAdd(st.ep_iou + env, iou);
-            if (io.next_plan) {
-                const int p = io.next_plan[idx];
-                if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
-            } else if (st.plan_mode == DMP_PLAN_PHILOX) {
-                e.plan_idx = draw_plan(plan_word(st.seed, (uint64_t)(st.env_base + env), t), st.n_plans);
-            } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
-                e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
-            }
-            total_brick = __ldg(st.plan_total + e.plan_idx);
-#pragma unroll
-            for (int w = 0; w < GRID2D_WORDS; ++w) g[w * B2] = 0;
-            e.pr = e.pc = D2_LO;
-            e.cb = e.cs = 0;
-            e.ret = 0.f;
-            dirty = 0xFu;
-        }
+        if constexpr (!RF) { if (fin) finish(); }
     }
 
     if (live) {
@@ -415,20 +422,26 @@ __global__ void k2d_import(const DmpState st, const int32_t* __restrict__ grid, 
     if (ret) wref(15) = __float_as_uint(ret[env]);
 }
 
-template <typename ObsT, bool TMA, int BT>
-int launch_rollout2_b(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+template <typename ObsT, bool TMA, int BT, bool RF>
+int launch_rollout2_r(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
     const size_t smem = (size_t)S2_WORDS * BT * 4 + (size_t)(BT / 32) * 32 * row_elems<ObsT, D2_OBS>() * sizeof(ObsT);
     static bool attr_done = false;           // per instantiation
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k2d_rollout<ObsT, TMA, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k2d_rollout<ObsT, TMA, BT, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return dmp_set_error(e);
-        e = cudaFuncSetAttribute(k2d_rollout<ObsT, TMA, BT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        e = cudaFuncSetAttribute(k2d_rollout<ObsT, TMA, BT, RF>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return dmp_set_error(e);
         attr_done = true;
     }
     const unsigned blocks = (unsigned)((st.n_envs + BT - 1) / BT);
-    return dmp_set_error(dmp_launch_pdl(!(io.flags & DMP_F_NO_PDL), k2d_rollout<ObsT, TMA, BT>, blocks, (unsigned)BT, smem, s,
+    return dmp_set_error(dmp_launch_pdl(!(io.flags & DMP_F_NO_PDL), k2d_rollout<ObsT, TMA, BT, RF>, blocks, (unsigned)BT, smem, s,
                                         st, io, K));
+}
+
+template <typename ObsT, bool TMA, int BT>
+int launch_rollout2_b(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    if (io.flags & DMP_F_RESET_OBS) return launch_rollout2_r<ObsT, TMA, BT, true>(st, io, K, s);
+    return launch_rollout2_r<ObsT, TMA, BT, false>(st, io, K, s);
 }
 
 // Launch shape by shard size: 128-thread blocks hold 768 envs per SM, 224-thread blocks 896 (see the top of the file).

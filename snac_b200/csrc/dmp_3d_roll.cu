@@ -90,7 +90,8 @@ template <typename ObsT>
 __host__ __device__ constexpr size_t warp_smem_bytes() { return (size_t)WARP_MAP_B + 32 * row_elems<ObsT, D3_OBS>() * sizeof(ObsT); }
 
 // TMA = true: each step's warp tile leaves through one bulk async copy (dmp_common.cuh: warp_tile_bulk_store).
-template <typename ObsT, bool TMA>
+// RF = true (DMP_F_RESET_OBS): finished envs are reset BEFORE the observation is cut (gym-style auto-reset observation).
+template <typename ObsT, bool TMA, bool RF>
 __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const DmpIO io, const int K) {
     extern __shared__ uint4 smem_raw[];
     constexpr bool REC = is_rec<ObsT>::value;
@@ -260,13 +261,62 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
         // The plan byte requested at build time is consumed only after the window has been formatted, which hides its
         // latency.  A record row (DMP_OBS_REC) carries the reward, so it is closed after (d); observation rows leave first.
         float reward = 0.f;
+        bool rewarded = false;
         auto reward_now = [&]() {
+            if constexpr (RF) {                          // called twice in that mode: before the reset and by the record path
+                if (rewarded) return;
+                rewarded = true;
+            }
             if (built) {
                 if (newh <= pplan) e.cross += 1;
                 if (!tail && !done) reward = (newh > pplan) ? -1.f : (newh == pplan ? 10.f : 1.f);
             }
             if (boxed_penalty) reward = -100.f;
         };
+        auto finish_all = [&]() {
+            // ---- (e) finished episodes --------------------------------------------------------------------
+            // IoU = cross / (total_brick + count_brick - cross) (:257-276); `cross` is kept up to date by every build.
+            // Episode statistics accumulate in registers and are folded into HBM once, after the last step.
+            const bool fin = done && autoreset && live;
+            const bool fin_wide = fin && tall;                  // a tall env's wide map is cleared with it
+            if (fin) {
+                const int den = total_brick + e.cb - e.cross;
+                const double iou = (e.cross == 0 && den != 0) ? 0.0 : __ddiv_rn((double)e.cross, (double)den);
+                acc_cnt += 1u; acc_len += (uint32_t)e.cs; acc_ret += e.ret; acc_iou += iou;
+                if (io.next_plan) {
+                    const int p = io.next_plan[idx];
+                    if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
+                } else if (st.plan_mode == DMP_PLAN_PHILOX) {
+                    e.plan_idx = draw_plan(plan_word(st.seed, gid, t), st.n_plans);
+                } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
+                    e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
+                }
+                total_brick = __ldg(st.plan_total + e.plan_idx);
+                e.pr = e.pc = D2_LO; e.cb = e.cs = 0; e.ret = 0.f; e.cross = 0;
+                tall = false;
+            }
+            unsigned dm = __ballot_sync(FULL, fin);
+            const unsigned dmw = __ballot_sync(FULL, fin_wide);
+            while (dm) {                                        // the warp clears each finished env's map
+                const int src = __ffs(dm) - 1;
+                dm &= dm - 1;
+                uint32_t* sg = reinterpret_cast<uint32_t*>(wmap + src * MAP_B) + lane;      // the whole slot, guards included
+                sg[0] = 0u;
+                if (lane < MAP_W - 32) sg[32] = 0u;
+                const uint4 z = make_uint4(0, 0, 0, 0);
+                if (lane < NIB3_STRIDE / 16) reinterpret_cast<uint4*>(nwarp + src * NIB3_STRIDE)[lane] = z;
+                if (lane < 25 && ((dmw >> src) & 1u)) {
+                    uint4* gg = reinterpret_cast<uint4*>(gwarp + src * CELLS3D) + 2 * lane;
+                    gg[0] = z; gg[1] = z;
+                }
+            }
+            __syncwarp();
+        };
+        if constexpr (RF) {                                 // reward and reset first: the observation below is the reset env's
+            reward_now();
+            e.ret += reward;
+            finish_all();
+        }
         if (io.obs) {
             if (TMA && bulk_pending) { warp_tile_bulk_wait(lane); bulk_pending = false; }   // previous copy has drained the tile
             ObsT* row = tile + lane * ROW;
@@ -299,49 +349,13 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
         } else {
             reward_now();
         }
-        e.ret += reward;
+        if constexpr (!RF) e.ret += reward;
         if (live) {
             if (io.reward) io.reward[idx] = reward;
             if (io.done) io.done[idx] = done ? 1 : 0;
         }
 
-        // ---- (e) finished episodes --------------------------------------------------------------------
-        // IoU = cross / (total_brick + count_brick - cross) (:257-276); `cross` is kept up to date by every build.
-        // Episode statistics accumulate in registers and are folded into HBM once, after the last step.
-        const bool fin = done && autoreset && live;
-        const bool fin_wide = fin && tall;                  // a tall env's wide map is cleared with it
-        if (fin) {
-            const int den = total_brick + e.cb - e.cross;
-            const double iou = (e.cross == 0 && den != 0) ? 0.0 : __ddiv_rn((double)e.cross, (double)den);
-            acc_cnt += 1u; acc_len += (uint32_t)e.cs; acc_ret += e.ret; acc_iou += iou;
-            if (io.next_plan) {
-                const int p = io.next_plan[idx];
-                if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
-            } else if (st.plan_mode == DMP_PLAN_PHILOX) {
-                e.plan_idx = draw_plan(plan_word(st.seed, gid, t), st.n_plans);
-            } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
-                e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
-            }
-            total_brick = __ldg(st.plan_total + e.plan_idx);
-            e.pr = e.pc = D2_LO; e.cb = e.cs = 0; e.ret = 0.f; e.cross = 0;
-            tall = false;
-        }
-        unsigned dm = __ballot_sync(FULL, fin);
-        const unsigned dmw = __ballot_sync(FULL, fin_wide);
-        while (dm) {                                        // the warp clears each finished env's map
-            const int src = __ffs(dm) - 1;
-            dm &= dm - 1;
-            uint32_t* sg = reinterpret_cast<uint32_t*>(wmap + src * MAP_B) + lane;      // the whole slot, guards included
-            sg[0] = 0u;
-            if (lane < MAP_W - 32) sg[32] = 0u;
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            if (lane < NIB3_STRIDE / 16) reinterpret_cast<uint4*>(nwarp + src * NIB3_STRIDE)[lane] = z;
-            if (lane < 25 && ((dmw >> src) & 1u)) {
-                uint4* gg = reinterpret_cast<uint4*>(gwarp + src * CELLS3D) + 2 * lane;
-                gg[0] = z; gg[1] = z;
-            }
-        }
-        __syncwarp();
+        if constexpr (!RF) finish_all();
     }
     if (live) {
         if ((e.cb | e.cs) > 0xFFFF) {                                 // 16-bit packed counters (include/dmp.h)
@@ -365,23 +379,29 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
 // Launch shape.  Every warp is an independent tile of 32 envs, so blocks are single warps: the block scheduler then refills
 // an SM warp by warp instead of waiting for the slowest warp of a big block (three-warp blocks: 16.6 vs 19.3 G env-steps/s).
 // Shared memory limits residency to 16 warps per SM for f32 observations (6.6 KB of maps + 6.5 KB of tile per warp).
-template <typename ObsT, bool TMA>
-int launch_cache_t(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+template <typename ObsT, bool TMA, bool RF>
+int launch_cache_r(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
     constexpr int wpb = 1;
     const size_t smem = (size_t)wpb * warp_smem_bytes<ObsT>() + 16;
     static_assert(warp_smem_bytes<ObsT>() + 16 <= SMEM_MAX, "one warp's byte cache + tile must fit a block");
     static bool attr_done = false;                           // per instantiation
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k3d_cache_rollout<ObsT, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k3d_cache_rollout<ObsT, TMA, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return dmp_set_error(e);
-        e = cudaFuncSetAttribute(k3d_cache_rollout<ObsT, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        e = cudaFuncSetAttribute(k3d_cache_rollout<ObsT, TMA, RF>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return dmp_set_error(e);
         attr_done = true;
     }
     const int64_t warps = (st.n_envs + 31) / 32;
     const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
-    return dmp_set_error(dmp_launch_pdl(!(io.flags & DMP_F_NO_PDL), k3d_cache_rollout<ObsT, TMA>, blocks,
+    return dmp_set_error(dmp_launch_pdl(!(io.flags & DMP_F_NO_PDL), k3d_cache_rollout<ObsT, TMA, RF>, blocks,
                                         (unsigned)(wpb * 32), smem, s, st, io, K));
+}
+
+template <typename ObsT, bool TMA>
+int launch_cache_t(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
+    if (io.flags & DMP_F_RESET_OBS) return launch_cache_r<ObsT, TMA, true>(st, io, K, s);
+    return launch_cache_r<ObsT, TMA, false>(st, io, K, s);
 }
 
 // the observation tile leaves through one bulk async copy per warp and step unless DMP_F_TILE_LDST asks for load/store pairs

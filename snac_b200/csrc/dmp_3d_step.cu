@@ -38,7 +38,8 @@ __host__ __device__ constexpr size_t warp_area_bytes() {
                ? (size_t)32 * row_elems<ObsT, D3_OBS>() * sizeof(ObsT) : (size_t)32 * SLOT3_B;
 }
 
-template <typename ObsT>
+// RF = true (DMP_F_RESET_OBS): a finished env's observation is the one its reset returns (gym-style auto-reset).
+template <typename ObsT, bool RF>
 __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, const DmpIO io) {
     constexpr bool REC = is_rec<ObsT>::value;
     constexpr int ROW = row_elems<ObsT, D3_OBS>();
@@ -207,13 +208,49 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
     // ---- (d) reward (reward_check :232-239): the plan byte is consumed after the window has been formatted; a record
     // row carries the reward, so it is closed after (d), observation rows leave first
     float reward = 0.f;
+    bool rewarded = false;
     auto reward_now = [&]() {
+        if constexpr (RF) {                              // called twice in that mode: before the reset and by the record path
+            if constexpr (RF) {                          // called twice in that mode: before the reset and by the record path
+                if (rewarded) return;
+                rewarded = true;
+            }
+        }
         if (built) {
             if (newh <= pplan) e.cross += 1;
             if (!tail && !done) reward = (newh > pplan) ? -1.f : (newh == pplan ? 10.f : 1.f);
         }
         if (boxed_penalty) reward = -100.f;
     };
+
+    // ---- (e) finished episodes: IoU = cross / (total_brick + count_brick - cross) (:257-276) ---------------
+    const bool fin = done && autoreset && live;
+    const bool fin_wide = fin && tall;                      // a tall env's wide map is cleared with it
+    auto finish_lane = [&]() {
+        if (fin) {
+            tall = false;
+            const int den = total_brick + e.cb - e.cross;
+            const double iou = (e.cross == 0 && den != 0) ? 0.0 : __ddiv_rn((double)e.cross, (double)den);
+            atomicAdd(st.ep_cnt + env, 1u);                 // fire-and-forget REDs
+            atomicAdd(st.ep_len + env, (uint32_t)e.cs);
+            atomicAdd(st.ep_ret + env, (double)e.ret);
+            atomicAdd(st.ep_iou + env, iou);
+            if (io.next_plan) {
+                const int p = io.next_plan[idx];
+                if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
+            } else if (st.plan_mode == DMP_PLAN_PHILOX) {
+                e.plan_idx = draw_plan(plan_word(st.seed, gid, t), st.n_plans);
+            } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
+                e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
+            }
+            e.pr = e.pc = D2_LO; e.cb = e.cs = 0; e.ret = 0.f; e.cross = 0;
+        }
+    };
+    if constexpr (RF) {                                     // reward and reset first: the observation below is the reset env's
+        reward_now();
+        e.ret += reward;
+        finish_lane();
+    }
 
     // ---- (c) observation: window -> registers, then the warp's [32][51] tile over the drained slots ----------
     bool bulk_pending = false;
@@ -238,6 +275,12 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
                 nib8_to_bytes(q, q0, q1);                               // seven nibbles -> seven bytes (the eighth is masked)
                 u0[k] = rowvalid ? ((q0 & m0) + b0) : 0u;
                 u1[k] = rowvalid ? ((q1 & m1) + b1) : 0u;
+            }
+        }
+        if constexpr (RF) {
+            if (fin) {                                   // window at [3, 3] of an empty map: rows / columns 0..2 are frame
+#pragma unroll
+                for (int k = 0; k < 7; ++k) { u0[k] = k < 3 ? 0u : 0x01000000u; u1[k] = k < 3 ? 0u : 0x00010101u; }
             }
         }
         __syncwarp();                                    // every lane has read its slot
@@ -279,33 +322,13 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
     } else {
         reward_now();
     }
-    e.ret += reward;
+    if constexpr (!RF) e.ret += reward;
     if (live) {
         if (io.reward) io.reward[idx] = reward;
         if (io.done) io.done[idx] = done ? 1 : 0;
     }
 
-    // ---- (e) finished episodes: IoU = cross / (total_brick + count_brick - cross) (:257-276) ---------------
-    const bool fin = done && autoreset && live;
-    const bool fin_wide = fin && tall;                      // a tall env's wide map is cleared with it
-    if (fin) {
-        tall = false;
-        const int den = total_brick + e.cb - e.cross;
-        const double iou = (e.cross == 0 && den != 0) ? 0.0 : __ddiv_rn((double)e.cross, (double)den);
-        atomicAdd(st.ep_cnt + env, 1u);                 // fire-and-forget REDs
-        atomicAdd(st.ep_len + env, (uint32_t)e.cs);
-        atomicAdd(st.ep_ret + env, (double)e.ret);
-        atomicAdd(st.ep_iou + env, iou);
-        if (io.next_plan) {
-            const int p = io.next_plan[idx];
-            if ((unsigned)p >= (unsigned)st.n_plans) errbits |= DMP_ERR_PLANIDX; else e.plan_idx = p;
-        } else if (st.plan_mode == DMP_PLAN_PHILOX) {
-            e.plan_idx = draw_plan(plan_word(st.seed, gid, t), st.n_plans);
-        } else if (st.plan_mode == DMP_PLAN_SEQUENTIAL) {
-            e.plan_idx = (e.plan_idx + 1 == st.n_plans) ? 0 : e.plan_idx + 1;
-        }
-        e.pr = e.pc = D2_LO; e.cb = e.cs = 0; e.ret = 0.f; e.cross = 0;
-    }
+    if constexpr (!RF) finish_lane();
     unsigned dm = __ballot_sync(FULL, fin);
     const unsigned dmw = __ballot_sync(FULL, fin_wide);
     while (dm) {                                            // the warp clears each finished env's map in HBM
@@ -334,23 +357,29 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
 // Launch shape: two-warp blocks, 28 warps per SM by registers (72): 8 192 warps (BASELINE's 262 144 envs) are 1.98 waves.  Measured 12.2 G env-steps/s
 // against 12.0 G with single-warp blocks.  (Per-lane cp.async copies of the rows instead of the per-lane bulk copy:
 // 10.9 G, MIO-throttled -- removed.)
-template <typename ObsT>
-int launch_bytes(const DmpState& st, const DmpIO& io, cudaStream_t s) {
+template <typename ObsT, bool RF>
+int launch_bytes_r(const DmpState& st, const DmpIO& io, cudaStream_t s) {
     static_assert(warp_area_bytes<ObsT>() % 16 == 0, "warp areas and the mbarriers behind them must stay 16 B aligned");
     constexpr int wpb = 2;
     const size_t smem = (size_t)wpb * warp_area_bytes<ObsT>() + (size_t)wpb * 8 + 16;
     static bool attr_done = false;                           // per instantiation
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k3d_step_bytes<ObsT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k3d_step_bytes<ObsT, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return dmp_set_error(e);
-        e = cudaFuncSetAttribute(k3d_step_bytes<ObsT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        e = cudaFuncSetAttribute(k3d_step_bytes<ObsT, RF>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return dmp_set_error(e);
         attr_done = true;
     }
     const int64_t warps = (st.n_envs + 31) / 32;
     const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
-    return dmp_set_error(dmp_launch_pdl(!(io.flags & DMP_F_NO_PDL), k3d_step_bytes<ObsT>, blocks, (unsigned)(wpb * 32), smem,
+    return dmp_set_error(dmp_launch_pdl(!(io.flags & DMP_F_NO_PDL), k3d_step_bytes<ObsT, RF>, blocks, (unsigned)(wpb * 32), smem,
                                         s, st, io));
+}
+
+template <typename ObsT>
+int launch_bytes(const DmpState& st, const DmpIO& io, cudaStream_t s) {
+    if (io.flags & DMP_F_RESET_OBS) return launch_bytes_r<ObsT, true>(st, io, s);
+    return launch_bytes_r<ObsT, false>(st, io, s);
 }
 
 }  // namespace

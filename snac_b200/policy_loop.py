@@ -86,9 +86,12 @@ def reset_observation(dim: int, dtype: torch.dtype, device) -> torch.Tensor:
 class DeviceRollout:
     """T steps of ``obs -> policy -> dmp_step`` for every env, captured in one CUDA graph.
 
-    env        a BatchedDMPEnv that has been reset (auto_reset=True keeps finished envs going: ``next_obs[t]`` then holds
-               the terminal observation of an episode that ended in step t and ``obs[t + 1]`` the reset observation the
-               next episode starts from)
+    env        a BatchedDMPEnv that has been reset.  auto_reset=True keeps finished envs going; the policy input after an
+               episode ends is the reset observation, like ``state = env.reset()`` in the reference's loops.  Build the
+               env with reset_obs=True for the fast form: the kernel writes that observation itself, ``next_obs`` is
+               ``obs[1:]`` (gym's vector-env convention: the terminal observation is not materialised) and the loop
+               is nothing but policy + step.  With reset_obs=False ``next_obs[t]`` keeps the terminal observation and
+               ``obs[t + 1]`` is patched with the reset observation by one extra pass over the batch per step
     policy     callable obs [N, D] -> uint8 actions [N] (see above); None = the kernels' own Philox actions
     horizon    steps per collect() (rounded up to an even number: the device step counter alternates two slots)
     graph      False runs the same loop eagerly (debugging / policies that cannot be captured)
@@ -106,7 +109,8 @@ class DeviceRollout:
         # what step t returned.  With auto_reset the kernel returns the TERMINAL observation of a finished episode and
         # resets the env in the same launch; the next policy input of that env is then the reset observation, like
         # ``state = env.reset()`` in the reference's loops (script/DQN/2d/DQN_2d_static.py:186-206)
-        self.next_obs = torch.zeros((self.T, n, D), dtype=env.obs_dtype, device=dev) if env.auto_reset else self.obs[1:]
+        self._patch = env.auto_reset and not env.reset_obs
+        self.next_obs = torch.zeros((self.T, n, D), dtype=env.obs_dtype, device=dev) if self._patch else self.obs[1:]
         self.reset_obs = reset_observation(env.dim, env.obs_dtype, dev)                  # constant [D] row
         self._cur = torch.zeros((n, D), dtype=env.obs_dtype, device=dev)                 # observation carried between collects
         self.actions = torch.zeros((self.T, n), dtype=torch.uint8, device=dev)
@@ -132,7 +136,7 @@ class DeviceRollout:
                 a = self.actions[t:t + 1]
             env.rollout(1, actions=a, out=(self.next_obs[t:t + 1], self.reward[t:t + 1], self.done[t:t + 1]),
                         use_device_t=True, t_slot=t & 1)
-            if env.auto_reset:                               # envs reset in this launch continue from the reset observation
+            if self._patch:                                  # envs reset in this launch continue from the reset observation
                 torch.where(self.done[t].view(torch.bool)[:, None], self.reset_obs, self.next_obs[t], out=self.obs[t + 1])
         self._cur.copy_(self.obs[self.T])                    # next collect() continues from the last observation
 

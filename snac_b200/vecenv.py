@@ -138,6 +138,9 @@ class BatchedDMPEnv:
     n_plans           size of the generated plan table (plans="generate" only; at most 65 535)
     random_choose_paln  (sic, reference spelling) True: random plan per reset; False: sequential with wrap
     auto_reset        fold finished episodes into the per-env statistics and reset them inside step()
+    reset_obs         with auto_reset: the observation returned for an env whose episode ends in a step is the one its reset
+                      returns (the next episode's first policy input, as gym's vector envs do) instead of the terminal
+                      observation; reward / done are the finished episode's (DMP_F_RESET_OBS).  Default: False
     obs_dtype         torch.float32 (default), torch.float64 (the reference's dtype), torch.int16, or "record": packed step
                       records (window + counters + reward + done in one uint8 [N, rec_bytes] buffer: the compact
                       host-facing kind, see record_dtype() / unpack_records())
@@ -157,7 +160,7 @@ class BatchedDMPEnv:
                  obs_dtype: torch.dtype = torch.float32, normalise: bool = False,
                  seed: int = L.SEED_DEFAULT, env_base: int = 0, action_dist: str = "uniform",
                  total_step: Optional[int] = None, dynamic_rules: Optional[bool] = None, n_plans: int = 4096,
-                 plan_id_base: int = 0, tuning: Optional[Sequence[str]] = None):
+                 plan_id_base: int = 0, tuning: Optional[Sequence[str]] = None, reset_obs: bool = False):
         if dim not in (1, 2, 3):
             raise ValueError("dim must be 1, 2 or 3")
         self.records = isinstance(obs_dtype, str) and obs_dtype == RECORD
@@ -187,6 +190,9 @@ class BatchedDMPEnv:
         self.l2_hints = not (self._tuning_flags & L.F_NO_L2_HINT)
         self.num_envs = int(num_envs)
         self.auto_reset = bool(auto_reset)
+        self.reset_obs = bool(reset_obs)
+        if self.reset_obs and not self.auto_reset:
+            raise ValueError("reset_obs needs auto_reset=True")
         self.obs_dtype, self.normalise = obs_dtype, bool(normalise)
         for k, v in _SPEC[dim].items():
             setattr(self, k, v)
@@ -297,6 +303,7 @@ class BatchedDMPEnv:
         # fractional evict_last / evict_first policies that keep a half or a quarter of the lines were slower still).
         hint = self.l2_hints and (K > 1 or self._cells.numel() <= 40 * 1024 * 1024)
         return ((L.F_AUTORESET if self.auto_reset else 0) | (L.F_NORMALISE if self.normalise else 0)
+                | (L.F_RESET_OBS if self.reset_obs else 0)
                 | (self._tuning_flags & ~L.F_NO_L2_HINT) | (0 if hint else L.F_NO_L2_HINT))
 
     def _u8(self, x, shape, what) -> torch.Tensor:

@@ -27,7 +27,9 @@ class OracleBatch:
         self.ret[:] = 0
         return obs
 
-    def step(self, actions, step_sizes, next_plan=None, auto_reset=True, normalise=False):
+    def step(self, actions, step_sizes, next_plan=None, auto_reset=True, normalise=False, reset_obs=False):
+        """reset_obs: the row of an env that finishes (and is reset) in this step is the observation its reset returns
+        (DMP_F_RESET_OBS) instead of the terminal observation."""
         n = self.n
         obs = np.zeros((n, self.D))
         rew = np.zeros(n, np.float32)
@@ -51,7 +53,9 @@ class OracleBatch:
                     p = (e.plan_idx + 1) % self.n_plans
                 else:
                     raise ValueError("random plan mode needs next_plan")
-                e.reset(p)
+                o = e.reset(p)
+                if reset_obs:
+                    obs[i] = (e.obs_normalised() if normalise else o)[0]
         return obs, rew, done
 
     def export(self):
@@ -67,7 +71,7 @@ class OracleBatch:
 
 
 def philox_rollout(batch, K, seed, env_base, t0, n_actions, ref3d=False, auto_reset=True, normalise=False,
-                   actions=None, step_sizes=None):
+                   actions=None, step_sizes=None, reset_obs=False):
     """K steps with the kernels' Philox streams (oracle/philox.py).  Returns obs [K,N,D], reward, done."""
     n = batch.n
     ids = np.arange(env_base, env_base + n)
@@ -84,5 +88,6 @@ def philox_rollout(batch, K, seed, env_base, t0, n_actions, ref3d=False, auto_re
             s = step_sizes[k]
         used_a[k], used_s[k] = a, s
         nxt = p if (batch.dynamic and not batch.sequential) else None
-        obs[k], rew[k], done[k] = batch.step(a, s, next_plan=nxt, auto_reset=auto_reset, normalise=normalise)
+        obs[k], rew[k], done[k] = batch.step(a, s, next_plan=nxt, auto_reset=auto_reset, normalise=normalise,
+                                             reset_obs=reset_obs)
     return obs, rew, done, used_a, used_s

@@ -522,3 +522,59 @@ def test_1d_fast_path_equals_generic(dynamic, n):
         a = outs[(torch.float32, "1")]
         assert np.array_equal(a[0].cpu().numpy().astype(np.float64), ref[0])
         assert np.array_equal(a[1].cpu().numpy(), ref[1]) and np.array_equal(a[2].cpu().numpy(), ref[2])
+
+
+# ------------------------------------------------------------------------------------------------
+# 9. DMP_F_RESET_OBS (BatchedDMPEnv(reset_obs=True)): the row written for an env that finishes in a step is the observation
+#    its reset returns -- every kernel, rollout and single steps, observations and packed records
+# ------------------------------------------------------------------------------------------------
+RESET_OBS_CASES = [
+    # dim, dynamic, density, ref3d, obs kind, normalise
+    (1, False, None, False, torch.float32, False), (1, True, "dense", False, "record", False),
+    (2, False, None, False, torch.float32, False), (2, True, "sparse", False, torch.float64, True),
+    (2, False, None, False, "record", False),
+    (3, False, None, False, torch.float32, False), (3, True, "dense", True, torch.float64, True),
+    (3, True, "dense", False, "record", False),
+]
+
+
+@pytest.mark.parametrize("dim,dynamic,density,ref3d,kind,normalise", RESET_OBS_CASES)
+def test_reset_observation_mode_matches_oracle(dim, dynamic, density, ref3d, kind, normalise):
+    from snac_b200.vecenv import unpack_records
+    plans = load_plans(dim, density, "train") if dynamic else None
+    n, K, T = 131, 120, (None if dim == 3 else 17)            # ragged last warp; short 1D / 2D episodes so that resets happen
+    env = make_gpu(dim, dynamic, n, 0, plans, auto_reset=True, reset_obs=True, env_base=31, seed=SEED, obs_dtype=kind,
+                   normalise=normalise, total_step=T, action_dist="ref3d" if ref3d else "uniform")
+    ob = OracleBatch(dim, dynamic, n, 0, plans)
+    if T is not None:
+        for e in ob.envs:
+            e.total_step = T
+    p0 = philox.reset_draw(SEED, np.arange(31, 31 + n), 0, ob.n_plans) if dynamic else None
+    env.reset()
+    ob.reset(p0)
+    r_obs, r_rew, r_done, _, _ = philox_rollout(ob, K, SEED, 31, 0, O.SPEC[dim]["actions"], ref3d, normalise=normalise,
+                                                reset_obs=True)
+    assert r_done.sum() > n // 2                              # resets happened all over the batch
+    K1 = K - 30
+    obs, rew, done = env.rollout(K1)                          # one launch, then single steps (3D: the other kernel)
+    outs = [(obs, rew, done)] + [tuple(x.clone()[None] for x in env.step(None)) for _ in range(K1, K)]
+    obs, rew, done = [torch.cat([o[i] for o in outs]) for i in range(3)]
+    if kind == "record":
+        o, r, d, _ = unpack_records(obs, dim)
+        assert np.array_equal(o, r_obs) and np.array_equal(r, r_rew) and np.array_equal(d, r_done)
+    else:
+        assert np.array_equal(obs.cpu().numpy().astype(np.float64), r_obs.astype(np.float32 if kind == torch.float32 else np.float64))
+    assert np.array_equal(rew.cpu().numpy(), r_rew) and np.array_equal(done.cpu().numpy(), r_done)
+    g_ref, sc_ref = ob.export()
+    st = env.export_state()
+    assert np.array_equal(st["grid"].cpu().numpy().reshape(g_ref.shape), g_ref)
+    assert np.array_equal(st["scalars"].cpu().numpy()[:, :6], sc_ref[:, :6])
+    cnt, ln, ret, iou = [x.cpu().numpy() for x in env.episode_stats()]
+    assert np.array_equal(cnt, ob.ep_cnt) and np.array_equal(ln, ob.ep_len) and np.array_equal(ret, ob.ep_ret)
+    assert np.array_equal(iou, ob.ep_iou, equal_nan=True)
+    env.check_errors()
+
+
+def test_reset_obs_needs_auto_reset():
+    with pytest.raises(ValueError):
+        make_gpu(2, False, 4, reset_obs=True)

@@ -22,12 +22,20 @@ def int_policy(A):
 
 @pytest.mark.parametrize("dim", [1, 2, 3])
 @pytest.mark.parametrize("graph", [True, False])
-def test_loop_matches_oracle(dim, graph):
+@pytest.mark.parametrize("reset_obs", [True, False], ids=["kernel_reset_obs", "patched"])
+def test_loop_matches_oracle(dim, graph, reset_obs):
+    """reset_obs=True: the kernel writes the reset observation for finished envs (next_obs IS obs[1:]); False: next_obs
+    keeps the terminal observation and obs[t + 1] is patched.  Either way the policy acts on the reset observation after
+    an episode ends."""
     from snac_b200.policy_loop import DeviceRollout
     from snac_b200.vecenv import BatchedDMPEnv
     n, T, A = 80, 30, O.SPEC[dim]["actions"]
-    env = BatchedDMPEnv(dim, plan_choose=0, num_envs=n, auto_reset=True, obs_dtype=torch.float32, seed=SEED, env_base=5)
+    env = BatchedDMPEnv(dim, plan_choose=0, num_envs=n, auto_reset=True, obs_dtype=torch.float32, seed=SEED, env_base=5,
+                        reset_obs=reset_obs, total_step=None if dim == 3 else 25)
     ob = OracleBatch(dim, False, n, 0)
+    if dim != 3:
+        for e in ob.envs:
+            e.total_step = 25                                 # short episodes: every env is reset inside each collect()
     o = env.reset()
     cur = ob.reset()
     assert np.array_equal(o.cpu().numpy().astype(np.float64), cur)
@@ -47,14 +55,14 @@ def test_loop_matches_oracle(dim, graph):
             nxt, r, d = ob.step(a, s)
             # next_obs is the terminal observation the step returned; on done the oracle batch has reset the env, and the
             # NEXT policy input of that env is the reset observation -- ``state = env.reset()`` in the reference's loops
-            assert np.array_equal(traj["next_obs"][k].cpu().numpy().astype(np.float64), nxt), (rep, k)
+            cur = np.where(d[:, None], reset_row[None, :], nxt)
+            assert np.array_equal(traj["next_obs"][k].cpu().numpy().astype(np.float64), cur if reset_obs else nxt), (rep, k)
             assert np.array_equal(traj["reward"][k].cpu().numpy(), r)
             assert np.array_equal(traj["done"][k].cpu().numpy(), d)
-            cur = np.where(d[:, None], reset_row[None, :], nxt)
             n_done += int(d.sum())
             t += 1
     assert env.t == 3 * T
-    assert n_done > 0 or dim != 3                            # 3D episodes end within 90 steps: the reset rows were exercised
+    assert n_done > n                                        # every env finished episodes: the reset rows were exercised
     g_ref, sc_ref = ob.export()
     st = env.export_state()
     assert np.array_equal(st["grid"].cpu().numpy().reshape(g_ref.shape), g_ref)

@@ -45,7 +45,7 @@ def main():
                 ("epsilon-greedy over the reference Q(s,a) MLP, fp32, all %d actions per env" % A, EpsilonGreedy(q, A, 0.2))]
     for name, pol in policies:
         n = args.envs if pol is None or not isinstance(pol, EpsilonGreedy) else min(args.envs, 262144)
-        env = BatchedDMPEnv(args.dim, plan_choose=0, num_envs=n, auto_reset=True)
+        env = BatchedDMPEnv(args.dim, plan_choose=0, num_envs=n, auto_reset=True, reset_obs=True)
         env.reset()
         loop = DeviceRollout(env, pol, horizon=args.horizon)
         loop.collect(); loop.collect()
