@@ -772,6 +772,18 @@ class VectorizedEnvWrapper:
             self._rew32_np = self._rew32_pin.numpy()[0]
             self._outs = [(b[:self._obs_bytes].view(obs_dtype).view(1, n, D), self._rew32_pin, b[self._off_done:].view(1, n))
                           for b in self._res_pin]
+            # the call itself, prepared once: a step of a small batch is bound by host latency, not by bytes
+            from .vecenv import _TORCH_OBS
+            self._ios = []
+            for o, r, d in self._outs:
+                io = L.DmpIO()
+                io.actions = self._in_pin.data_ptr()
+                io.step_sizes = self._in_pin.data_ptr() + n if step_size_rng == "numpy" else None
+                io.next_plan = None
+                io.obs, io.reward, io.done = o.data_ptr(), r.data_ptr(), d.data_ptr()
+                io.obs_kind, io.flags = _TORCH_OBS[obs_dtype], self.vec._flags(1)
+                self._ios.append(io)
+            self._dev_index = self.vec.device.index
 
     def _draw_plans(self, n):
         if not self._proto._dynamic:
@@ -795,6 +807,16 @@ class VectorizedEnvWrapper:
         obs = self.vec.reset(mask=m, plan_idx=pi)
         return obs[env_index].cpu().numpy().reshape(1, -1)
 
+    def _step_prepared(self, j):
+        vec = self.vec
+        stream = torch.cuda.current_stream(vec.device)
+        vec._st.t_dev = None
+        rc = L.lib.dmp_rollout(C.byref(vec._st), C.byref(self._ios[j]), 1, stream.cuda_stream)
+        if rc:
+            L.check(rc, "dmp_rollout")
+        vec._st.t = vec._st.t + 1
+        stream.synchronize()
+
     def step(self, actions):
         n, vec = self.num_envs, self.vec
         numpy_rng = self.step_size_rng == "numpy"
@@ -806,10 +828,13 @@ class VectorizedEnvWrapper:
         pin, out = self._res_pin[j], self._views[j]
         self._i ^= 1
         if self.mapped:
-            with torch.cuda.device(vec.device):
-                vec.rollout(1, actions=self._in_pin[:n].view(1, n),
-                            step_sizes=self._in_pin[n:].view(1, n) if numpy_rng else None, out=self._outs[j])
-                torch.cuda.current_stream(vec.device).synchronize()
+            if vec._needs_initial_reset:
+                raise RuntimeError("call reset() before step()")
+            if torch.cuda.current_device() == self._dev_index:
+                self._step_prepared(j)
+            else:
+                with torch.cuda.device(vec.device):
+                    self._step_prepared(j)
             out[1][:] = self._rew32_np                          # float64 rewards like the reference's np.asarray(...)
             return out
         with torch.cuda.device(vec.device):

@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
     __syncwarp();                                                                       // mbarrier init visible
     if (live) {
         mbar_arrive_expect_tx(bar, (uint32_t)(b_hi - b_lo));
+        // (plain policy: an evict_last hint on these copies -- the 54.5 MB of nibble maps would fit L2 -- measured 5 % slower)
         bulk_g2s(slot + 16, ne + b_lo, (uint32_t)(b_hi - b_lo), bar);
     } else {
         mbar_arrive(bar);
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
     // is frame follows from one coordinate.  The decision only asks "== 0 / > 0 / frame": saturated nibbles answer it.
     int c6[6];
     {
+        // unconditional reads at an index clamped into the staged span (measured 3-7 % faster than predicated reads)
         const int lo_cell = row_lo * 20, hi_cell = row_hi * 20 + 19;
         const int dstep = dr * 20 + dc, sgn = dr + dc;
         const int coord = (dir < 2 ? e.pc : e.pr) - 3;
