@@ -340,6 +340,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))     # torchrun pins it to 1; the C port uses OpenMP
     wl = args.workload
     dim, dynamic, plan_choose, density, default_envs, _ = WORKLOADS[wl]
     per_proc = args.ref_envs_per_proc or (256 if dynamic else 2048)

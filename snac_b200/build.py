@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-]
+] + os.environ.get("SNAC_B200_NVCC_FLAGS", "").split()      # build-time experiments only (e.g. -DDMP3_EARLY_ROWS=1)
 
 
 def _nvcc() -> str:
