@@ -486,6 +486,8 @@ class Bench:
             base = count[0]
             graphs, events, in_graph = [], [], True
             try:
+                if self.args.timing == "stream":
+                    raise RuntimeError("--timing stream")
                 for g in range(n_graphs):
                     count[0] = base + g * len(launches)
                     e0 = torch.cuda.Event(enable_timing=True, external=True)
@@ -850,6 +852,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="skip the short measurements of the other BASELINE configs")
     ap.add_argument("--no-e2e", action="store_true", help="kernel A/B runs: only the record-kind e2e")
+    ap.add_argument("--timing", default="graph", choices=["graph", "stream"],
+                    help="graph: the timing events are the first / last node of each region's CUDA graph (default); stream: "
+                         "stream events around the graph replay, behind a spin kernel that hides the host's launch latency "
+                         "(the fallback where event nodes cannot be captured)")
     args = ap.parse_args()
     if args.action_dist == "ref3d" and (WORKLOADS[args.workload][0] != 3 or args.actions != "philox"):
         ap.error("--action-dist ref3d needs a 3D workload and in-kernel (philox) actions")
