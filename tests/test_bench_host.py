@@ -54,3 +54,16 @@ def test_reference_arm_prints_one_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "30", "--warmup", "3"],
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_byte_formulas_follow_survey_8d():
+    """B_alg per env-step (fp32 observations), and the same with this repository's 3D nibble layout."""
+    B = bench.Bench
+    assert B.b_alg(2, 262, 51, 1, True) == 261 and B.b_alg(2, 262, 51, 1, False) == 262
+    assert B.b_alg(2, 262, 51, 20, True) == 204 + 5 + (12 + 8 + 100) / 20 == 215.0
+    assert B.b_alg(1, 67, 7, 64, True) == 28 + 5 + (10 + 8 + 120) / 64
+    assert B.b_alg(3, 330, 51, 1, True, mean_len=25.0) == 329 + 64.0
+    assert B.b_alg(3, 330, 51, 20, True, mean_len=25.0) == 204 + 5 + (12 + 8 + 1600) / 20 + 64.0
+    assert B.b_layout(2, 262, 51, 20, True) == B.b_alg(2, 262, 51, 20, True)
+    assert B.b_layout(3, 330, 51, 1, True, mean_len=26.0) == 330 - 100 + 25.5 - 1 + 16.0
+    assert B.b_layout(3, 330, 51, 20, True, mean_len=26.0) == 204 + 5 + (12 + 8 + 416) / 20 + 16.0
