@@ -22,6 +22,9 @@ CASES = [
     ("cfg3_2d_static_dense", 2, False, None, 1048576, 16, None, False),
     ("cfg3_2d_static_dense_short_episodes", 2, False, None, 1048576, 24, 10, False),
     ("cfg4_2d_dynamic_dense_short_episodes", 2, True, "dense", 1048576, 24, 10, False),
+    # the 8-GPU shard of cfg 3 / cfg 4 runs in 224-thread blocks (one wave instead of 1.15): full and ragged
+    ("cfg3_2d_static_dense_shard_of_8", 2, False, None, 131072, 24, 10, False),
+    ("cfg4_2d_dynamic_dense_ragged_wide_blocks", 2, True, "dense", 120001, 24, 10, False),
     ("cfg5_3d_static_dense", 3, False, None, 262144, 64, None, False),
     ("cfg5_3d_dynamic_dense_ref_actions", 3, True, "dense", 262144, 64, None, True),
 ]

@@ -57,11 +57,12 @@ def test_record_rollout_matches_oracle(dim, dynamic, density, ref3d, n, K):
     env.check_errors()
 
 
-@pytest.mark.parametrize("dim", [1, 2, 3])
-def test_records_equal_float_observations_at_scale(dim):
-    """Same seed, same launch shape as the throughput runs (full blocks, 1D: the specialised instantiation)."""
+@pytest.mark.parametrize("dim,n", [(1, 128 * 148 * 4), (2, 128 * 148 * 4), (3, 128 * 148 * 4), (2, 118400)])
+def test_records_equal_float_observations_at_scale(dim, n):
+    """Same seed, same launch shape as the throughput runs (full blocks, 1D: the specialised instantiation; 2D at 118 400
+    envs: the 224-thread blocks of the 8-GPU shard, last block ragged)."""
     from snac_b200.vecenv import unpack_records
-    n, K = 128 * 148 * 4, 40
+    K = 40
     a = make_gpu(dim, False, n, 0, auto_reset=True, seed=SEED, obs_dtype="record", total_step=25)
     b = make_gpu(dim, False, n, 0, auto_reset=True, seed=SEED, obs_dtype=torch.float32, total_step=25)
     a.reset(), b.reset()
