@@ -318,7 +318,7 @@ bool stage_args_ok(const DmpState* st, const DmpIO* io, const int32_t* scratch) 
 inline unsigned sblocks(int64_t n) { return (unsigned)((n + SB - 1) / SB); }
 
 // 3D: the stage kernels read and write the wide (u16) height maps only (dmp_common.cuh): make them current before a
-// stage and fold them back into the byte maps / tall flags after it
+// stage and fold them back into the nibble maps / tall flags after it
 int stage_enter(const DmpState* st, void* stream) {
     return st->dim == 3 ? dmp3d_widen(*st, true, as_stream(stream)) : DMP_OK;
 }
