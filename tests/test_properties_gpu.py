@@ -23,7 +23,7 @@ def window_of(dim, grid, pos):
     return np.stack([g[i, pos[i, 0] - 3:pos[i, 0] + 4, pos[i, 1] - 3:pos[i, 1] + 4].reshape(-1) for i in range(n)]).astype(np.float64)
 
 
-@settings(max_examples=30, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@settings(max_examples=int(__import__("os").environ.get("SNAC_PROPERTY_EXAMPLES", "40")), deadline=None, derandomize=__import__("os").environ.get("SNAC_PROPERTY_RANDOM", "0") != "1", suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
 @given(dim=st.sampled_from([1, 2, 3]), n=st.integers(1, 700), K=st.integers(1, 90), seed=st.integers(0, 2**31 - 1),
        inject=st.booleans(), drop_bias=st.floats(0.0, 0.9), plan_choose=st.integers(0, 1), step_mode=st.booleans())
 def test_invariants_hold_on_random_configurations(dim, n, K, seed, inject, drop_bias, plan_choose, step_mode):
