@@ -213,6 +213,61 @@ class _ScalarDMP:
             tab, tot = self._env.plan_table().clone(), self._env.plan_totals().clone()
             self._env._install_plans(torch.cat([tab, torch.zeros_like(tab[:1])]), torch.cat([tot, tot[:1]]))
             self._scratch_row = self._env.n_plans - 1
+            self._prepare_step()
+
+    # ---- one env per step is bound by call latency, not by bytes: the step and the state export that refreshes the
+    # reference's attributes run back to back on mapped pinned host buffers (the kernels read the action from and write
+    # observation / reward / done / grid / scalars into host memory) behind ONE stream synchronisation
+    def _prepare_step(self):
+        env = self._env
+        lay = env._lay
+        cells = lay.grid_rows * lay.grid_cols
+        self._pin = dict(inp=torch.zeros(2, dtype=torch.uint8, pin_memory=True),
+                         obs=torch.zeros(lay.obs_dim, dtype=torch.float64, pin_memory=True),
+                         rew=torch.zeros(1, dtype=torch.float32, pin_memory=True),
+                         done=torch.zeros(1, dtype=torch.uint8, pin_memory=True),
+                         grid=torch.zeros(cells, dtype=torch.int32, pin_memory=True),
+                         sc=torch.zeros(8, dtype=torch.int32, pin_memory=True))
+        self._pin_np = {k: v.numpy() for k, v in self._pin.items()}
+        self._grid_shape = (1, lay.grid_cols) if self._dim == 1 else (lay.grid_rows, lay.grid_cols)
+        io = L.DmpIO()
+        io.actions, io.step_sizes, io.next_plan = self._pin["inp"].data_ptr(), self._pin["inp"].data_ptr() + 1, None
+        io.obs, io.reward, io.done = self._pin["obs"].data_ptr(), self._pin["rew"].data_ptr(), self._pin["done"].data_ptr()
+        io.obs_kind, io.flags = L.OBS_F64, env._flags(1)
+        self._step_io = io
+        self._dev_index = env.device.index
+
+    def _launch_step_and_export(self):
+        env = self._env
+        stream = torch.cuda.current_stream(env.device)
+        env._st.t_dev = None
+        rc = L.lib.dmp_rollout(C.byref(env._st), C.byref(self._step_io), 1, stream.cuda_stream)
+        if rc:
+            L.check(rc, "dmp_rollout")
+        env._st.t = env._st.t + 1
+        rc = L.lib.dmp_export_state(C.byref(env._st), self._pin["grid"].data_ptr(), self._pin["sc"].data_ptr(), None,
+                                    stream.cuda_stream)
+        if rc:
+            L.check(rc, "dmp_export_state")
+        stream.synchronize()
+
+    def _step_device(self, a, step_size):
+        """One step of the env + a fresh export of its state, through the prepared call.  Returns (obs, reward, done, pos)."""
+        inp = self._pin_np["inp"]
+        inp[0], inp[1] = a, step_size
+        if torch.cuda.current_device() == self._dev_index:
+            self._launch_step_and_export()
+        else:
+            with torch.cuda.device(self._env.device):
+                self._launch_step_and_export()
+        sc = self._pin_np["sc"]
+        self.environment_memory = self._pin_np["grid"].reshape(self._grid_shape).astype(np.float64)
+        if self._lnet and self._dim == 2:                    # frame value 2 (Env/2D/DMP_Env_2D_static_Lnet.py:61-64)
+            self.environment_memory[self.environment_memory == -1] = 2
+        self._set_count_brick(int(sc[2]))
+        self.count_step = int(sc[3])
+        pos = int(sc[0]) if self._dim == 1 else [int(sc[0]), int(sc[1])]
+        return (self._pin_np["obs"].reshape(1, -1).copy(), float(self._pin_np["rew"][0]), bool(self._pin_np["done"][0]), pos)
 
     # ---- hindsight relabelling: the reference's learners overwrite ``env.plan`` between reset() and step(), by
     # assignment (script/DRQN_hindsight/1d/DRQN_hindsight_1D_dynamic.py:255) or in place
@@ -306,20 +361,17 @@ class _ScalarDMP:
         self.step_size = int(np.random.randint(1, 4)) if step_size is None else int(step_size)
         if self._dim != 3 and not (0 <= a < self.action_dim):
             # the reference increments count_step, draws, then fails on the unbound 'position'
-            self._env.step([255], [self.step_size])
+            self._step_device(255, self.step_size)
             self._env._err.zero_()
-            self._sync_attrs()
             raise UnboundLocalError("local variable 'position' referenced before assignment")
         if self._dim == 3 and a < 0:
             raise ValueError("negative actions are not supported by the device path")
-        obs, rew, done = self._env.step([min(a, 255)], [self.step_size])
-        obs = obs.cpu().numpy().reshape(1, -1).copy()
-        r, d = float(rew.item()), bool(done.item())
-        pos = self._sync_attrs()
+        obs, r, d, pos = self._step_device(min(a, 255), self.step_size)
         self.position_memory.append(pos)
         if self._dim == 1:
             self.brick_memory.append([pos, self.environment_memory[0, pos]] if a == 2 else [-1, -1])
-        self._env._err.zero_()
+        if a >= self.action_dim:                             # 3D: an action past the table is an unbuilt brick, not an error
+            self._env._err.zero_()
         return self._format_obs(obs, pos, reset=False), self._reward_type(a, r, d), d
 
     def _reward_type(self, a, r, d):
