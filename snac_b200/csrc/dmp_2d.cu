@@ -370,32 +370,37 @@ __global__ void k2d_iou(const DmpState st, double* __restrict__ out) {
     out[env] = __ddiv_rn((double)inter, (double)uni);
 }
 
+// one warp per env: the 676 cells of the padded grid leave as coalesced stores (the scalar drop-in classes export one env
+// after every step, into mapped host memory: a single thread's 676 stores were a third of that step's latency)
 __global__ void k2d_export(const DmpState st, int32_t* __restrict__ grid, int32_t* __restrict__ scalars, float* __restrict__ ret) {
     const int64_t n = st.n_envs;
-    const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (env >= n) return;
     const uint32_t* cw = reinterpret_cast<const uint32_t*>(st.cells);
     auto word = [&](int w) { return cw[((int64_t)(w >> 2) * n + env) * 4 + (w & 3)]; };
     if (grid) {
         int32_t* g = grid + env * 676;
-        for (int r = 0; r < 26; ++r)
-            for (int c = 0; c < 26; ++c) {
-                int v = -1;
-                if (r >= 3 && r < 23 && c >= 3 && c < 23) {
-                    const int b = (r - 3) * 20 + (c - 3);
-                    v = (word(b >> 5) >> (b & 31)) & 1;
-                }
-                g[r * 26 + c] = v;
+        for (int i = lane; i < 676; i += 32) {
+            const int r = i / 26, c = i - r * 26;
+            int v = -1;
+            if (r >= 3 && r < 23 && c >= 3 && c < 23) {
+                const int b = (r - 3) * 20 + (c - 3);
+                v = (word(b >> 5) >> (b & 31)) & 1;
             }
+            g[i] = v;
+        }
     }
-    const uint32_t w13 = word(13), w14 = word(14);
-    if (scalars) {
-        int32_t* s = scalars + env * 8;
-        const int p = w13 >> 16;
-        s[0] = w13 & 0xFF; s[1] = (w13 >> 8) & 0xFF; s[2] = w14 & 0xFFFF; s[3] = w14 >> 16; s[4] = p;
-        s[5] = st.plan_total[p]; s[6] = 0; s[7] = 0;
+    if (lane == 0) {
+        const uint32_t w13 = word(13), w14 = word(14);
+        if (scalars) {
+            int32_t* s = scalars + env * 8;
+            const int p = w13 >> 16;
+            s[0] = w13 & 0xFF; s[1] = (w13 >> 8) & 0xFF; s[2] = w14 & 0xFFFF; s[3] = w14 >> 16; s[4] = p;
+            s[5] = st.plan_total[p]; s[6] = 0; s[7] = 0;
+        }
+        if (ret) ret[env] = __uint_as_float(word(15));
     }
-    if (ret) ret[env] = __uint_as_float(word(15));
 }
 
 __global__ void k2d_import(const DmpState st, const int32_t* __restrict__ grid, const int32_t* __restrict__ scalars,
@@ -501,7 +506,7 @@ int dmp2d_iou(const DmpState& st, double* out, cudaStream_t s) {
     return dmp_set_error(cudaGetLastError());
 }
 int dmp2d_export(const DmpState& st, int32_t* grid, int32_t* scalars, float* ret, cudaStream_t s) {
-    k2d_export<<<(unsigned)((st.n_envs + 127) / 128), 128, 0, s>>>(st, grid, scalars, ret);
+    k2d_export<<<(unsigned)((st.n_envs + 3) / 4), 128, 0, s>>>(st, grid, scalars, ret);        // four warps = four envs per block
     return dmp_set_error(cudaGetLastError());
 }
 int dmp2d_import(const DmpState& st, const int32_t* grid, const int32_t* scalars, const float* ret, cudaStream_t s) {

@@ -30,12 +30,6 @@ __device__ __forceinline__ uint4 pack3(const Env3& e) {
                       (uint32_t)(e.cb & 0xFFFF) | ((uint32_t)e.cs << 16), __float_as_uint(e.ret), (uint32_t)e.cross);
 }
 
-// value of environment_memory[r][c] in padded coordinates: -1 on the 3-cell frame (:72-75)
-__device__ __forceinline__ int cell3(const uint16_t* grid, int r, int c) {
-    const unsigned ir = (unsigned)(r - 3), ic = (unsigned)(c - 3);
-    return (ir < 20u && ic < 20u) ? (int)grid[ir * 20u + ic] : -1;
-}
-
 // (d) IoU of Env/3D/DMP_simulator_3d_static_circle.py:257-276, one warp per env:
 // cross = sum(min(h, plan)); iou = cross / (total_brick + count_brick - cross).  Optionally clears the map.
 __device__ __forceinline__ double warp_iou3(uint16_t* grid, const uint8_t* __restrict__ plan, int total_brick,
@@ -121,12 +115,24 @@ __global__ void k3d_export(const DmpState st, int32_t* __restrict__ grid, int32_
     const int lane = threadIdx.x & 31;
     const int64_t env = (int64_t)blockIdx.x * WPB3 + (threadIdx.x >> 5);
     if (env >= st.n_envs) return;
+    // heights of an env that is not tall are its nibbles (its wide map is scratch); a tall env's are in its wide map
+    const uint4 ax = reinterpret_cast<const uint4*>(st.aux)[env];
+    const bool tall = (ax.x & AUX3_TALL) != 0u;
     const uint16_t* g = reinterpret_cast<const uint16_t*>(st.cells) + env * CELLS3D;
+    const uint8_t* nib = nmap3(st) + env * NIB3_STRIDE;
     if (grid)
-        for (int i = lane; i < 676; i += 32) grid[env * 676 + i] = cell3(g, i / 26, i % 26);
+        for (int i = lane; i < 676; i += 32) {
+            const int r = i / 26, c = i % 26;
+            int v = -1;
+            if (r >= 3 && r < 23 && c >= 3 && c < 23) {
+                const int ci = (r - 3) * 20 + (c - 3);
+                v = tall ? (int)g[ci] : (int)((nib[ci >> 1] >> ((ci & 1) * 4)) & 0xFu);
+            }
+            grid[env * 676 + i] = v;
+        }
     if (lane == 0) {
         Env3 e;
-        unpack3(reinterpret_cast<const uint4*>(st.aux)[env], e);
+        unpack3(ax, e);
         if (scalars) {
             int32_t* s = scalars + env * 8;
             s[0] = e.pr; s[1] = e.pc; s[2] = e.cb; s[3] = e.cs; s[4] = e.plan_idx;
@@ -254,10 +260,6 @@ int dmp3d_iou(const DmpState& st, double* out, cudaStream_t s) {
     return dmp_set_error(cudaGetLastError());
 }
 int dmp3d_export(const DmpState& st, int32_t* grid, int32_t* scalars, float* ret, cudaStream_t s) {
-    if (grid) {
-        const int rc = dmp3d_widen(st, false, s);
-        if (rc != DMP_OK) return rc;
-    }
     k3d_export<<<blocks3(st.n_envs), WPB3 * 32, 0, s>>>(st, grid, scalars, ret);
     return dmp_set_error(cudaGetLastError());
 }

@@ -328,7 +328,7 @@ int dmp_set_error(cudaError_t e);   // records e, returns DMP_OK / DMP_ECUDA
 //   dmp3d_widen(st, clear_flags) : wide map := nibbles for every env that is not tall; optionally drops all flags
 //   dmp3d_sync_bytes(st)         : nibbles := min(wide, 15) and flag := any(wide >= TALL3), for every env
 // The stage kernels and import only know the wide maps: widen(clear) runs before them and sync_bytes after;
-// export / iou read the wide maps after widen(keep).
+// iou reads the wide maps after widen(keep); export reads whichever map is the env's exact one.
 constexpr int TALL3 = 15;                    // nibbles of a non-tall env are <= 14: exact heights
 constexpr int NIB3_STRIDE = 208;             // bytes per env in the nibble area (200 used)
 constexpr uint32_t AUX3_TALL = 0x80u;        // aux.x bit 7 (pos_row is 3..22)
