@@ -632,8 +632,8 @@ class Bench:
 
     def e2e_suite(self, wl, total_envs, K):
         """The reference-facing calls with HOST buffers: numpy actions in, numpy results out, H2D + D2H inside the timed
-        region.  `record` = packed step records (56 B / 16 B per env: one buffer, one D2H copy, the compact host-facing
-        kind); f32 / i16 = [N, D] observations + reward + done (one fused D2H copy); wrapper = the drop-in
+        region.  `bits` = bit-packed step records (2D 16 B / 3D 32 B per env: one buffer, one D2H copy, the smallest
+        host-facing kind and the line's `e2e`); `record` = byte records (56 B / 16 B per env); f32 / i16 = [N, D] observations + reward + done (one fused D2H copy); wrapper = the drop-in
         VectorizedEnvWrapper.step of multiprocess.py (float64 (N,1,D) observations, numpy-RNG step sizes)."""
         import numpy as np
         import torch
@@ -644,6 +644,8 @@ class Bench:
         rng = np.random.RandomState(99 + self.rank)
         out = {}
         kinds = [("record", "record", False), ("record_mapped", "record", True)]
+        if dim > 1:                                          # bit records: 16 B (2D) / 32 B (3D) per env-step
+            kinds += [("bits", "bits", False), ("bits_mapped", "bits", True), ("bits_mapped_out", "bits", "out")]
         if not args.no_e2e:
             kinds += [("f32", torch.float32, False), ("i16", torch.int16, False)]
         for name, dt, mapped in kinds:
@@ -655,9 +657,12 @@ class Bench:
             env.check_errors()
             api = {"record": "HostStepper.step(actions: np.uint8[N]) -> records: structured numpy array [N] (%d B each: u8 window + 1 [49] | flags | u16 count_brick | u16 count_step | i8 reward | bool done), a view of the pinned buffer the one D2H copy filled" % (hs.d2h_bytes // n) if dim > 1 else
                              "HostStepper.step(actions: np.uint8[N]) -> records: structured numpy array [N] (16 B each: i16 window[5] | u16 count_brick | u16 count_step | i8 reward | bool done)",
+                   "bits": "HostStepper.step(actions: np.uint8[N]) -> bit records: np.uint8 [N, %d] (DMP_OBS_BITS: 49 x %d-bit window code | 12-bit count_brick | 12-bit count_step | 3-bit reward code | done | saturated), a view of the pinned buffer the one D2H copy filled; snac_b200.vecenv.unpack_bits / unpack_records_device expand them to the [N, 51] rows" % (hs.d2h_bytes // n, 2 if dim == 2 else 4),
                    "f32": "HostStepper.step(actions) -> (obs f32[N,%d], reward f32[N], done bool[N]) numpy views of one pinned buffer" % env.obs_dim,
                    "i16": "HostStepper.step(actions) -> (obs i16[N,%d], reward f32[N], done bool[N])" % env.obs_dim}[name.split("_")[0]]
-            if mapped:
+            if mapped == "out":
+                api += '; mapped="out": the actions go through one staged copy, the kernel writes the records into mapped pinned host memory'
+            elif mapped:
                 api += "; mapped=True: no staging copies, the kernel reads the actions from and writes the records into mapped pinned host memory"
             out[name] = {"value": v, "unit": "env-steps/s", "steps": Ke, "h2d_bytes_per_step": int(hs.h2d_bytes) * self.world,
                          "d2h_bytes_per_step": int(hs.d2h_bytes) * self.world, "api": api}
@@ -765,7 +770,8 @@ class Bench:
                            "l2": main["ring"] + " + state %.1f MB" % (n * state_bytes / 1e6),
                            "parallelism": "env-sharded x%d, NCCL all-reduce of episode stats only (%.3f ms, outside the timed region)" % (self.world, ar_ms)},
                 "clocks": main["clocks"],
-                "e2e": e2e["record"], "e2e_record_mapped": e2e.get("record_mapped"), "e2e_f32": e2e.get("f32"), "e2e_i16": e2e.get("i16"),
+                "e2e": e2e["bits" if dim > 1 else "record"], "e2e_bits_mapped": e2e.get("bits_mapped"), "e2e_bits_mapped_out": e2e.get("bits_mapped_out"),
+                "e2e_record": e2e["record"], "e2e_record_mapped": e2e.get("record_mapped"), "e2e_f32": e2e.get("f32"), "e2e_i16": e2e.get("i16"),
                 "e2e_wrapper": e2e.get("wrapper"), "e2e_wrapper_f32_philox": e2e.get("wrapper_f32_philox"),
                 "pcie": pcie,
                 "gpu_launches": main["launches_per_region"] * main["repeats"],

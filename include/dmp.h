@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define DMP_ABI_VERSION 3
+#define DMP_ABI_VERSION 4
 
 /* return codes */
 #define DMP_OK       0
@@ -72,6 +72,19 @@ extern "C" {
                                      win = raw heights (-1 = wall)
                             Every reward of the six classes (-100, -1, 0, 1, 5, 10) fits the i8.  DmpIO.reward / DmpIO.done
                             are still written when they are not NULL. */
+#define DMP_OBS_BITS 4   /* bit-packed step record, 2D and 3D only (1D: DMP_EINVAL -- its DMP_OBS_REC record is 16 B already): the
+                            smallest host-facing kind, for callers that are bound by the device-to-host link (a replay buffer
+                            holds these records as they are; dmp_records_unpack / unpack_records() turn any batch of them
+                            back into observation rows).  Little-endian bit string, field i of width b at bits [i b, i b + b):
+                            2D : 16 B  49 x 2-bit window code (value + 1: 0 = the -1 frame, 1 = empty, 2 = occupied), row-major,
+                                       then the trailer at bit 98
+                            3D : 32 B  49 x 4-bit window code (0 = the -1 frame, else min(height + 1, 15)), row-major; the
+                                       trailer is the last 32-bit word (bit 224)
+                            trailer: count_brick (12 bits, saturating), count_step (12 bits, saturating), reward code (3 bits:
+                                     index into {0, 1, 5, 10, -1, -100}), done (1 bit), saturated (1 bit: a counter passed
+                                     4 095 or -- 3D -- a window cell holds a height >= 14; read that env's exact observation
+                                     through another kind).  Raw counters only.  DmpIO.reward / DmpIO.done are still written
+                                     when they are not NULL. */
 #define DMP_REC_DONE       1
 #define DMP_REC_SATURATED  2   /* 3D only: the env holds a height >= 15 ("tall"); its window bytes are exact up to 253 and saturate
                                   at 255; read that env's exact observation through another obs kind / dmp_export_state */
@@ -156,7 +169,8 @@ typedef struct DmpLayout {
     int32_t obs_dim, n_actions;            /* D and A of the env family          */
     int32_t grid_rows, grid_cols;          /* padded grid of dmp_export_state    */
     int32_t total_step_static, total_step_dynamic;
-    int32_t rec_bytes, reserved;           /* bytes of one DMP_OBS_REC record (16 / 56)   */
+    int32_t rec_bytes, bits_bytes;         /* bytes of one DMP_OBS_REC record (16 / 56 / 56) and of one DMP_OBS_BITS record
+                                              (0 = not available / 16 / 32) */
 } DmpLayout;
 
 /* version / diagnostics */
@@ -230,6 +244,16 @@ int dmp_reset(const DmpState* st, const uint8_t* mask, const int32_t* plan_idx, 
  * The caller advances DmpState.t by K afterwards. */
 int dmp_step(const DmpState* st, const DmpIO* io, void* stream);
 int dmp_rollout(const DmpState* st, const DmpIO* io, int K, void* stream);
+
+/* ---- packed records back to observation rows ----------------------------------------------------
+ * dmp_records_unpack expands n device-resident step records of kind DMP_OBS_REC or DMP_OBS_BITS (as written by dmp_step /
+ * dmp_rollout for env family `dim`) into what the numeric kinds would have written for the same steps: obs [n][D] of
+ * obs_kind (DMP_OBS_F32 / F64 / I16, raw counters), reward f32 [n], done u8 [n], saturated u8 [n] (the record's
+ * saturation flag: its observation is not exact) -- each nullable.  The learner-side inverse of the compact kinds: a
+ * minibatch sampled from a host replay buffer of records is uploaded as records and expanded here
+ * (the reference stores float64 rows, e.g. script/DQN/2d/DQN_2d_static.py:196-204). */
+int dmp_records_unpack(int dim, int rec_kind, const void* records, int64_t n, void* obs, int obs_kind, float* reward,
+                       uint8_t* done, uint8_t* saturated, void* stream);
 
 /* ---- IoU / statistics ----------------------------------------------------------------------------
  * dmp_iou replaces iou(): Env/1D/DMP_Env_1D_static.py:138-151, Env/3D/DMP_simulator_3d_static_circle.py:257-276

@@ -8,9 +8,10 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libdmp.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 OK, EINVAL, ECUDA = 0, 1, 2
-OBS_F32, OBS_F64, OBS_I16, OBS_REC = 0, 1, 2, 3
+OBS_F32, OBS_F64, OBS_I16, OBS_REC, OBS_BITS = 0, 1, 2, 3, 4
+BITS_REWARDS = (0.0, 1.0, 5.0, 10.0, -1.0, -100.0, 0.0, 0.0)     # reward code of a DMP_OBS_BITS trailer -> value
 REC_DONE, REC_SATURATED = 1, 2
 F_AUTORESET, F_NORMALISE, F_TSLOT1, F_NO_L2_HINT = 1, 2, 4, 8
 F_NO_PDL, F_TILE_LDST, F_GENERIC, F_ROLLOUT_K1 = 16, 32, 64, 128
@@ -49,7 +50,7 @@ class DmpLayout(C.Structure):
         ("cells_bytes", C.c_int64), ("aux_bytes", C.c_int64), ("plan_row_bytes", C.c_int64),
         ("obs_dim", C.c_int32), ("n_actions", C.c_int32), ("grid_rows", C.c_int32), ("grid_cols", C.c_int32),
         ("total_step_static", C.c_int32), ("total_step_dynamic", C.c_int32),
-        ("rec_bytes", C.c_int32), ("reserved", C.c_int32),
+        ("rec_bytes", C.c_int32), ("bits_bytes", C.c_int32),
     ]
 
 
@@ -65,6 +66,7 @@ _SIGNATURES = {
     "dmp_reset": (C.c_int, [C.POINTER(DmpState), _P, _P, C.c_uint64, _P, C.c_int, _P]),
     "dmp_step": (C.c_int, [C.POINTER(DmpState), C.POINTER(DmpIO), _P]),
     "dmp_rollout": (C.c_int, [C.POINTER(DmpState), C.POINTER(DmpIO), C.c_int, _P]),
+    "dmp_records_unpack": (C.c_int, [C.c_int, C.c_int, _P, C.c_int64, _P, C.c_int, _P, _P, _P, _P]),
     "dmp_iou": (C.c_int, [C.POINTER(DmpState), _P, _P]),
     "dmp_stats_scratch_bytes": (C.c_int64, [C.c_int64]),
     "dmp_stats_reduce": (C.c_int, [C.POINTER(DmpState), _P, _P, _P]),

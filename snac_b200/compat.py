@@ -68,11 +68,15 @@ class HostStepper:
     * ``obs_dtype="record"`` envs: ``step(actions) -> records``, a structured array (``record_dtype``) whose fields ``win``,
       ``count_brick``, ``count_step``, ``reward``, ``done`` are views into the one buffer that was copied -- 56 B per env
       instead of 209 B: the PCIe link carries 3.7x fewer bytes per step.
+    * ``obs_dtype="bits"`` envs (2D / 3D): ``step(actions) -> uint8 [N, 16 | 32]`` bit-packed records (DMP_OBS_BITS): 13x /
+      6.5x fewer bytes than float32 rows; ``unpack_bits`` (host) / ``unpack_records_device`` expand them.
 
     ``mapped=True`` drops both copies: the pinned host buffers are mapped into the device's address space (unified
     addressing), the kernel reads the actions from host memory and writes its results straight into the pinned result
-    buffer -- one launch and one synchronisation per step, and the transfer overlaps the kernel.  Default: mapped for
-    small batches (a step is then bound by call latency, not bytes), staged copies otherwise.
+    buffer -- one launch and one synchronisation per step, and the transfer overlaps the kernel.  ``mapped="out"`` maps only
+    the result buffer (the actions still go through one staged copy: a kernel reading one byte per env over the link issues
+    32-byte requests).  Default: mapped for small batches (a step is then bound by call latency, not bytes), staged copies
+    otherwise.
     """
     MAPPED_MAX_BYTES = 1 << 18       # default switch-over: results of at most 256 KB per step go through mapped memory
 
@@ -90,12 +94,13 @@ class HostStepper:
             self._off_done = self._off_rew + _align16(4 * n)
             total = self._off_done + n
         self._total = total
-        self.mapped = (total <= self.MAPPED_MAX_BYTES) if mapped is None else bool(mapped)
+        self.mapped = (total <= self.MAPPED_MAX_BYTES) if mapped is None else (mapped if mapped == "out" else bool(mapped))
+        self._map_in, self._map_out = self.mapped is True, bool(self.mapped)
         self._res_pin = [torch.empty(total, dtype=torch.uint8, pin_memory=True) for _ in range(max(1, int(buffers)))]
         self._views = [self._host_views(b.numpy()) for b in self._res_pin]
         # what the kernel writes: the device result buffer, or (mapped) each pinned buffer itself
-        self._res_dev = None if self.mapped else torch.empty(total, dtype=torch.uint8, device=dev)
-        self._outs = [self._out_tensors(b) for b in ((self._res_pin) if self.mapped else [self._res_dev])]
+        self._res_dev = None if self._map_out else torch.empty(total, dtype=torch.uint8, device=dev)
+        self._outs = [self._out_tensors(b) for b in ((self._res_pin) if self._map_out else [self._res_dev])]
         self._in_pin = torch.empty(2 * n, dtype=torch.uint8, pin_memory=True)          # [actions | step sizes]
         self._in_dev = torch.empty(2 * n, dtype=torch.uint8, device=dev)
         self._in_np = self._in_pin.numpy()
@@ -104,6 +109,22 @@ class HostStepper:
         self._i = 0
         self.h2d_bytes = n                                  # 2 n when step sizes are injected
         self.d2h_bytes = total
+        # the C-ABI call itself, prepared once per result buffer and per "step sizes injected?": a step of a compact kind is
+        # a few hundred microseconds, of which the argument checks / tensor views of the generic path were a quarter
+        src = self._in_pin if self._map_in else self._in_dev
+        self._ios = []
+        for o, r, d in self._outs:
+            pair = []
+            for with_sizes in (False, True):
+                io = L.DmpIO()
+                io.actions = src.data_ptr()
+                io.step_sizes = src.data_ptr() + n if with_sizes else None
+                io.next_plan = None
+                io.obs, io.reward, io.done = o.data_ptr(), (None if r is None else r.data_ptr()), (None if d is None else d.data_ptr())
+                io.obs_kind, io.flags = env._kind_of(env.obs_dtype), env._flags(1)
+                pair.append(io)
+            self._ios.append(pair)
+        self._dev_index = env.device.index
 
     def _out_tensors(self, buf: torch.Tensor):
         env, n = self.env, self.env.num_envs
@@ -116,35 +137,47 @@ class HostStepper:
     def _host_views(self, buf: np.ndarray):
         env, n = self.env, self.env.num_envs
         if env.records:
-            from .vecenv import record_dtype
+            from .vecenv import BITS, record_dtype
+            if env.record_kind == BITS:                     # bit records have no field view: uint8 [N, 16 | 32] (unpack_bits)
+                return buf[:self._obs_bytes].reshape(n, env.obs_row)
             return buf[:self._obs_bytes].view(record_dtype(env.dim))
         npdt = {torch.float32: np.float32, torch.float64: np.float64, torch.int16: np.int16}[env.obs_dtype]
         return (buf[:self._obs_bytes].view(npdt).reshape(n, env.obs_row),
                 buf[self._off_rew:self._off_rew + 4 * n].view(np.float32),
                 buf[self._off_done:self._off_done + n].view(np.bool_))
 
+    def _step_on_device(self, j: int, with_sizes: bool, nin: int):
+        env = self.env
+        stream = torch.cuda.current_stream(env.device)
+        if not self._map_in:
+            self._in_dev[:nin].copy_(self._in_pin[:nin], non_blocking=True)
+        st = env._st
+        st.t_dev = None
+        rc = L.lib.dmp_rollout(C.byref(st), C.byref(self._ios[j if self._map_out else 0][1 if with_sizes else 0]), 1, stream.cuda_stream)
+        if rc:
+            L.check(rc, "dmp_rollout")
+        st.t = st.t + 1
+        if not self._map_out:
+            self._res_pin[j].copy_(self._res_dev, non_blocking=True)
+        stream.synchronize()
+
     def step(self, actions, step_sizes=None):
         env, n = self.env, self.env.num_envs
+        if env._needs_initial_reset:
+            raise RuntimeError("call reset() before step()")
         if actions is not self.actions_buffer:
             self.actions_buffer[:] = actions
         if step_sizes is not None and step_sizes is not self.step_sizes_buffer:
             self.step_sizes_buffer[:] = step_sizes
         nin = n if step_sizes is None else 2 * n
         j = self._i
-        pin, out = self._res_pin[j], self._views[j]
         self._i = (j + 1) % len(self._res_pin)
-        with torch.cuda.device(env.device):
-            if self.mapped:                                 # the kernel reads / writes the pinned host buffers themselves
-                env.rollout(1, actions=self._in_pin[:n].view(1, n),
-                            step_sizes=None if step_sizes is None else self._in_pin[n:].view(1, n),
-                            out=self._outs[j])
-            else:
-                self._in_dev[:nin].copy_(self._in_pin[:nin], non_blocking=True)
-                env.rollout(1, actions=self._in_dev[:n].view(1, n),
-                            step_sizes=None if step_sizes is None else self._in_dev[n:].view(1, n), out=self._outs[0])
-                pin.copy_(self._res_dev, non_blocking=True)
-            torch.cuda.current_stream(env.device).synchronize()
-        return out
+        if torch.cuda.current_device() == self._dev_index:
+            self._step_on_device(j, step_sizes is not None, nin)
+        else:
+            with torch.cuda.device(env.device):
+                self._step_on_device(j, step_sizes is not None, nin)
+        return self._views[j]
 
 
 # --------------------------------------------------------------------------------------------------

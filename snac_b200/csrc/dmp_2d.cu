@@ -66,16 +66,14 @@ __device__ __forceinline__ uint32_t stage_deposit2(uint32_t* g, const Env2& e, i
     return old & bit;
 }
 
-// stage (c): observation window -> this thread's row of the warp tile.  observation_ :78-82 + hstack.
-// For a record row (Rec56) the seven row codes ARE the window bytes; reward and done ride along.
-template <typename ObsT, int BT>
-__device__ __forceinline__ void stage_observe2(const uint32_t* g, const Env2& e, ObsT* row,
-                                               bool normalise, int total_brick, int total_step,
-                                               float reward = 0.f, bool done = false) {
-    // rows pr-3 .. pr+3 of the padded grid are interior rows pr-6 .. pr: a 143-bit span [B0, B0+143) of the bit grid that
-    // starts up to 63 bits before it and ends up to 124 bits behind it.  Starting 3 bits early puts interior column c of
-    // every row at bit c+3 = its padded column.  Words outside the grid are read at a clamped index: whatever they hold
-    // only reaches rows that are masked as frame below (a valid row's 20 bits always lie inside words 0..12).
+// stage (c): observation window.  observation_ :78-82 + hstack.
+// The seven window rows as padded rows (bits 3..22 valid, rest garbage): rows pr-3 .. pr+3 of the padded grid are interior rows
+// pr-6 .. pr: a 143-bit span [B0, B0+143) of the bit grid that starts up to 63 bits before it and ends up to 124 bits behind it.
+// Starting 3 bits early puts interior column c of every row at bit c+3 = its padded column.  Words outside the grid are read
+// at a clamped index: whatever they hold only reaches rows that are masked as frame by the callers (a valid row's 20 bits
+// always lie inside words 0..12).
+template <int BT>
+__device__ __forceinline__ void window_rows2(const uint32_t* g, const Env2& e, uint32_t (&R)[7]) {
     const int B0 = (e.pr - 2 * D2_HW) * D2_W - D2_HW;                  // -63 .. 317
     const int w0 = B0 >> 5, off = B0 & 31;                               // arithmetic shift: floor for negative B0
     auto gw = [&](int j) { return g[min(max(w0 + j, 0), GRID2D_WORDS - 1) * BT]; };
@@ -83,7 +81,6 @@ __device__ __forceinline__ void stage_observe2(const uint32_t* g, const Env2& e,
     const uint32_t q0 = __funnelshift_r(x0, x1, off), q1 = __funnelshift_r(x1, x2, off);
     const uint32_t q2 = __funnelshift_r(x2, x3, off), q3 = __funnelshift_r(x3, x4, off);
     const uint32_t q4 = __funnelshift_r(x4, x5, off);
-    uint32_t R[7];                                      // padded rows (bits 3..22 valid, rest garbage)
     R[0] = q0;
     R[1] = __funnelshift_r(q0, q1, 20);
     R[2] = q1 >> 8;
@@ -91,6 +88,16 @@ __device__ __forceinline__ void stage_observe2(const uint32_t* g, const Env2& e,
     R[4] = __funnelshift_r(q2, q3, 16);
     R[5] = q3 >> 4;
     R[6] = __funnelshift_r(q3, q4, 24);
+}
+
+// -> this thread's row of the warp tile.  For a record row (Rec56) the seven row codes ARE the window bytes; reward and done
+// ride along.
+template <typename ObsT, int BT>
+__device__ __forceinline__ void stage_observe2(const uint32_t* g, const Env2& e, ObsT* row,
+                                               bool normalise, int total_brick, int total_step,
+                                               float reward = 0.f, bool done = false) {
+    uint32_t R[7];
+    window_rows2<BT>(g, e, R);
     const int sh = e.pc - D2_HW;                       // window column 0 = padded column pc-3
     const uint32_t colvalid = (COLVALID >> sh) & 0x7Fu;
     const uint64_t vcode = spread7(colvalid);          // 1 where the window column is inside the plan area
@@ -124,6 +131,33 @@ __device__ __forceinline__ void stage_observe2(const uint32_t* g, const Env2& e,
         }
         obs_counters<ObsT>(normalise, e.cb, e.cs, total_brick, total_step, row[49], row[50]);
     }
+}
+
+// DMP_OBS_BITS: the same window as 49 two-bit codes (0 frame / 1 empty / 2 occupied, row-major from bit 0), then the 29-bit
+// trailer at bit 98 -- one 128-bit word per env, built in registers.  Two rows share a register while their bits are spread
+// (bit j -> bit 2j in each 16-bit half); the code of a cell is spread(valid) + spread(occupied).
+template <int BT>
+__device__ __forceinline__ uint4 observe2_bits(const uint32_t* g, const Env2& e, float reward, bool done) {
+    uint32_t R[7];
+    window_rows2<BT>(g, e, R);
+    const int sh = e.pc - D2_HW;
+    const uint32_t colvalid = (COLVALID >> sh) & 0x7Fu;
+    const uint32_t rowvalid = (COLVALID >> (e.pr - D2_HW)) & 0x7Fu;     // bit k: window row k is inside the plan area
+    const uint32_t vv = spread2x7(colvalid | (colvalid << 16));
+    auto occ = [&](int k) { return (R[k] >> sh) & colvalid; };
+    auto pair = [&](int k) -> uint32_t {                                // codes of rows k (low half) and k + 1 (high half)
+        const uint32_t m = ((rowvalid >> k) & 1u ? 0x0000FFFFu : 0u) | ((rowvalid >> (k + 1)) & 1u ? 0xFFFF0000u : 0u);
+        return (spread2x7(occ(k) | (occ(k + 1) << 16)) + vv) & m;
+    };
+    const uint32_t p01 = pair(0), p23 = pair(2), p45 = pair(4);
+    const uint32_t c6 = ((rowvalid >> 6) & 1u) ? ((spread2x7(occ(6)) + vv) & 0x3FFFu) : 0u;
+    const uint32_t c0 = p01 & 0xFFFFu, c1 = p01 >> 16, c2 = p23 & 0xFFFFu, c3 = p23 >> 16, c4 = p45 & 0xFFFFu, c5 = p45 >> 16;
+    uint4 r;
+    r.x = c0 | (c1 << 14) | (c2 << 28);
+    r.y = (c2 >> 4) | (c3 << 10) | (c4 << 24);
+    r.z = (c4 >> 8) | (c5 << 6) | (c6 << 20);
+    r.w = (c6 >> 12) | (bits_trailer(e.cb, e.cs, reward, done, false) << 2);
+    return r;
 }
 
 // stage (d) helper: IoU = |G & P| / |G | P| over the interior (render :169-175) with warp-free popc.
@@ -259,7 +293,9 @@ __global__ void __launch_bounds__(BT, BT == 128 ? 6 : 4) k2d_rollout(const DmpSt
         if constexpr (RF) { if (fin) finish(); }            // DMP_F_RESET_OBS: the observation below is the reset env's
 
         // ---- (c) observation ------------------------------------------------------------------
-        if (io.obs) {
+        if constexpr (is_bits<ObsT>::value) {               // one 128-bit record per env, straight from registers
+            if (io.obs && live) __stcs(reinterpret_cast<uint4*>(io.obs) + idx, observe2_bits<BT>(g, e, reward, done));
+        } else if (io.obs) {
             ObsT* dst = reinterpret_cast<ObsT*>(io.obs) + ((int64_t)k * n + env0) * ROW;
             if constexpr (TMA) {
                 if (k > 0) warp_tile_bulk_wait(lane);               // the previous step's copy has drained the tile
@@ -306,7 +342,7 @@ __global__ void __launch_bounds__(BT, BT == 128 ? 6 : 4) k2d_rollout(const DmpSt
         if (errbits) atomicOr(st.err, errbits);
     }
     if (st.t_dev && blockIdx.x == 0 && tid == 0) st.t_dev[tslot ^ 1] = t0 + (uint64_t)K;
-    if constexpr (TMA) warp_tile_bulk_wait(lane);                        // the tile must outlive the copy that reads it
+    if constexpr (TMA && !is_bits<ObsT>::value) warp_tile_bulk_wait(lane);   // the tile must outlive the copy that reads it
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -339,7 +375,12 @@ __global__ void k2d_reset(const DmpState st, const uint8_t* __restrict__ mask, c
     uint4 v3; pack2(e, 0u, v3);
     cells[3 * n + env] = v3;
     if (obs) {                       // window at [3,3] of an empty grid: rows/cols 0..2 are frame
-        if constexpr (is_rec<ObsT>::value) {
+        if constexpr (is_bits<ObsT>::value) {
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            for (int i = 0; i < 49; ++i)
+                if (i / 7 >= 3 && i % 7 >= 3) w[(2 * i) >> 5] |= 1u << ((2 * i) & 31);
+            reinterpret_cast<uint4*>(obs)[env] = make_uint4(w[0], w[1], w[2], w[3]);
+        } else if constexpr (is_rec<ObsT>::value) {
             uint8_t* o = reinterpret_cast<uint8_t*>(obs + env);
             for (int i = 0; i < 56; ++i) o[i] = (i < 49 && i / 7 >= 3 && i % 7 >= 3) ? 1 : 0;
         } else {
@@ -429,7 +470,8 @@ __global__ void k2d_import(const DmpState st, const int32_t* __restrict__ grid, 
 
 template <typename ObsT, bool TMA, int BT, bool RF>
 int launch_rollout2_r(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
-    const size_t smem = (size_t)S2_WORDS * BT * 4 + (size_t)(BT / 32) * 32 * row_elems<ObsT, D2_OBS>() * sizeof(ObsT);
+    const size_t smem = (size_t)S2_WORDS * BT * 4 +                       // bit records need no tile
+                        (is_bits<ObsT>::value ? 0 : (size_t)(BT / 32) * 32 * row_elems<ObsT, D2_OBS>() * sizeof(ObsT));
     static bool attr_done = false;           // per instantiation
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k2d_rollout<ObsT, TMA, BT, RF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -484,6 +526,7 @@ int dmp2d_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t s) {
         case DMP_OBS_F64: return launch_rollout2<double>(st, io, K, s);
         case DMP_OBS_I16: return launch_rollout2<int16_t>(st, io, K, s);
         case DMP_OBS_REC: return launch_rollout2<Rec56>(st, io, K, s);
+        case DMP_OBS_BITS: return launch_rollout2_t<Bits16, false>(st, io, K, s);
     }
     return DMP_EINVAL;
 }
@@ -496,6 +539,7 @@ int dmp2d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx
         case DMP_OBS_F64: k2d_reset<double><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (double*)obs); break;
         case DMP_OBS_I16: k2d_reset<int16_t><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (int16_t*)obs); break;
         case DMP_OBS_REC: k2d_reset<Rec56><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (Rec56*)obs); break;
+        case DMP_OBS_BITS: k2d_reset<Bits16><<<blocks, 256, 0, s>>>(st, mask, plan_idx, t_draw, (Bits16*)obs); break;
         default: return DMP_EINVAL;
     }
     return dmp_set_error(cudaGetLastError());

@@ -88,7 +88,14 @@ __global__ void k3d_reset(const DmpState st, const uint8_t* __restrict__ mask, c
     if (lane < NIB3_STRIDE / 16) reinterpret_cast<uint4*>(nmap3(st) + env * NIB3_STRIDE)[lane] = z;      // nibble map
     if (lane == 0) aux[env] = pack3(Env3{D2_LO, D2_LO, p, 0, 0, 0.f, 0});
     if (obs) {
-        if constexpr (is_rec<ObsT>::value) {
+        if constexpr (is_bits<ObsT>::value) {               // 49 four-bit codes: 0 frame (rows / columns 0..2), 1 empty
+            if (lane < 8) {
+                uint32_t w = 0u;
+                for (int i = lane * 8; i < lane * 8 + 8 && i < 49; ++i)
+                    if (i / 7 >= 3 && i % 7 >= 3) w |= 1u << ((i & 7) * 4);
+                reinterpret_cast<uint32_t*>(obs + env)[lane] = w;
+            }
+        } else if constexpr (is_rec<ObsT>::value) {
             uint8_t* o = reinterpret_cast<uint8_t*>(obs + env);
             for (int i = lane; i < 56; i += 32) o[i] = (i < 49 && i / 7 >= 3 && i % 7 >= 3) ? 1 : 0;
         } else {
@@ -248,6 +255,7 @@ int dmp3d_reset(const DmpState& st, const uint8_t* mask, const int32_t* plan_idx
         case DMP_OBS_F64: k3d_reset<double><<<b, WPB3 * 32, 0, s>>>(st, mask, plan_idx, t_draw, (double*)obs); break;
         case DMP_OBS_I16: k3d_reset<int16_t><<<b, WPB3 * 32, 0, s>>>(st, mask, plan_idx, t_draw, (int16_t*)obs); break;
         case DMP_OBS_REC: k3d_reset<Rec56><<<b, WPB3 * 32, 0, s>>>(st, mask, plan_idx, t_draw, (Rec56*)obs); break;
+        case DMP_OBS_BITS: k3d_reset<Bits32><<<b, WPB3 * 32, 0, s>>>(st, mask, plan_idx, t_draw, (Bits32*)obs); break;
         default: return DMP_EINVAL;
     }
     return dmp_set_error(cudaGetLastError());

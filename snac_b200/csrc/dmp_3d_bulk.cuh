@@ -87,4 +87,26 @@ static __device__ __noinline__ void fix_saturated_codes(const uint16_t* ge, int 
             }
 }
 
+
+// ---- DMP_OBS_BITS (include/dmp.h): the seven window rows of biased bytes (height + 1 <= 16, 0 = frame) -> 49 four-bit
+// codes min(height + 1, 15) + the trailer word: one 32 B record, two 128-bit streaming stores from registers (no tile).
+// A code of 15 stands for "height >= 14": such a record carries the saturation flag.
+__device__ __forceinline__ void bits32_store(void* obs, int64_t idx, const uint32_t (&u0)[7], const uint32_t (&u1)[7], int cb, int cs,
+                                             float reward, bool done) {
+    uint32_t r[7], any15 = 0u;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const uint32_t a = u0[k] - ((u0[k] >> 4) & 0x01010101u), b = u1[k] - ((u1[k] >> 4) & 0x01010101u);   // 16 -> 15
+        r[k] = __byte_perm(a | (a >> 4), 0u, 0x4420) | (__byte_perm(b | (b >> 4), 0u, 0x4420) << 16);       // 7 nibbles, 28 bits
+        uint32_t t = r[k] & (r[k] >> 1);
+        t &= t >> 2;
+        any15 |= t;
+    }
+    const bool sat = (any15 & 0x01111111u) != 0u;
+    uint4* d = reinterpret_cast<uint4*>(obs) + 2 * idx;
+    __stcs(d, make_uint4(r[0] | (r[1] << 28), (r[1] >> 4) | (r[2] << 24), (r[2] >> 8) | (r[3] << 20), (r[3] >> 12) | (r[4] << 16)));
+    __stcs(d + 1, make_uint4((r[4] >> 16) | (r[5] << 12), (r[5] >> 20) | (r[6] << 8), r[6] >> 24,
+                             bits_trailer(cb, cs, reward, done, sat)));
+}
+
 }  // namespace d3

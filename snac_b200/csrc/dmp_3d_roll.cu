@@ -87,7 +87,9 @@ __device__ __forceinline__ void observe_cache(const uint32_t* gw, const uint16_t
 
 // shared memory: [WPB][WARP_MAP_B] nibble maps | [WPB][32*51] ObsT tiles
 template <typename ObsT>
-__host__ __device__ constexpr size_t warp_smem_bytes() { return (size_t)WARP_MAP_B + 32 * row_elems<ObsT, D3_OBS>() * sizeof(ObsT); }
+__host__ __device__ constexpr size_t warp_smem_bytes() {                 // bit records leave from registers: no tile
+    return (size_t)WARP_MAP_B + (is_bits<ObsT>::value ? 0 : 32 * row_elems<ObsT, D3_OBS>() * sizeof(ObsT));
+}
 
 // TMA = true: each step's warp tile leaves through one bulk async copy (dmp_common.cuh: warp_tile_bulk_store).
 // RF = true (DMP_F_RESET_OBS): finished envs are reset BEFORE the observation is cut (gym-style auto-reset observation).
@@ -317,7 +319,16 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
             e.ret += reward;
             finish_all();
         }
-        if (io.obs) {
+        if constexpr (is_bits<ObsT>::value) {
+            if (io.obs) {
+                uint32_t u0[7], u1[7];
+                window_cache(gw, e.pr, e.pc, u0, u1);
+                reward_now();
+                if (live) bits32_store(io.obs, idx, u0, u1, e.cb, e.cs, reward, done);
+            } else {
+                reward_now();
+            }
+        } else if (io.obs) {
             if (TMA && bulk_pending) { warp_tile_bulk_wait(lane); bulk_pending = false; }   // previous copy has drained the tile
             ObsT* row = tile + lane * ROW;
             if constexpr (REC) {
@@ -419,6 +430,7 @@ int dmp3d_cache_rollout(const DmpState& st, const DmpIO& io, int K, cudaStream_t
         case DMP_OBS_F64: return launch_cache<double>(st, io, K, s);
         case DMP_OBS_I16: return launch_cache<int16_t>(st, io, K, s);
         case DMP_OBS_REC: return launch_cache<Rec56>(st, io, K, s);
+        case DMP_OBS_BITS: return launch_cache_t<Bits32, false>(st, io, K, s);
     }
     return DMP_EINVAL;
 }

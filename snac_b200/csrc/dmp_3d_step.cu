@@ -286,6 +286,10 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
                 for (int k = 0; k < 7; ++k) { u0[k] = k < 3 ? 0u : 0x01000000u; u1[k] = k < 3 ? 0u : 0x00010101u; }
             }
         }
+        if constexpr (is_bits<ObsT>::value) {            // one 32 B record per env, straight from registers
+            reward_now();
+            if (live) bits32_store(io.obs, idx, u0, u1, e.cb, e.cs, reward, done);
+        } else {
         __syncwarp();                                    // every lane has read its slot
         ObsT* row = tile + lane * ROW;
         const bool fix = tall && window_saturated(u0, u1);      // a cell of 15 or more in a tall env's window: practically never
@@ -322,6 +326,7 @@ __global__ void __launch_bounds__(128, 7) k3d_step_bytes(const DmpState st, cons
             tile_rows_store<ObsT, D3_OBS>(dst, tile, nvalid, lane);
         }
         if constexpr (!REC) reward_now();
+        }
     } else {
         reward_now();
     }
@@ -393,6 +398,7 @@ int dmp3d_step_bytes(const DmpState& st, const DmpIO& io, cudaStream_t s) {
         case DMP_OBS_F64: return launch_bytes<double>(st, io, s);
         case DMP_OBS_I16: return launch_bytes<int16_t>(st, io, s);
         case DMP_OBS_REC: return launch_bytes<Rec56>(st, io, s);
+        case DMP_OBS_BITS: return launch_bytes<Bits32>(st, io, s);
     }
     return DMP_EINVAL;
 }

@@ -197,6 +197,53 @@ inline int stats_blocks(int64_t n) {
     return (int)b;
 }
 
+// ---------------------------------------------------------------------------------------------
+// packed step records -> observation rows (dmp_records_unpack): one thread per output value, so the rows leave as
+// coalesced stores; the few record words a warp needs stay in L1
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bits_reward_value(uint32_t code) {
+    return code == 0u ? 0.f : (code == 1u ? 1.f : (code == 2u ? 5.f : (code == 3u ? 10.f : (code == 4u ? -1.f : -100.f))));
+}
+
+template <typename ObsT>
+__global__ void k_records_unpack(int dim, int kind, const uint8_t* __restrict__ rec, int64_t n, ObsT* __restrict__ obs,
+                                 float* __restrict__ reward, uint8_t* __restrict__ done, uint8_t* __restrict__ sat) {
+    const int D = dim == 1 ? D1_OBS : D2_OBS, W = D - 2;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * D) return;
+    const int64_t env = i / D;
+    const int col = (int)(i - env * D);
+    int v, cb, cs, dn, st_;
+    float rw;
+    if (kind == DMP_OBS_BITS) {
+        const int rb = dim == 2 ? 16 : 32, cw = dim == 2 ? 2 : 4;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(rec + env * rb);
+        const uint32_t tr = dim == 2 ? (w[3] >> 2) : w[7];
+        cb = tr & 0xFFF; cs = (tr >> 12) & 0xFFF; rw = bits_reward_value((tr >> 24) & 7u); dn = (tr >> 27) & 1; st_ = (tr >> 28) & 1;
+        const int b = col * cw;
+        v = col < W ? (int)((w[b >> 5] >> (b & 31)) & ((1u << cw) - 1u)) - 1 : 0;
+    } else if (dim == 1) {
+        const uint8_t* r = rec + env * 16;
+        const int16_t* h = reinterpret_cast<const int16_t*>(r);
+        cb = reinterpret_cast<const uint16_t*>(r)[5]; cs = reinterpret_cast<const uint16_t*>(r)[6];
+        rw = (float)(int8_t)r[14]; dn = r[15]; st_ = 0;
+        v = col < W ? (int)h[col] : 0;
+    } else {
+        const uint8_t* r = rec + env * 56;
+        cb = reinterpret_cast<const uint16_t*>(r)[25]; cs = reinterpret_cast<const uint16_t*>(r)[26];
+        rw = (float)(int8_t)r[54]; dn = r[55]; st_ = (r[49] & DMP_REC_SATURATED) ? 1 : 0;
+        v = col < W ? (int)r[col] - 1 : 0;
+    }
+    if (col == W) v = cb;
+    if (col == W + 1) v = cs;
+    if (obs) obs[i] = obs_from_int<ObsT>(v);
+    if (col == 0) {
+        if (reward) reward[env] = rw;
+        if (done) done[env] = (uint8_t)dn;
+        if (sat) sat[env] = (uint8_t)st_;
+    }
+}
+
 bool state_ok(const DmpState* st) {
     if (!st) return false;
     if (st->dim < 1 || st->dim > 3) return false;
@@ -224,11 +271,12 @@ int dmp_layout(int dim, int64_t n, DmpLayout* out) {
             *out = DmpLayout{64 * n, 8 * n, PLAN1D_BYTES, D1_OBS, D1_ACT, 1, 34, 750, 750, (int32_t)sizeof(Rec16), 0};
             return DMP_OK;
         case 2:
-            *out = DmpLayout{64 * n, 0, PLAN2D_WORDS * 4, D2_OBS, D2_ACT, 26, 26, 600, 600, (int32_t)sizeof(Rec56), 0};
+            *out = DmpLayout{64 * n, 0, PLAN2D_WORDS * 4, D2_OBS, D2_ACT, 26, 26, 600, 600, (int32_t)sizeof(Rec56),
+                             (int32_t)sizeof(Bits16)};
             return DMP_OK;
         case 3:
             *out = DmpLayout{(800 + NIB3_STRIDE) * n, 16 * n, CELLS3D, D3_OBS, D3_ACT, 26, 26, 1300, 1000,    // u16 maps + nibble maps
-                             (int32_t)sizeof(Rec56), 0};
+                             (int32_t)sizeof(Rec56), (int32_t)sizeof(Bits32)};
             return DMP_OK;
     }
     return DMP_EINVAL;
@@ -259,8 +307,9 @@ int dmp_reset(const DmpState* st, const uint8_t* mask, const int32_t* plan_idx, 
 
 int dmp_rollout(const DmpState* st, const DmpIO* io, int K, void* stream) {
     if (!state_ok(st) || !io || K < 1) return DMP_EINVAL;
-    if (io->obs_kind < DMP_OBS_F32 || io->obs_kind > DMP_OBS_REC) return DMP_EINVAL;
-    if ((io->flags & DMP_F_NORMALISE) && (io->obs_kind == DMP_OBS_I16 || io->obs_kind == DMP_OBS_REC)) return DMP_EINVAL;
+    if (io->obs_kind < DMP_OBS_F32 || io->obs_kind > DMP_OBS_BITS) return DMP_EINVAL;
+    if (io->obs_kind == DMP_OBS_BITS && st->dim == 1) return DMP_EINVAL;
+    if ((io->flags & DMP_F_NORMALISE) && io->obs_kind >= DMP_OBS_I16) return DMP_EINVAL;
     if ((io->flags & DMP_F_AUTORESET) && (!st->ep_cnt || !st->ep_len || !st->ep_ret || !st->ep_iou)) return DMP_EINVAL;
     switch (st->dim) {
         case 1: return dmp1d_rollout(*st, *io, K, as_stream(stream));
@@ -270,6 +319,23 @@ int dmp_rollout(const DmpState* st, const DmpIO* io, int K, void* stream) {
 }
 
 int dmp_step(const DmpState* st, const DmpIO* io, void* stream) { return dmp_rollout(st, io, 1, stream); }
+
+int dmp_records_unpack(int dim, int rec_kind, const void* records, int64_t n, void* obs, int obs_kind, float* reward,
+                       uint8_t* done, uint8_t* saturated, void* stream) {
+    if (dim < 1 || dim > 3 || !records || n < 1) return DMP_EINVAL;
+    if (rec_kind != DMP_OBS_REC && !(rec_kind == DMP_OBS_BITS && dim != 1)) return DMP_EINVAL;
+    if (obs && (obs_kind < DMP_OBS_F32 || obs_kind > DMP_OBS_I16)) return DMP_EINVAL;
+    const int64_t total = n * (dim == 1 ? D1_OBS : D2_OBS);
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    const uint8_t* r = reinterpret_cast<const uint8_t*>(records);
+    cudaStream_t s = as_stream(stream);
+    switch (obs ? obs_kind : DMP_OBS_F32) {
+        case DMP_OBS_F32: k_records_unpack<float><<<blocks, 256, 0, s>>>(dim, rec_kind, r, n, (float*)obs, reward, done, saturated); break;
+        case DMP_OBS_F64: k_records_unpack<double><<<blocks, 256, 0, s>>>(dim, rec_kind, r, n, (double*)obs, reward, done, saturated); break;
+        default: k_records_unpack<int16_t><<<blocks, 256, 0, s>>>(dim, rec_kind, r, n, (int16_t*)obs, reward, done, saturated); break;
+    }
+    return dmp_set_error(cudaGetLastError());
+}
 
 int dmp_iou(const DmpState* st, double* iou_out, void* stream) {
     if (!state_ok(st) || !iou_out) return DMP_EINVAL;

@@ -140,9 +140,19 @@ __device__ __forceinline__ void obs_counters(bool normalise, int cb, int cs, int
 // ---------------------------------------------------------------------------------------------
 struct Rec56 { uint32_t w[14]; };
 struct Rec16 { uint32_t w[4]; };
+// DMP_OBS_BITS: bit-packed step records (include/dmp.h), one or two 128-bit words per env that leave the thread's registers
+// through 128-bit streaming stores -- no shared-memory tile.  Bits16 (2D): 49 x 2-bit window codes + 12-bit counters + reward
+// code + done; Bits32 (3D): 49 x 4-bit window codes (height + 1, saturating at 15) + the same trailer.
+struct Bits16 { uint32_t w[4]; };
+struct Bits32 { uint32_t w[8]; };
 template <typename T> struct is_rec { static constexpr bool value = false; };
 template <> struct is_rec<Rec56> { static constexpr bool value = true; };
 template <> struct is_rec<Rec16> { static constexpr bool value = true; };
+template <> struct is_rec<Bits16> { static constexpr bool value = true; };
+template <> struct is_rec<Bits32> { static constexpr bool value = true; };
+template <typename T> struct is_bits { static constexpr bool value = false; };
+template <> struct is_bits<Bits16> { static constexpr bool value = true; };
+template <> struct is_bits<Bits32> { static constexpr bool value = true; };
 // elements of ObsT per env in an observation buffer / warp tile
 template <typename ObsT, int D> __host__ __device__ constexpr int row_elems() { return is_rec<ObsT>::value ? 1 : D; }
 
@@ -165,6 +175,25 @@ __device__ __forceinline__ void rec56_store(Rec56* row, const uint32_t (&w)[13],
     for (int j = 0; j < 6; ++j) d[j] = make_uint2(w[2 * j], w[2 * j + 1]);
     d[6] = make_uint2((w[12] & 0xFFu) | (flags << 8) | ((uint32_t)(cb & 0xFFFF) << 16),
                       (uint32_t)(cs & 0xFFFF) | (((uint32_t)(int)reward & 0xFFu) << 16) | (done ? 1u << 24 : 0u));
+}
+
+// DMP_OBS_BITS trailer: 12-bit counters (saturating, flagged), the reward as an index into {0, 1, 5, 10, -1, -100} (every reward
+// of the six classes), done, and the saturation flag: 30 bits starting at bit `sh` of the record's last payload word.
+__device__ __forceinline__ uint32_t bits_reward_code(float r) {
+    const int v = (int)r;
+    return v == 0 ? 0u : (v == 1 ? 1u : (v == 5 ? 2u : (v == 10 ? 3u : (v == -1 ? 4u : 5u))));
+}
+__device__ __forceinline__ uint32_t bits_trailer(int cb, int cs, float reward, bool done, bool saturated) {
+    const bool over = (cb | cs) > 0xFFF;
+    return (uint32_t)min(cb, 0xFFF) | ((uint32_t)min(cs, 0xFFF) << 12) | (bits_reward_code(reward) << 24) |
+           (done ? 1u << 27 : 0u) | ((saturated || over) ? 1u << 28 : 0u);
+}
+// two 7-bit values held in the two halves of x (bits 0..6 and 16..22): bit j of each half moves to bit 2j of its half
+__device__ __forceinline__ uint32_t spread2x7(uint32_t x) {
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
 }
 
 // ---------------------------------------------------------------------------------------------

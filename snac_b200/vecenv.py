@@ -19,6 +19,8 @@ from . import _lib as L
 
 _TORCH_OBS = {torch.float32: L.OBS_F32, torch.float64: L.OBS_F64, torch.int16: L.OBS_I16, torch.uint8: L.OBS_REC}
 RECORD = "record"      # obs_dtype=RECORD: packed step records (DMP_OBS_REC, include/dmp.h), uint8 [..., rec_bytes]
+BITS = "bits"          # obs_dtype=BITS: bit-packed step records (DMP_OBS_BITS, 2D 16 B / 3D 32 B), uint8 [..., bits_bytes]
+_NP_OBS = {torch.float32: np.float32, torch.float64: np.float64, torch.int16: np.int16}
 
 
 def record_dtype(dim: int) -> np.dtype:
@@ -34,12 +36,72 @@ def record_dtype(dim: int) -> np.dtype:
                      "itemsize": 56})
 
 
+def bits_bytes(dim: int) -> int:
+    """Size of one DMP_OBS_BITS record (include/dmp.h): 16 B in 2D, 32 B in 3D (1D has no bit records)."""
+    if dim not in (2, 3):
+        raise ValueError("bit records exist for 2D and 3D envs (the 1D step record is 16 B already)")
+    return 16 if dim == 2 else 32
+
+
+def unpack_bits(rec, dim: int, dtype=np.float64):
+    """Bit-packed step records (DMP_OBS_BITS) -> (obs [..., 51], reward float32 [...], done bool [...], saturated bool
+    [...]) on the host with numpy.  ``rec``: uint8 array [..., 16 | 32] (numpy or torch).  ``saturated`` marks records whose
+    observation is not exact (a counter above 4 095, or in 3D a window cell of height >= 14)."""
+    if torch.is_tensor(rec):
+        rec = rec.cpu().numpy()
+    rb = bits_bytes(dim)
+    if rec.dtype != np.uint8 or rec.shape[-1] != rb:
+        raise ValueError("expected a uint8 array [..., %d]" % rb)
+    w = np.ascontiguousarray(rec).view("<u4")                       # [..., 4 | 8]
+    cw = 2 if dim == 2 else 4
+    obs = np.empty(rec.shape[:-1] + (51,), dtype=dtype)
+    for j in range(49):
+        b = j * cw
+        obs[..., j] = ((w[..., b >> 5] >> np.uint32(b & 31)) & np.uint32((1 << cw) - 1)).astype(np.int64) - 1
+    tr = (w[..., 3] >> np.uint32(2)) if dim == 2 else w[..., 7]
+    obs[..., 49] = tr & np.uint32(0xFFF)
+    obs[..., 50] = (tr >> np.uint32(12)) & np.uint32(0xFFF)
+    reward = np.asarray(L.BITS_REWARDS, np.float32)[(tr >> np.uint32(24)) & np.uint32(7)]
+    return obs, reward, ((tr >> np.uint32(27)) & np.uint32(1)).astype(bool), ((tr >> np.uint32(28)) & np.uint32(1)).astype(bool)
+
+
+def unpack_records_device(rec: torch.Tensor, dim: int, kind: str = RECORD, dtype: torch.dtype = torch.float32):
+    """The same expansion ON THE DEVICE (``dmp_records_unpack``): a uint8 CUDA tensor [..., record bytes] of step records
+    (``kind`` "record" or "bits") -> (obs [..., D] of ``dtype``, reward float32 [...], done bool [...], saturated bool
+    [...]) CUDA tensors.  For learners that keep a replay buffer of compact records on the host and expand each sampled
+    minibatch after uploading it."""
+    if not (torch.is_tensor(rec) and rec.is_cuda and rec.dtype == torch.uint8):
+        raise ValueError("rec must be a uint8 CUDA tensor")
+    rk = {RECORD: L.OBS_REC, BITS: L.OBS_BITS}[kind]
+    rb = bits_bytes(dim) if kind == BITS else record_dtype(dim).itemsize
+    if rec.shape[-1] != rb:
+        raise ValueError("expected records of %d bytes" % rb)
+    rec = rec.contiguous()
+    shape = tuple(rec.shape[:-1])
+    n = int(np.prod(shape)) if shape else 1
+    D = 7 if dim == 1 else 51
+    dev = rec.device
+    obs = torch.empty(shape + (D,), dtype=dtype, device=dev)
+    reward = torch.empty(shape, dtype=torch.float32, device=dev)
+    done = torch.empty(shape, dtype=torch.uint8, device=dev)
+    sat = torch.empty(shape, dtype=torch.uint8, device=dev)
+    if n:
+        with torch.cuda.device(dev):
+            L.check(L.lib.dmp_records_unpack(dim, rk, rec.data_ptr(), n, obs.data_ptr(), _TORCH_OBS[dtype], reward.data_ptr(),
+                                             done.data_ptr(), sat.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+                    "dmp_records_unpack")
+    return obs, reward, done.view(torch.bool), sat.view(torch.bool)
+
+
 def unpack_records(rec, dim: int, dtype=np.float64):
     """Step records -> (obs [..., D], reward float32 [...], done bool [...], saturated bool [...]) numpy arrays in the
     layout of the other observation kinds (raw counters).  ``rec``: uint8 array [..., rec_bytes] (numpy or torch) or an
-    array of record_dtype(dim)."""
+    array of record_dtype(dim); a uint8 array whose last axis has the size of a bit record (2D 16 / 3D 32) goes through
+    unpack_bits()."""
     if torch.is_tensor(rec):
         rec = rec.cpu().numpy()
+    if not rec.dtype.names and dim != 1 and rec.shape[-1] == bits_bytes(dim):
+        return unpack_bits(rec, dim, dtype)
     r = rec if rec.dtype.names else np.ascontiguousarray(rec).view(record_dtype(dim))[..., 0]
     win = r["win"].astype(dtype) - (0 if dim == 1 else 1)
     obs = np.concatenate([win, r["count_brick"][..., None].astype(dtype), r["count_step"][..., None].astype(dtype)], axis=-1)
@@ -143,7 +205,8 @@ class BatchedDMPEnv:
                       observation; reward / done are the finished episode's (DMP_F_RESET_OBS).  Default: False
     obs_dtype         torch.float32 (default), torch.float64 (the reference's dtype), torch.int16, or "record": packed step
                       records (window + counters + reward + done in one uint8 [N, rec_bytes] buffer: the compact
-                      host-facing kind, see record_dtype() / unpack_records())
+                      host-facing kind, see record_dtype() / unpack_records()), or "bits" (2D / 3D): the same content
+                      bit-packed into 16 B / 32 B per env (DMP_OBS_BITS; unpack_bits() / unpack_records_device())
     normalise         emit the dynamic classes' normalised counter columns (default: False = raw counters)
     env_base          global index of env 0 (multi-GPU sharding; keeps Philox streams shard-independent)
     tuning            names of kernel tuning switches (snac_b200._lib.TUNING_FLAGS: "no_pdl", "tile_ldst", "generic",
@@ -163,11 +226,14 @@ class BatchedDMPEnv:
                  plan_id_base: int = 0, tuning: Optional[Sequence[str]] = None, reset_obs: bool = False):
         if dim not in (1, 2, 3):
             raise ValueError("dim must be 1, 2 or 3")
-        self.records = isinstance(obs_dtype, str) and obs_dtype == RECORD
+        self.records = isinstance(obs_dtype, str) and obs_dtype in (RECORD, BITS)
+        self.record_kind = obs_dtype if self.records else None
         if self.records:
+            if obs_dtype == BITS and dim == 1:
+                raise ValueError('obs_dtype="bits" exists for 2D and 3D envs; the 1D step record ("record") is 16 B already')
             obs_dtype = torch.uint8
         elif obs_dtype not in (torch.float32, torch.float64, torch.int16):
-            raise ValueError('obs_dtype must be float32, float64, int16 or "record"')
+            raise ValueError('obs_dtype must be float32, float64, int16, "record" or "bits"')
         if normalise and obs_dtype in (torch.int16, torch.uint8):
             raise ValueError("normalised counters need a floating obs_dtype")
         if tuning is None:
@@ -252,7 +318,7 @@ class BatchedDMPEnv:
                 L.check(rc, "dmp_plan_static")
                 self._plans_raw = None
             # ---- output buffers (reused by step(); rollout() allocates [K,...] on demand) -----
-            D = lay.rec_bytes if self.records else lay.obs_dim
+            D = self.obs_row
             self._obs = torch.zeros((n, D), dtype=obs_dtype, device=dev)
             self._reward = torch.zeros(n, dtype=torch.float32, device=dev)
             self._done = torch.zeros(n, dtype=torch.uint8, device=dev)
@@ -290,7 +356,15 @@ class BatchedDMPEnv:
     @property
     def obs_row(self) -> int:
         """Elements of obs_dtype per env in an observation buffer: obs_dim, or the record size in bytes."""
-        return self._lay.rec_bytes if self.records else self._lay.obs_dim
+        if self.records:
+            return self._lay.bits_bytes if self.record_kind == BITS else self._lay.rec_bytes
+        return self._lay.obs_dim
+
+    def _kind_of(self, dtype) -> int:
+        """DMP_OBS_* of an observation buffer of this env with the given torch dtype."""
+        if dtype == torch.uint8:
+            return L.OBS_BITS if self.record_kind == BITS else L.OBS_REC
+        return _TORCH_OBS[dtype]
 
     @property
     def t(self) -> int:
@@ -339,7 +413,7 @@ class BatchedDMPEnv:
         self._nvtx.range_push("dmp_reset")
         with torch.cuda.device(self.device):
             L.check(L.lib.dmp_reset(C.byref(self._st), _ptr(m), _ptr(p), C.c_uint64(L.T_INIT - self._st.t),
-                                    obs.data_ptr(), _TORCH_OBS[obs.dtype], self._stream()), "dmp_reset")
+                                    obs.data_ptr(), self._kind_of(obs.dtype), self._stream()), "dmp_reset")
         self._nvtx.range_pop()
         if mask is None:
             self._needs_initial_reset = False
@@ -383,7 +457,7 @@ class BatchedDMPEnv:
         io = L.DmpIO()
         io.actions, io.step_sizes, io.next_plan = _ptr(a), _ptr(s), _ptr(p)
         io.obs, io.reward, io.done = _ptr(obs), _ptr(rew), _ptr(done)
-        io.obs_kind = _TORCH_OBS[self.obs_dtype if obs is None else obs.dtype]
+        io.obs_kind = self._kind_of(self.obs_dtype if obs is None else obs.dtype)
         io.flags = self._flags(K) | (L.F_TSLOT1 if (use_device_t and t_slot) else 0)
         self._st.t_dev = self._t_dev.data_ptr() if use_device_t else None
         self._nvtx.range_push("dmp_step" if K == 1 else "dmp_rollout")
@@ -413,7 +487,7 @@ class BatchedDMPEnv:
         io = L.DmpIO()
         io.actions, io.step_sizes, io.next_plan = _ptr(a), _ptr(s), _ptr(p)
         io.obs, io.reward, io.done = self._obs.data_ptr(), self._reward.data_ptr(), self._done.data_ptr()
-        io.obs_kind, io.flags = _TORCH_OBS[self.obs_dtype], self._flags()
+        io.obs_kind, io.flags = self._kind_of(self.obs_dtype), self._flags()
         self._st.t_dev = None
         fns = {"move": L.lib.dmp_stage_move, "deposit": L.lib.dmp_stage_deposit, "observe": L.lib.dmp_stage_observe,
                "reward": L.lib.dmp_stage_reward, "done_reset": L.lib.dmp_stage_done_reset}

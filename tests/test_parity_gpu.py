@@ -333,7 +333,7 @@ def test_3d_kernels_agree(dynamic, K):
     assert np.array_equal(torch.cat([r[2] for r in outs["d"][0]]).cpu().numpy(), r_done)
 
 
-@pytest.mark.parametrize("kind", ["c", "d1", "c1", "cr", "d1r"])
+@pytest.mark.parametrize("kind", ["c", "d1", "c1", "cr", "d1r", "cb", "d1b"])
 @pytest.mark.parametrize("dynamic", [False, True])
 def test_3d_tall_columns_match_oracle(kind, dynamic):
     """Heights around the nibble paths' threshold (13..17: an env turns "tall" at 15), around the record bytes' (252..256)
@@ -344,8 +344,10 @@ def test_3d_tall_columns_match_oracle(kind, dynamic):
     rng = np.random.RandomState(11)
     # "c": one rollout launch; "d1": step by step through the single-step kernel; "c1": step by step through the rollout
     # kernel; a trailing "r": packed step records (window bytes saturate at 255 and the record says so)
-    records = kind.endswith("r")
-    env = make_gpu(3, dynamic, n, 0, plans, auto_reset=False, seed=SEED, obs_dtype="record" if records else torch.float32,
+    # a trailing "b": bit records (window codes saturate at 15 = "height 14 or more" and the record says so)
+    records, bits = kind.endswith("r"), kind.endswith("b")
+    env = make_gpu(3, dynamic, n, 0, plans, auto_reset=False, seed=SEED,
+                   obs_dtype="record" if records else ("bits" if bits else torch.float32),
                    tuning=("rollout_k1",) if kind.startswith("c1") else ())
     ob = OracleBatch(3, dynamic, n, 0, plans)
     p0 = rng.randint(ob.n_plans, size=n).astype(np.int32) if dynamic else None
@@ -381,6 +383,15 @@ def test_3d_tall_columns_match_oracle(kind, dynamic):
         assert np.array_equal(o[..., :49], np.minimum(r_obs[..., :49], 254)) and np.array_equal(o[..., 49:], r_obs[..., 49:])
         assert (sat | (r_obs[..., :49].max(axis=-1) < 254)).all() and sat.any()
         assert np.array_equal(r, r_rew) and np.array_equal(d, r_done)
+    elif bits:
+        from snac_b200.vecenv import unpack_bits, unpack_records_device
+        o, r, d, sat = unpack_bits(obs, 3)
+        assert np.array_equal(o[..., :49], np.minimum(r_obs[..., :49], 14)) and np.array_equal(o[..., 49:], r_obs[..., 49:])
+        assert np.array_equal(sat, r_obs[..., :49].max(axis=-1) >= 14) and sat.any() and not sat.all()
+        assert np.array_equal(r, r_rew) and np.array_equal(d, r_done)
+        od, rd, dd, sd = unpack_records_device(obs, 3, "bits", torch.float64)      # the device-side expansion agrees
+        assert np.array_equal(od.cpu().numpy(), o) and np.array_equal(rd.cpu().numpy(), r)
+        assert np.array_equal(dd.cpu().numpy(), d) and np.array_equal(sd.cpu().numpy(), sat)
     else:
         assert np.array_equal(obs.cpu().numpy().astype(np.float64), r_obs)
     assert np.array_equal(rew.cpu().numpy(), r_rew)
@@ -535,6 +546,7 @@ RESET_OBS_CASES = [
     (2, False, None, False, "record", False),
     (3, False, None, False, torch.float32, False), (3, True, "dense", True, torch.float64, True),
     (3, True, "dense", False, "record", False),
+    (2, True, "dense", False, "bits", False), (3, False, None, True, "bits", False),
 ]
 
 
@@ -559,7 +571,7 @@ def test_reset_observation_mode_matches_oracle(dim, dynamic, density, ref3d, kin
     obs, rew, done = env.rollout(K1)                          # one launch, then single steps (3D: the other kernel)
     outs = [(obs, rew, done)] + [tuple(x.clone()[None] for x in env.step(None)) for _ in range(K1, K)]
     obs, rew, done = [torch.cat([o[i] for o in outs]) for i in range(3)]
-    if kind == "record":
+    if kind in ("record", "bits"):
         o, r, d, _ = unpack_records(obs, dim)
         assert np.array_equal(o, r_obs) and np.array_equal(r, r_rew) and np.array_equal(d, r_done)
     else:
