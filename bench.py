@@ -645,7 +645,7 @@ class Bench:
         out = {}
         kinds = [("record", "record", False), ("record_mapped", "record", True)]
         if dim > 1:                                          # bit records: 16 B (2D) / 32 B (3D) per env-step
-            kinds += [("bits", "bits", False), ("bits_mapped", "bits", True), ("bits_mapped_out", "bits", "out")]
+            kinds += [("bits", "bits", None), ("bits_staged", "bits", False)]
         if not args.no_e2e:
             kinds += [("f32", torch.float32, False), ("i16", torch.int16, False)]
         for name, dt, mapped in kinds:
@@ -660,9 +660,7 @@ class Bench:
                    "bits": "HostStepper.step(actions: np.uint8[N]) -> bit records: np.uint8 [N, %d] (DMP_OBS_BITS: 49 x %d-bit window code | 12-bit count_brick | 12-bit count_step | 3-bit reward code | done | saturated), a view of the pinned buffer the one D2H copy filled; snac_b200.vecenv.unpack_bits / unpack_records_device expand them to the [N, 51] rows" % (hs.d2h_bytes // n, 2 if dim == 2 else 4),
                    "f32": "HostStepper.step(actions) -> (obs f32[N,%d], reward f32[N], done bool[N]) numpy views of one pinned buffer" % env.obs_dim,
                    "i16": "HostStepper.step(actions) -> (obs i16[N,%d], reward f32[N], done bool[N])" % env.obs_dim}[name.split("_")[0]]
-            if mapped == "out":
-                api += '; mapped="out": the actions go through one staged copy, the kernel writes the records into mapped pinned host memory'
-            elif mapped:
+            if hs.mapped:
                 api += "; mapped=True: no staging copies, the kernel reads the actions from and writes the records into mapped pinned host memory"
             out[name] = {"value": v, "unit": "env-steps/s", "steps": Ke, "h2d_bytes_per_step": int(hs.h2d_bytes) * self.world,
                          "d2h_bytes_per_step": int(hs.d2h_bytes) * self.world, "api": api}
@@ -770,7 +768,7 @@ class Bench:
                            "l2": main["ring"] + " + state %.1f MB" % (n * state_bytes / 1e6),
                            "parallelism": "env-sharded x%d, NCCL all-reduce of episode stats only (%.3f ms, outside the timed region)" % (self.world, ar_ms)},
                 "clocks": main["clocks"],
-                "e2e": e2e["bits" if dim > 1 else "record"], "e2e_bits_mapped": e2e.get("bits_mapped"), "e2e_bits_mapped_out": e2e.get("bits_mapped_out"),
+                "e2e": e2e["bits" if dim > 1 else "record"], "e2e_bits_staged": e2e.get("bits_staged"),
                 "e2e_record": e2e["record"], "e2e_record_mapped": e2e.get("record_mapped"), "e2e_f32": e2e.get("f32"), "e2e_i16": e2e.get("i16"),
                 "e2e_wrapper": e2e.get("wrapper"), "e2e_wrapper_f32_philox": e2e.get("wrapper_f32_philox"),
                 "pcie": pcie,

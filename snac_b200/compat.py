@@ -75,8 +75,10 @@ class HostStepper:
     addressing), the kernel reads the actions from host memory and writes its results straight into the pinned result
     buffer -- one launch and one synchronisation per step, and the transfer overlaps the kernel.  ``mapped="out"`` maps only
     the result buffer (the actions still go through one staged copy: a kernel reading one byte per env over the link issues
-    32-byte requests).  Default: mapped for small batches (a step is then bound by call latency, not bytes), staged copies
-    otherwise.
+    32-byte requests).  Default: mapped for small batches (a step is then bound by call latency, not bytes) and for bit
+    records (16 / 32 B per env: the kernel's own writes keep the link as busy as a copy would, and nothing waits for the
+    kernel to finish first -- 1 M 2D envs: 403 us per step against 441 us staged), staged copies otherwise (56 B records and
+    wider rows: the copy engine moves them ~15 % faster than the SMs' writes do).
     """
     MAPPED_MAX_BYTES = 1 << 18       # default switch-over: results of at most 256 KB per step go through mapped memory
 
@@ -94,7 +96,10 @@ class HostStepper:
             self._off_done = self._off_rew + _align16(4 * n)
             total = self._off_done + n
         self._total = total
-        self.mapped = (total <= self.MAPPED_MAX_BYTES) if mapped is None else (mapped if mapped == "out" else bool(mapped))
+        if mapped is None:
+            from .vecenv import BITS
+            mapped = total <= self.MAPPED_MAX_BYTES or env.record_kind == BITS
+        self.mapped = mapped if mapped == "out" else bool(mapped)
         self._map_in, self._map_out = self.mapped is True, bool(self.mapped)
         self._res_pin = [torch.empty(total, dtype=torch.uint8, pin_memory=True) for _ in range(max(1, int(buffers)))]
         self._views = [self._host_views(b.numpy()) for b in self._res_pin]
@@ -803,13 +808,19 @@ class VectorizedEnvWrapper:
 
     step_size_rng  "numpy" (default): per-env step sizes are drawn as np.random.randint(1, 4, size=N), the same
                    global-RNG stream the reference consumes when it loops over N env objects (bit-exact drop-in; the
-                   draw costs ~10 ns per env on the host); "philox": the kernels' counter-based stream (throughput).
+                   draw costs ~6 ns per env on the host); "philox": the kernels' counter-based stream (throughput).
     obs_dtype      torch.float64 (default, the reference's dtype), float32 or int16: dtype of the returned observations.
+    shards         the batch is held as this many independent device shards (contiguous env ranges) that a step runs as a
+                   pipeline: while the copy engine brings shard c's results to the host, the host draws shard c+1's step
+                   sizes (in env order, so the numpy stream is consumed exactly as by one draw of N) and launches it.
+                   Default: one shard per 131 072 envs (at most 16) with numpy step sizes, else 1.  Results do not depend
+                   on the number of shards (Philox streams are keyed by the global env index).
     The arrays returned by step() are zero-copy views of pinned staging buffers (two alternate: an array stays valid until
     the step after next; copy what must live longer).  Rewards are converted to float64 on the device."""
+    PIPELINE_SHARD_ENVS = 1 << 17
 
     def __init__(self, env_: _ScalarDMP, num_envs: int = 1, obs_dtype=torch.float64, auto_reset: bool = False,
-                 step_size_rng: str = "numpy", mapped: Optional[bool] = None):
+                 step_size_rng: str = "numpy", mapped: Optional[bool] = None, shards: Optional[int] = None):
         if step_size_rng not in ("numpy", "philox"):
             raise ValueError('step_size_rng must be "numpy" or "philox"')
         self.env = env_
@@ -818,17 +829,38 @@ class VectorizedEnvWrapper:
         self._proto = env_
         self.total_step = env_.total_step
         self.step_size_rng = step_size_rng
-        self.vec = BatchedDMPEnv(env_._dim, dynamic=env_._dynamic, plan_choose=env_.plan_choose,
-                                 plans=env_._plans_arg, num_envs=num_envs, device=env_._device,
-                                 obs_dtype=obs_dtype, random_choose_paln=env_.random_choose_paln,
-                                 auto_reset=auto_reset, normalise=False)
-        n, D, dev = num_envs, self.vec.obs_dim, self.vec.device
+        n = num_envs
         esz = torch.empty(0, dtype=obs_dtype).element_size()
-        # one device result buffer [obs | reward f64 | done] mirrored by two pinned host buffers: one D2H copy per step
+        lay = L.DmpLayout()
+        L.check(L.lib.dmp_layout(env_._dim, n, C.byref(lay)), "dmp_layout")
+        D = lay.obs_dim
+        # one device result buffer [obs | reward f64 | done] mirrored by two pinned host buffers
         self._obs_bytes = n * D * esz
         self._off_rew = _align16(self._obs_bytes)
         self._off_done = self._off_rew + 8 * n
         total = self._off_done + n
+        # small batches (the reference's own --num_envs 3 / 5): no staging copies at all -- the kernel reads the actions from
+        # and writes its results into mapped pinned host memory; a step is one launch and one synchronisation
+        self.mapped = (total <= HostStepper.MAPPED_MAX_BYTES) if mapped is None else bool(mapped)
+        if shards is None:
+            shards = 1 if (step_size_rng != "numpy" or self.mapped) else min(16, n // self.PIPELINE_SHARD_ENVS)
+        self.n_shards = max(1, min(int(shards), n))
+        if self.mapped and self.n_shards != 1:
+            raise ValueError("mapped host buffers are for small batches: one shard")
+        from .sharding import shard_bounds
+        self._bounds = [shard_bounds(n, c, self.n_shards) for c in range(self.n_shards)]
+        self.vecs = []
+        for first, cnt in self._bounds:
+            plans = env_._plans_arg
+            if self.vecs and env_._dynamic:                    # one packed plan table, shared by every shard
+                plans = (self.vecs[0].plan_table(), self.vecs[0].plan_totals())
+            self.vecs.append(BatchedDMPEnv(env_._dim, dynamic=env_._dynamic, plan_choose=env_.plan_choose, plans=plans,
+                                           num_envs=cnt, device=env_._device, obs_dtype=obs_dtype, env_base=first,
+                                           random_choose_paln=env_.random_choose_paln, auto_reset=auto_reset,
+                                           normalise=False))
+        self.vec = self.vecs[0]
+        dev = self.vec.device
+        self._D, self._esz = D, esz
         self._res_dev = torch.empty(total, dtype=torch.uint8, device=dev)
         self._obs_dev = self._res_dev[:self._obs_bytes].view(obs_dtype).view(1, n, D)
         self._rew64_dev = self._res_dev[self._off_rew:self._off_done].view(torch.float64)
@@ -849,26 +881,46 @@ class VectorizedEnvWrapper:
         self._i = 0
         self.h2d_bytes = 2 * n if step_size_rng == "numpy" else n
         self.d2h_bytes = total
-        # small batches (the reference's own --num_envs 3 / 5): no staging copies at all -- the kernel reads the actions from
-        # and writes its results into mapped pinned host memory; a step is one launch and one synchronisation
-        self.mapped = (total <= HostStepper.MAPPED_MAX_BYTES) if mapped is None else bool(mapped)
+        self._dev_index = dev.index
+        from .vecenv import _TORCH_OBS
+        kind = _TORCH_OBS[obs_dtype]
+        numpy_rng = step_size_rng == "numpy"
         if self.mapped:
             self._rew32_pin = torch.empty((1, n), dtype=torch.float32, pin_memory=True)
             self._rew32_np = self._rew32_pin.numpy()[0]
             self._outs = [(b[:self._obs_bytes].view(obs_dtype).view(1, n, D), self._rew32_pin, b[self._off_done:].view(1, n))
                           for b in self._res_pin]
             # the call itself, prepared once: a step of a small batch is bound by host latency, not by bytes
-            from .vecenv import _TORCH_OBS
             self._ios = []
             for o, r, d in self._outs:
                 io = L.DmpIO()
                 io.actions = self._in_pin.data_ptr()
-                io.step_sizes = self._in_pin.data_ptr() + n if step_size_rng == "numpy" else None
+                io.step_sizes = self._in_pin.data_ptr() + n if numpy_rng else None
                 io.next_plan = None
                 io.obs, io.reward, io.done = o.data_ptr(), r.data_ptr(), d.data_ptr()
-                io.obs_kind, io.flags = _TORCH_OBS[obs_dtype], self.vec._flags(1)
+                io.obs_kind, io.flags = kind, self.vec._flags(1)
                 self._ios.append(io)
-            self._dev_index = self.vec.device.index
+        else:
+            # staged path: per shard, the prepared call on its slice of the shared buffers and the copies around it
+            self._stages = []
+            for (first, cnt), vec in zip(self._bounds, self.vecs):
+                io = L.DmpIO()
+                io.actions = self._in_dev.data_ptr() + first
+                io.step_sizes = self._in_dev.data_ptr() + n + first if numpy_rng else None
+                io.next_plan = None
+                io.obs = self._res_dev.data_ptr() + first * D * esz
+                io.reward = self._rew32_dev.data_ptr() + 4 * first
+                io.done = self._res_dev.data_ptr() + self._off_done + first
+                io.obs_kind, io.flags = kind, vec._flags(1)
+                sl = slice(first, first + cnt)
+                ob = slice(first * D * esz, (first + cnt) * D * esz)
+                rw = slice(self._off_rew + 8 * first, self._off_rew + 8 * (first + cnt))
+                dn = slice(self._off_done + first, self._off_done + first + cnt)
+                h2d = [(self._in_dev[sl], self._in_pin[sl])]
+                if numpy_rng:
+                    h2d.append((self._in_dev[n + first:n + first + cnt], self._in_pin[n + first:n + first + cnt]))
+                d2h = [[(b[ob], self._res_dev[ob]), (b[rw], self._res_dev[rw]), (b[dn], self._res_dev[dn])] for b in self._res_pin]
+                self._stages.append((vec, io, sl, h2d, (self._rew64_dev[sl], self._rew32_dev[0, sl]), d2h))
 
     def _draw_plans(self, n):
         if not self._proto._dynamic:
@@ -878,19 +930,23 @@ class VectorizedEnvWrapper:
         return None
 
     def reset(self):
-        obs = self.vec.reset(plan_idx=self._draw_plans(self.num_envs))
+        p = self._draw_plans(self.num_envs)
+        obs = [vec.reset(plan_idx=None if p is None else p[f:f + c]) for (f, c), vec in zip(self._bounds, self.vecs)]
+        obs = obs[0] if len(obs) == 1 else torch.cat(obs)
         return obs.cpu().numpy().reshape(self.num_envs, 1, -1)
 
     def reset_at(self, env_index):
         p = self._draw_plans(1)
-        m = np.zeros(self.num_envs, np.uint8)
-        m[env_index] = 1
+        c = next(i for i, (f, k) in enumerate(self._bounds) if f <= env_index < f + k)
+        vec, local = self.vecs[c], env_index - self._bounds[c][0]
+        m = np.zeros(vec.num_envs, np.uint8)
+        m[local] = 1
         pi = None
         if p is not None:
-            pi = np.zeros(self.num_envs, np.int32)
-            pi[env_index] = p[0]
-        obs = self.vec.reset(mask=m, plan_idx=pi)
-        return obs[env_index].cpu().numpy().reshape(1, -1)
+            pi = np.zeros(vec.num_envs, np.int32)
+            pi[local] = p[0]
+        obs = vec.reset(mask=m, plan_idx=pi)
+        return obs[local].cpu().numpy().reshape(1, -1)
 
     def _step_prepared(self, j):
         vec = self.vec
@@ -902,34 +958,55 @@ class VectorizedEnvWrapper:
         vec._st.t = vec._st.t + 1
         stream.synchronize()
 
-    def step(self, actions):
-        n, vec = self.num_envs, self.vec
+    def _step_staged(self, j, actions):
+        """The shard pipeline: everything is enqueued on one stream; the host only waits at the end, so drawing shard c+1's
+        step sizes overlaps shard c's kernel and device-to-host copies."""
         numpy_rng = self.step_size_rng == "numpy"
-        if numpy_rng:
-            self._in_np[n:] = np.random.randint(1, 4, size=n)
-        self._in_np[:n] = actions
-        nin = 2 * n if numpy_rng else n
+        n = self.num_envs
+        stream = torch.cuda.current_stream(self.vec.device)
+        sp = stream.cuda_stream
+        for vec, io, sl, h2d, rew, d2h in self._stages:
+            if numpy_rng:
+                self._in_np[n + sl.start:n + sl.stop] = np.random.randint(1, 4, size=sl.stop - sl.start)
+            self._in_np[sl] = actions[sl]
+            for dst, src in h2d:
+                dst.copy_(src, non_blocking=True)
+            vec._st.t_dev = None
+            rc = L.lib.dmp_rollout(C.byref(vec._st), C.byref(io), 1, sp)
+            if rc:
+                L.check(rc, "dmp_rollout")
+            vec._st.t = vec._st.t + 1
+            rew[0].copy_(rew[1])                                # float64 rewards like the reference's np.asarray(...)
+            for dst, src in d2h[j]:
+                dst.copy_(src, non_blocking=True)
+        stream.synchronize()
+
+    def step(self, actions):
+        n = self.num_envs
+        if self.vec._needs_initial_reset:
+            raise RuntimeError("call reset() before step()")
         j = self._i
-        pin, out = self._res_pin[j], self._views[j]
+        out = self._views[j]
         self._i ^= 1
         if self.mapped:
-            if vec._needs_initial_reset:
-                raise RuntimeError("call reset() before step()")
+            if self.step_size_rng == "numpy":
+                self._in_np[n:] = np.random.randint(1, 4, size=n)
+            self._in_np[:n] = actions
             if torch.cuda.current_device() == self._dev_index:
                 self._step_prepared(j)
             else:
-                with torch.cuda.device(vec.device):
+                with torch.cuda.device(self.vec.device):
                     self._step_prepared(j)
             out[1][:] = self._rew32_np                          # float64 rewards like the reference's np.asarray(...)
             return out
-        with torch.cuda.device(vec.device):
-            self._in_dev[:nin].copy_(self._in_pin[:nin], non_blocking=True)
-            vec.rollout(1, actions=self._in_dev[:n].view(1, n),
-                        step_sizes=self._in_dev[n:].view(1, n) if numpy_rng else None,
-                        out=(self._obs_dev, self._rew32_dev, self._done_dev))
-            self._rew64_dev.copy_(self._rew32_dev[0])           # float64 rewards like the reference's np.asarray(...)
-            pin.copy_(self._res_dev, non_blocking=True)
-            torch.cuda.current_stream(vec.device).synchronize()
+        actions = np.asarray(actions)
+        if actions.shape != (n,):
+            raise ValueError("actions must have shape (%d,)" % n)
+        if torch.cuda.current_device() == self._dev_index:
+            self._step_staged(j, actions)
+        else:
+            with torch.cuda.device(self.vec.device):
+                self._step_staged(j, actions)
         return out
 
 

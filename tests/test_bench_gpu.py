@@ -30,7 +30,7 @@ def test_bench_line_contract_small(workload, extra):
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert d["config"]["workload"] == workload and d["gpu_launches"] == d["gpu_launches_per_region"] * d["repeats"]
-    for k in ("e2e", "e2e_f32", "e2e_i16", "e2e_record", "e2e_record_mapped") + (() if workload.startswith("1d") else ("e2e_bits_mapped",)):
+    for k in ("e2e", "e2e_f32", "e2e_i16", "e2e_record", "e2e_record_mapped") + (() if workload.startswith("1d") else ("e2e_bits_staged",)):
         assert d[k]["value"] > 0 and d[k]["d2h_bytes_per_step"] > 0 and d[k]["h2d_bytes_per_step"] == 16384
     assert d["e2e"]["d2h_bytes_per_step"] == 16384 * {"1": 16, "2": 16, "3": 32}[workload[0]]
     assert d["e2e_record"]["d2h_bytes_per_step"] == 16384 * (16 if workload.startswith("1d") else 56)

@@ -109,6 +109,44 @@ def test_vectorized_wrapper_equals_independent_reference_style_envs():
                 env.reset_at(i)
 
 
+@pytest.mark.parametrize("dim,dynamic", [(2, False), (3, True), (1, True)])
+@pytest.mark.parametrize("mapped", [False, True], ids=["staged", "mapped"])
+def test_vectorized_wrapper_shard_pipeline_is_invisible(dim, dynamic, mapped):
+    """The staged wrapper runs a step as a pipeline over device shards (numpy step sizes drawn shard by shard while the
+    previous shard's results are copied out): same arrays, same consumption of the global numpy stream as one shard -- and
+    as the mapped small-batch path."""
+    import snac_b200 as S
+    n, T = 1003, 40
+    def proto():
+        if not dynamic:
+            return {1: S.deep_mobile_printing_1d1r, 2: S.deep_mobile_printing_2d1r, 3: S.deep_mobile_printing_3d1r}[dim](plan_choose=0)
+        cls = {1: S.deep_mobile_printing_1d1r_dynamic, 2: S.deep_mobile_printing_2d1r_dynamic, 3: S.deep_mobile_printing_3d1r_dynamic}[dim]
+        return cls(plans=load_plans(dim, "dense", "val"))
+    a = S.VectorizedEnvWrapper(proto(), num_envs=n, auto_reset=True, mapped=False, shards=4)
+    b = S.VectorizedEnvWrapper(proto(), num_envs=n, auto_reset=True, mapped=mapped, shards=1)
+    assert a.n_shards == 4 and b.n_shards == 1 and [c for _, c in a._bounds] == [251, 251, 251, 250]
+    A = a.vec.action_dim
+    rng = np.random.RandomState(3)
+    np.random.seed(21)
+    oa = a.reset()
+    sa = np.random.get_state()
+    np.random.seed(21)
+    ob_ = b.reset()
+    assert np.array_equal(oa, ob_) and np.array_equal(sa[1], np.random.get_state()[1]) and sa[2] == np.random.get_state()[2]
+    for t in range(T):
+        acts = rng.randint(A, size=n)
+        state = np.random.get_state()
+        oa, ra, da = a.step(acts)
+        after = np.random.get_state()
+        np.random.set_state(state)
+        ob_, rb, db = b.step(acts)
+        assert np.array_equal(oa, ob_) and np.array_equal(ra, rb) and np.array_equal(da, db), t
+        assert np.array_equal(after[1], np.random.get_state()[1]) and after[2] == np.random.get_state()[2]
+    assert da.any() or dim != 3                               # 3D episodes are short: auto-resets happened
+    one = a.reset_at(700)
+    assert one.shape == (1, a._D)
+
+
 def test_multiprocess_cli_config1():
     """BASELINE config 1: --env 1DStatic --plan_type 2 --num_envs 5."""
     from snac_b200.compat import main
