@@ -72,3 +72,43 @@ def test_invariants_hold_on_random_configurations(dim, n, K, seed, inject, drop_
     assert ((iou >= 0) & (iou <= 1)).all()
     assert o0.shape == (n, obs.shape[-1])
     env.check_errors()
+
+
+@settings(max_examples=int(__import__("os").environ.get("SNAC_PROPERTY_EXAMPLES", "30")), deadline=None, derandomize=__import__("os").environ.get("SNAC_PROPERTY_RANDOM", "0") != "1", suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(dim=st.sampled_from([2, 3]), n=st.integers(1, 600), K=st.integers(1, 120), seed=st.integers(0, 2**31 - 1),
+       drop_bias=st.floats(0.0, 0.95), step_mode=st.booleans(), auto_reset=st.booleans(), reset_obs=st.booleans())
+def test_bit_records_carry_what_the_float_rows_carry(dim, n, K, seed, drop_bias, step_mode, auto_reset, reset_obs):
+    """DMP_OBS_BITS on random configurations: the expansion of the bit records equals the float64 rows of a twin env fed the
+    same draws -- window cells clipped at 14 in 3D, with the saturation flag exactly on the records that were clipped -- on
+    the host and on the device; rewards, done flags and the final state agree."""
+    from snac_b200.vecenv import BatchedDMPEnv, unpack_bits, unpack_records_device
+    A = {2: 5, 3: 8}[dim]
+    kw = dict(plan_choose=seed & 1, num_envs=n, auto_reset=auto_reset, reset_obs=auto_reset and reset_obs, seed=seed)
+    a = BatchedDMPEnv(dim, obs_dtype="bits", **kw)
+    b = BatchedDMPEnv(dim, obs_dtype=torch.float64, **kw)
+    a.reset(), b.reset()
+    rng = np.random.RandomState(seed % 7919)
+    p = np.r_[np.full(4, (1 - drop_bias) / 4), np.full(A - 4, drop_bias / (A - 4))]
+    acts = torch.as_tensor(rng.choice(A, size=(K, n), p=p).astype(np.uint8), device=a.device)
+    sizes = torch.as_tensor(rng.randint(1, 4, size=(K, n)).astype(np.uint8), device=a.device)
+
+    def run(env):
+        if step_mode:
+            outs = [[x.clone() for x in env.step(acts[k], sizes[k])] for k in range(K)]
+            return [torch.stack([o[i] for o in outs]) for i in range(3)]
+        return env.rollout(K, actions=acts, step_sizes=sizes)
+    rec, ra, da = run(a)
+    obs, rb, db = run(b)
+    torch.cuda.synchronize()
+    o, r, d, sat = unpack_bits(rec, dim)
+    ref = obs.cpu().numpy()
+    clipped = np.concatenate([np.minimum(ref[..., :49], 14), ref[..., 49:]], axis=-1)
+    assert np.array_equal(o, clipped) and np.array_equal(sat, ref[..., :49].max(axis=-1) >= 14)
+    assert np.array_equal(r, rb.cpu().numpy()) and np.array_equal(d, db.cpu().numpy())
+    assert torch.equal(ra, rb) and torch.equal(da, db)
+    od, rd, dd, sd = unpack_records_device(rec, dim, "bits", torch.float64)
+    assert np.array_equal(od.cpu().numpy(), o) and np.array_equal(rd.cpu().numpy(), r)
+    assert np.array_equal(dd.cpu().numpy(), d) and np.array_equal(sd.cpu().numpy(), sat)
+    ea, eb = a.export_state(), b.export_state()
+    assert torch.equal(ea["grid"], eb["grid"]) and torch.equal(ea["scalars"], eb["scalars"])
+    a.check_errors()
