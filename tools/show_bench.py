@@ -20,7 +20,7 @@ for path in sys.argv[1:]:
     o = d.get("other_mode")
     if o:
         print("  other mode %s: %.4g  frac %.3f (layout %.3f)" % (o["mode"], o["value"], o["roofline_frac"], o["roofline_frac_this_layout"]))
-    print("  e2e: " + "  ".join("%s %.4g" % (k[4:] or "record", v["value"]) for k, v in d.items() if k.startswith("e2e") and v))
+    print("  e2e: " + "  ".join("%s %.4g" % (k[4:] or "(headline: %d B/env)" % (v["d2h_bytes_per_step"] // d["config"]["total_envs"]), v["value"]) for k, v in d.items() if k.startswith("e2e") and v))
     if d.get("pcie"):
         print("  pcie d2h: %.1f GB/s per GPU, %.1f GB/s all" % (d["pcie"]["d2h_gbs_per_gpu"], d["pcie"]["d2h_gbs_all_gpus"]))
     for k, w in (d.get("workloads") or {}).items():
