@@ -83,8 +83,9 @@ extern "C" {
                             trailer: count_brick (12 bits, saturating), count_step (12 bits, saturating), reward code (3 bits:
                                      index into {0, 1, 5, 10, -1, -100}), done (1 bit), saturated (1 bit: a counter passed
                                      4 095 or -- 3D -- a window cell holds a height >= 14; read that env's exact observation
-                                     through another kind).  Raw counters only.  DmpIO.reward / DmpIO.done are still written
-                                     when they are not NULL. */
+                                     through another kind).  Raw counters only.  DmpIO.obs must be 16 B aligned (the records
+                                     leave as 128-bit stores).  DmpIO.reward / DmpIO.done are still written when they are
+                                     not NULL. */
 #define DMP_REC_DONE       1
 #define DMP_REC_SATURATED  2   /* 3D only: the env holds a height >= 15 ("tall"); its window bytes are exact up to 253 and saturate
                                   at 255; read that env's exact observation through another obs kind / dmp_export_state */

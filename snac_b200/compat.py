@@ -75,10 +75,12 @@ class HostStepper:
     addressing), the kernel reads the actions from host memory and writes its results straight into the pinned result
     buffer -- one launch and one synchronisation per step, and the transfer overlaps the kernel.  ``mapped="out"`` maps only
     the result buffer (the actions still go through one staged copy: a kernel reading one byte per env over the link issues
-    32-byte requests).  Default: mapped for small batches (a step is then bound by call latency, not bytes) and for bit
-    records (16 / 32 B per env: the kernel's own writes keep the link as busy as a copy would, and nothing waits for the
-    kernel to finish first -- 1 M 2D envs: 403 us per step against 441 us staged), staged copies otherwise (56 B records and
-    wider rows: the copy engine moves them ~15 % faster than the SMs' writes do).
+    32-byte requests).  Default: mapped for small batches (a step is then bound by call latency, not bytes) and for 2D bit
+    records (one 128-bit store per env, 512 contiguous bytes per warp: the kernel's own writes keep the link as busy as a
+    copy would, and nothing waits for the kernel to finish first -- 1 M 2D envs: 403 us per step against 441 us staged),
+    staged copies otherwise (56 B records and wider rows: the copy engine moves them ~15 % faster than the SMs' writes do;
+    3D bit records leave as two 128-bit stores per env, half-filled sectors that the link carries badly: 262 144 envs
+    0.51 G env-steps/s mapped against 1.22 G staged).
     """
     MAPPED_MAX_BYTES = 1 << 18       # default switch-over: results of at most 256 KB per step go through mapped memory
 
@@ -98,7 +100,7 @@ class HostStepper:
         self._total = total
         if mapped is None:
             from .vecenv import BITS
-            mapped = total <= self.MAPPED_MAX_BYTES or env.record_kind == BITS
+            mapped = total <= self.MAPPED_MAX_BYTES or (env.record_kind == BITS and env.dim == 2)
         self.mapped = mapped if mapped == "out" else bool(mapped)
         self._map_in, self._map_out = self.mapped is True, bool(self.mapped)
         self._res_pin = [torch.empty(total, dtype=torch.uint8, pin_memory=True) for _ in range(max(1, int(buffers)))]

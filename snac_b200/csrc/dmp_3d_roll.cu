@@ -297,7 +297,8 @@ __global__ void __launch_bounds__(32) k3d_cache_rollout(const DmpState st, const
                 e.pr = e.pc = D2_LO; e.cb = e.cs = 0; e.ret = 0.f; e.cross = 0;
                 tall = false;
             }
-            unsigned dm = __ballot_sync(FULL, fin);
+            __syncwarp();                                       // slots are cleared by OTHER lanes: this lane's brick write and
+            unsigned dm = __ballot_sync(FULL, fin);             // window reads are ordered before them
             const unsigned dmw = __ballot_sync(FULL, fin_wide);
             while (dm) {                                        // the warp clears each finished env's map
                 const int src = __ffs(dm) - 1;

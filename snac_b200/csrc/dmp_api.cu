@@ -308,7 +308,7 @@ int dmp_reset(const DmpState* st, const uint8_t* mask, const int32_t* plan_idx, 
 int dmp_rollout(const DmpState* st, const DmpIO* io, int K, void* stream) {
     if (!state_ok(st) || !io || K < 1) return DMP_EINVAL;
     if (io->obs_kind < DMP_OBS_F32 || io->obs_kind > DMP_OBS_BITS) return DMP_EINVAL;
-    if (io->obs_kind == DMP_OBS_BITS && st->dim == 1) return DMP_EINVAL;
+    if (io->obs_kind == DMP_OBS_BITS && (st->dim == 1 || (reinterpret_cast<uintptr_t>(io->obs) & 15))) return DMP_EINVAL;
     if ((io->flags & DMP_F_NORMALISE) && io->obs_kind >= DMP_OBS_I16) return DMP_EINVAL;
     if ((io->flags & DMP_F_AUTORESET) && (!st->ep_cnt || !st->ep_len || !st->ep_ret || !st->ep_iou)) return DMP_EINVAL;
     switch (st->dim) {

@@ -10,12 +10,12 @@ O=gpurun_out/${1:-rs}; mkdir -p $O
 K="kernels_agree or tall_columns or bulk_copy_out or rollout_shapes or stage or philox or shard"
 CS="compute-sanitizer --error-exitcode 86 --print-limit 20"
 timeout 1500 $CS --tool memcheck python -m pytest tests/test_parity_gpu.py tests/test_records_gpu.py -m gpu -x -q \
-   -k "$K or record_rollout or host_stepper" > $O/memcheck_parity.log 2>&1
+   -k "$K or record_rollout or host_stepper or bit_record or device_unpack" > $O/memcheck_parity.log 2>&1
 echo "memcheck parity exit $?" | tee -a $O/memcheck_parity.log
 timeout 600 $CS --tool memcheck python __graft_entry__.py smoke > $O/memcheck_smoke.log 2>&1
 echo "memcheck smoke exit $?" | tee -a $O/memcheck_smoke.log
 timeout 1500 $CS --tool racecheck --racecheck-report all python -m pytest tests/test_parity_gpu.py tests/test_records_gpu.py -m gpu -x -q \
-   -k "bulk_copy_out or kernels_agree or rollout_shapes or tall_columns or record_rollout" > $O/racecheck_parity.log 2>&1
+   -k "bulk_copy_out or kernels_agree or rollout_shapes or tall_columns or record_rollout or bit_record" > $O/racecheck_parity.log 2>&1
 echo "racecheck parity exit $?" | tee -a $O/racecheck_parity.log
 timeout 900 $CS --tool racecheck --racecheck-report all python __graft_entry__.py smoke > $O/racecheck_smoke.log 2>&1
 echo "racecheck smoke exit $?" | tee -a $O/racecheck_smoke.log
