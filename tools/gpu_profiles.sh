@@ -21,6 +21,9 @@ cap prof_2d_step k2d_rollout 40 --workload 2d_static_dense --mode step --steps 6
 cap prof_3d_roll20 k3d_cache_rollout 4 --workload 3d_static_dense --steps 20 --warmup 40
 cap prof_3d_step k3d_step_bytes 100 --workload 3d_static_dense --mode step --steps 64 --warmup 64
 cap prof_1d_roll64 k1d_rollout 4 --workload 1d_dynamic --steps 64 --warmup 64
+# the bit-record instantiation (DMP_OBS_BITS): one 20-step launch into device buffers, tools/time_kinds.py
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:Bits16 -s 6 -c 1 -o $O/prof_2d_bits_roll20 -f \
+    python tools/time_kinds.py > $O/prof_2d_bits_roll20.log 2>&1
 traffic() {  # workload, envs, steps, kernel regex, skip, extra args
   local wl=$1 envs=$2 K=$3 k=$4 skip=$5; shift 5
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:$k -s $skip -c 1 \
