@@ -75,9 +75,10 @@ class HostStepper:
     addressing), the kernel reads the actions from host memory and writes its results straight into the pinned result
     buffer -- one launch and one synchronisation per step, and the transfer overlaps the kernel.  ``mapped="out"`` maps only
     the result buffer (the actions still go through one staged copy: a kernel reading one byte per env over the link issues
-    32-byte requests).  Default: mapped for small batches (a step is then bound by call latency, not bytes) and for 2D bit
-    records (one 128-bit store per env, 512 contiguous bytes per warp: the kernel's own writes keep the link as busy as a
-    copy would, and nothing waits for the kernel to finish first -- 1 M 2D envs: 403 us per step against 441 us staged),
+    32-byte requests).  Default: mapped for small batches (a step is then bound by call latency, not bytes) and for the 16 B
+    records -- 2D bit records, 1D step records -- (one 128-bit store per env, 512 contiguous bytes per warp: the kernel's own
+    writes keep the link as busy as a copy would, and nothing waits for the kernel to finish first -- 1 M 2D envs: 403 us per
+    step against 441 us staged; 65 536 1D envs: 46 against 56 us),
     staged copies otherwise (56 B records and wider rows: the copy engine moves them ~15 % faster than the SMs' writes do;
     3D bit records leave as two 128-bit stores per env, half-filled sectors that the link carries badly: 262 144 envs
     0.51 G env-steps/s mapped against 1.22 G staged).
@@ -99,8 +100,7 @@ class HostStepper:
             total = self._off_done + n
         self._total = total
         if mapped is None:
-            from .vecenv import BITS
-            mapped = total <= self.MAPPED_MAX_BYTES or (env.record_kind == BITS and env.dim == 2)
+            mapped = total <= self.MAPPED_MAX_BYTES or (env.records and env.obs_row == 16)     # one 128-bit store per env
         self.mapped = mapped if mapped == "out" else bool(mapped)
         self._map_in, self._map_out = self.mapped is True, bool(self.mapped)
         self._res_pin = [torch.empty(total, dtype=torch.uint8, pin_memory=True) for _ in range(max(1, int(buffers)))]
