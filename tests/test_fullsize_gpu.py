@@ -79,3 +79,35 @@ def test_full_size_rollout_equals_compiled_oracle(name, dim, dynamic, density, n
     stats = env.stats().cpu().numpy()
     assert stats[2] == cb.ep_cnt.sum() and stats[3] == cb.ep_len.sum() and stats[0] == cb.ep_ret.sum()
     env.check_errors()
+
+
+@pytest.mark.parametrize("dim,n,total_step", [(2, 1048576, 10), (3, 262144, None)], ids=["cfg3_2d_bits_host", "cfg5_3d_bits_host"])
+def test_full_size_host_steps_with_bit_records_equal_compiled_oracle(dim, n, total_step):
+    """The call bench.py's `e2e` times, at BASELINE's size: HostStepper.step(numpy actions) -> bit records in pinned host
+    memory (2D: written by the kernel itself through mapped memory), every step against the compiled oracle."""
+    import psutil
+    if psutil.virtual_memory().available < 24 * 2**30 and n > 300000:
+        pytest.skip("needs ~15 GB of host memory for the oracle's 10^6 float64 grids")
+    from snac_b200.compat import HostStepper
+    from snac_b200.vecenv import BatchedDMPEnv, unpack_bits
+    A, T = O.SPEC[dim]["actions"], 14
+    env = BatchedDMPEnv(dim, plan_choose=0, num_envs=n, auto_reset=True, seed=SEED, obs_dtype="bits", total_step=total_step)
+    cb = COracleBatch(dim, False, n, 0, None)
+    if total_step is not None:
+        cb.cfg.total_step = total_step
+    o0, _, _, _ = unpack_bits(env.reset(), dim)
+    assert np.array_equal(o0, cb.reset(None))
+    hs = HostStepper(env)
+    assert hs.mapped == (dim == 2) and hs.d2h_bytes == n * (16 if dim == 2 else 32)
+    rng = np.random.RandomState(17)
+    for t in range(T):
+        acts = rng.randint(0, A, size=n).astype(np.uint8)
+        sizes = rng.randint(1, 4, size=n).astype(np.uint8)
+        rec = hs.step(acts, sizes)
+        r_obs, r_rew, r_done, err = cb.rollout(acts[None], sizes[None], None)
+        o, r, d, sat = unpack_bits(rec, dim, np.float32)
+        assert err == 0 and not sat.any()
+        assert np.array_equal(o, r_obs[0].astype(np.float32)), t
+        assert np.array_equal(r, r_rew[0]) and np.array_equal(d, r_done[0]), t
+    assert cb.ep_cnt.sum() > 0
+    env.check_errors()
