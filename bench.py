@@ -597,7 +597,7 @@ class Bench:
         return s.cpu().numpy(), self.max_over_ranks(e0.elapsed_time(e1))
 
     # -------------------------------------------------------------------------------------------
-    def host_loop(self, step_fn, Ke, total_envs, batches=3):
+    def host_loop(self, step_fn, Ke, total_envs, batches=5):
         """Wall-clock env-steps/s of Ke synchronous host-buffer steps (median of `batches` batches, max over ranks)."""
         import torch
         for i in range(3):
@@ -851,7 +851,7 @@ def main():
                     help="in-kernel action distribution: uniform over the env's actions, or (3D) the reference's own "
                          "p = [.2, .2, .2, .2, .05, .05, .05, .05] (SURVEY.md 8(d) cfg 5)")
     ap.add_argument("--envs", type=int, default=0, help="total envs over all GPUs (default: the BASELINE config's)")
-    ap.add_argument("--e2e-steps", type=int, default=24)
+    ap.add_argument("--e2e-steps", type=int, default=48)
     ap.add_argument("--ref-envs-per-proc", type=int, default=0, help="--impl reference: env objects per host process")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="skip the short measurements of the other BASELINE configs")
