@@ -156,7 +156,8 @@ __device__ __forceinline__ uint4 observe2_bits(const uint32_t* g, const Env2& e,
     r.x = c0 | (c1 << 14) | (c2 << 28);
     r.y = (c2 >> 4) | (c3 << 10) | (c4 << 24);
     r.z = (c4 >> 8) | (c5 << 6) | (c6 << 20);
-    r.w = (c6 >> 12) | (bits_trailer(e.cb, e.cs, reward, done, false) << 2);
+    // a 2D reward is 0 or 5 (code 0 / 2): no float-to-int conversion, no select chain
+    r.w = (c6 >> 12) | (bits_trailer_code(e.cb, e.cs, reward != 0.f ? 2u : 0u, done, false) << 2);
     return r;
 }
 

@@ -183,10 +183,13 @@ __device__ __forceinline__ uint32_t bits_reward_code(float r) {
     const int v = (int)r;
     return v == 0 ? 0u : (v == 1 ? 1u : (v == 5 ? 2u : (v == 10 ? 3u : (v == -1 ? 4u : 5u))));
 }
-__device__ __forceinline__ uint32_t bits_trailer(int cb, int cs, float reward, bool done, bool saturated) {
+__device__ __forceinline__ uint32_t bits_trailer_code(int cb, int cs, uint32_t reward_code, bool done, bool saturated) {
     const bool over = (cb | cs) > 0xFFF;
-    return (uint32_t)min(cb, 0xFFF) | ((uint32_t)min(cs, 0xFFF) << 12) | (bits_reward_code(reward) << 24) |
+    return (uint32_t)min(cb, 0xFFF) | ((uint32_t)min(cs, 0xFFF) << 12) | (reward_code << 24) |
            (done ? 1u << 27 : 0u) | ((saturated || over) ? 1u << 28 : 0u);
+}
+__device__ __forceinline__ uint32_t bits_trailer(int cb, int cs, float reward, bool done, bool saturated) {
+    return bits_trailer_code(cb, cs, bits_reward_code(reward), done, saturated);
 }
 // two 7-bit values held in the two halves of x (bits 0..6 and 16..22): bit j of each half moves to bit 2j of its half
 __device__ __forceinline__ uint32_t spread2x7(uint32_t x) {
