@@ -28,7 +28,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // the real kernel's read path: ONE bulk async copy (TMA) of 128 B per lane into a shared-memory slot, completion on the warp's
 // mbarrier; MODE 0 plain, 1 evict_last, 2 evict_first hint on the copies
 template <int MODE>
-__global__ void __launch_bounds__(64) k(const uint8_t* __restrict__ maps, uint4* __restrict__ obs, int64_t n_tiles, int step, unsigned* smid_out, int what = 3, int passes = 1, size_t ring_stride = 0) {
+__global__ void __launch_bounds__(64) k(const uint8_t* __restrict__ maps, uint4* __restrict__ obs, int64_t n_tiles, int step, unsigned* smid_out, int what = 3, int passes = 1, size_t ring_stride = 0, int wmode = 0) {
     __shared__ __align__(16) uint8_t slots[2][32][144];
     __shared__ uint64_t bars[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -73,7 +73,11 @@ __global__ void __launch_bounds__(64) k(const uint8_t* __restrict__ maps, uint4*
         if (what & 2) {
 #pragma unroll
         for (int i = 0; i < 13; ++i)
-            if (i * 32 + lane < 408) st_hint(dst + i * 32, acc, pf);
+            if (i * 32 + lane < 408) {
+                if (wmode == 0) st_hint(dst + i * 32, acc, pf);
+                else if (wmode == 1) dst[i * 32] = acc;
+                else __stcs(dst + i * 32, acc);
+            }
         } else if (acc.x == 0x12345678u && acc.y == 77u) {
             dst[0] = acc;
         }
@@ -115,29 +119,42 @@ int main() {
     cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev);
     printf("L2 %d MB, max persisting set-aside %d MB\n", l2 >> 20, maxp >> 20);
     // (3) the same persistent grid looping over its tiles `passes` times inside ONE launch (what PDL-overlapped launches
-    // approach): time per pass with the launch overhead amortised
-    for (int what : {3, 1, 2})
-      for (int64_t nt : {n_tiles, n_tiles / 2, n_tiles / 4})
-        for (int hint = 0; hint < 2; ++hint) {
-            if (what == 2 && hint) continue;
-            const int G = 148 * 14, P = 32;
+    // approach): time per pass with the launch overhead amortised.  Variants: read hint (none / evict_last), write policy
+    // (evict_first hint / plain / st.cs), and the driver's own mechanism -- an access-policy window over the maps
+    // (hitProp persisting, missProp streaming) with an L2 set-aside.
+    cudaStream_t strm; CK(cudaStreamCreate(&strm));
+    for (int window_mb : {0, 60, 79})
+      for (int64_t nt : {n_tiles, n_tiles / 2})
+        for (int hint = 0; hint < 2; ++hint)
+          for (int wmode = 0; wmode < 3; ++wmode) {
+            if (window_mb && (hint || wmode == 1)) continue;
+            CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)window_mb << 20));
+            cudaStreamAttrValue av = {};
+            av.accessPolicyWindow.base_ptr = maps;
+            av.accessPolicyWindow.num_bytes = window_mb ? (size_t)nt * 32 * 208 : 0;
+            av.accessPolicyWindow.hitRatio = 1.0f;
+            av.accessPolicyWindow.hitProp = window_mb ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            CK(cudaStreamSetAttribute(strm, cudaStreamAttributeAccessPolicyWindow, &av));
+            const int G = 148 * 14, P = 32, what = 3;
             auto launch = [&]() {
-                if (hint) k<1><<<G, 64>>>(maps, obs, nt, 0, nullptr, what, P, obs_bytes / 16);
-                else k<0><<<G, 64>>>(maps, obs, nt, 0, nullptr, what, P, obs_bytes / 16);
+                if (hint) k<1><<<G, 64, 0, strm>>>(maps, obs, nt, 0, nullptr, what, P, obs_bytes / 16, wmode);
+                else k<0><<<G, 64, 0, strm>>>(maps, obs, nt, 0, nullptr, what, P, obs_bytes / 16, wmode);
             };
             launch(); launch();
-            CK(cudaDeviceSynchronize());
-            cudaEventRecord(e0);
+            CK(cudaStreamSynchronize(strm));
+            cudaEventRecord(e0, strm);
             const int R = 10;
             for (int r = 0; r < R; ++r) launch();
-            cudaEventRecord(e1);
-            CK(cudaDeviceSynchronize());
+            cudaEventRecord(e1, strm);
+            CK(cudaStreamSynchronize(strm));
             float ms; cudaEventElapsedTime(&ms, e0, e1);
-            const double req = (double)nt * 32 * ((what & 1 ? 128 : 0) + (what & 2 ? 204 : 0));
+            const double req = (double)nt * 32 * (128 + 204);
             const double us = ms * 1e3 / R / P;
-            printf("%s envs %6lld (maps %4.1f MB)  persistent x%d passes  %-10s  %6.2f us per pass  %5.0f GB/s of requested bytes\n",
-                   what == 3 ? "read+write" : (what == 1 ? "read only " : "write only"), (long long)nt * 32, nt * 32 * 208 / 1e6, P,
-                   hint ? "evict_last" : "no hint", us, req / (us * 1e-6) / 1e9);
-        }
+            printf("window %2d MB  envs %6lld (maps %4.1f MB)  reads %-10s writes %-11s %6.2f us per pass  %5.0f GB/s of requested bytes\n",
+                   window_mb, (long long)nt * 32, nt * 32 * 208 / 1e6, hint ? "evict_last" : "no hint",
+                   wmode == 0 ? "evict_first" : (wmode == 1 ? "plain" : "st.cs"), us, req / (us * 1e-6) / 1e9);
+            CK(cudaCtxResetPersistingL2Cache());
+          }
     return 0;
 }
